@@ -1,0 +1,167 @@
+/*
+ * pypairs_b200.h -- C ABI of the B200-native PyPairs hot paths.
+ *
+ * The reference (rfechtner/pypairs) is pure Python + Numba; it has no FFI.  Its
+ * de-facto operator seam is the pair of kernel entry points
+ *
+ *     check_pairs(X[N,G] f64, cats[N] i64, thr[C] i64) -> i64[G,G]
+ *         pypairs/tools/sandbag.py:126 (call site), :160-199 (body)
+ *     get_phase_scores(X[N,G] f64, iterations, min_iter, min_pairs,
+ *                      pairs[P,2] i64, used[G] bool) -> f64[N]
+ *         pypairs/tools/cyclone.py:155 (call site), :223-257 (body)
+ *
+ * Each entry point below names the reference interface it replaces.  Plain C:
+ * pointers and sizes only; no torch / C++ types cross the boundary.  One
+ * process drives one GPU (one pp_ctx = one device + its streams and scratch);
+ * multi-GPU jobs run one process per GPU and pass (shard, n_shards).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a PP_E* code otherwise; the message
+ *     is available from pp_last_error(ctx) (ctx may be NULL for create errors);
+ *   - the library never exits or aborts the process;
+ *   - `x` may be a host pointer (pageable or pinned) or a device pointer on the
+ *     ctx's device (x_is_device != 0); the caller owns every input;
+ *   - variable-length outputs are malloc'ed by the library and released with
+ *     pp_free(); fixed-size outputs are caller-allocated host buffers;
+ *   - a pp_ctx is not thread-safe; calls block until results are on the host.
+ */
+#ifndef PYPAIRS_B200_H
+#define PYPAIRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+
+/* error codes */
+#define PP_OK 0
+#define PP_EINVAL 1   /* bad argument (message says which) */
+#define PP_ECUDA 2    /* CUDA runtime error */
+#define PP_ENOMEM 3   /* host or device allocation failed */
+#define PP_ENAN 4     /* NaN in the expression matrix (undefined in the reference: fastmath, utils.py:185) */
+#define PP_ELIMIT 5   /* size beyond what the kernels support (message says which limit) */
+
+/* element type of the expression matrix */
+#define PP_F32 0
+#define PP_F64 1
+
+/* cyclone permutation source */
+#define PP_RNG_MT19937 0 /* bit-exact replay of Numba's np.random.seed(seed)+shuffle stream (cyclone.py:196-199,236) */
+#define PP_RNG_PHILOX 1  /* counter-based Philox4x32-10 table generated on the device */
+#define PP_RNG_TABLE 2   /* caller supplies the permutation table (validation mode) */
+
+typedef struct pp_ctx pp_ctx;
+
+/* Device-side timing of the last call, milliseconds (CUDA events on the ctx stream). */
+typedef struct pp_timings {
+    float h2d_ms;     /* host -> device copy of the expression matrix (0 if x_is_device) */
+    float prep_ms;    /* rank transform + layout kernels */
+    float main_ms;    /* the dominant kernel (sandbag pair kernel / cyclone score kernel) */
+    float post_ms;    /* compaction sort / table build + device -> host of results */
+    float total_ms;   /* first enqueue to results on host */
+    int32_t n_planes; /* sandbag: bit planes used for the rank encoding */
+    int32_t n_launches; /* kernels launched by this call */
+    int64_t n_units;  /* sandbag: gene pairs evaluated by this shard; cyclone: cells scored by this shard */
+} pp_timings;
+
+int pp_version(void);
+int pp_device_count(void);
+/* device < 0: use the current CUDA device. */
+int pp_ctx_create(int device, pp_ctx **out);
+void pp_ctx_destroy(pp_ctx *ctx);
+const char *pp_last_error(pp_ctx *ctx);
+void pp_free(void *p);
+int pp_get_timings(pp_ctx *ctx, pp_timings *out);
+
+/*
+ * pp_sandbag -- replaces check_pairs + the np.where scan
+ * (pypairs/tools/sandbag.py:126-129, 160-199).
+ *
+ * x            [n_rows, n_cols] matrix, row-major with leading dimension ld
+ *              (elements), rows = samples, cols = genes (as the reference's
+ *              `data`, sandbag.py:98-100).
+ * cell_rows    [n_cells] row index of every KEPT sample, class-sorted: all
+ *              samples of class 0 first, then class 1, ... (the host's
+ *              equivalent of data[sample_mask] + cats, sandbag.py:120,126).
+ * class_sizes  [n_classes] number of kept samples per class (all > 0).
+ * gene_cols    [n_genes] column index of every KEPT gene, ascending
+ *              (data[:, gene_mask], sandbag.py:126).
+ * thresholds   [n_classes] ceil(n_k * fraction) (sandbag.py:212-217).
+ * shard/n_shards  this call evaluates gene-pair tiles t with t % n_shards == shard.
+ *
+ * out_keys     *out_keys = malloc'ed uint64[n]: row * n_genes + col of every
+ *              non -1 entry of the reference's result matrix that falls in this
+ *              shard, ascending (== the reference's row-major np.where order,
+ *              sandbag.py:129).  row/col index the KEPT genes.
+ * out_class    *out_class = malloc'ed int32[n]: result[row, col].
+ * probe_pairs  optional [n_probe,2] int64 (g1 < g2, kept-gene indices): the
+ *              library writes num_pos / num_neg (sandbag.py:175-182) of those
+ *              pairs to probe_pos / probe_neg [n_probe, n_classes] int32.
+ */
+int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+               int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
+               int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
+               int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
+               const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg);
+
+/*
+ * pp_cyclone -- replaces the per-class loop over get_phase_scores
+ * (pypairs/tools/cyclone.py:151-158, 223-257) for all classes in one call.
+ *
+ * x              as above; rows = cells.  Rows [row_begin, row_begin+n_cells)
+ *                are scored (a cell shard of the job).
+ * n_classes      number of marker classes.
+ * used_idx       concatenated ascending gene-column indices of each class's
+ *                `used` mask (np.where(used[c])[0], cyclone.py:291);
+ *                used_off[n_classes+1] delimits the classes.
+ * pairs          concatenated [P_c,2] int32 pairs indexing the class's compacted
+ *                used-gene vector (cyclone.py:294-306); pair_off[n_classes+1].
+ * iterations, min_iter, min_pairs   as cyclone.py:17-26.
+ * rng_mode/seed  PP_RNG_*; seed = settings.seed (2803) for parity.
+ * perm_tables    PP_RNG_TABLE only: concatenated int32[iterations, U_c] tables,
+ *                class after class (row k = cumulative permutation after k+1
+ *                shuffles of arange(U_c)).
+ * out_scores     host f64[n_classes, n_cells] (class-major), NaN per cyclone.py:243-249.
+ * out_obs_hits/out_obs_total  optional host int32[n_classes, n_cells]: the
+ *                observed counters of get_proportion (cyclone.py:206-215).
+ */
+int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+               int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes, const int32_t *used_idx,
+               const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off, int32_t iterations,
+               int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
+               const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits,
+               int32_t *out_obs_total);
+
+/*
+ * pp_phase_scores -- single-class form with the reference kernel's exact
+ * argument meaning: get_phase_scores(matrix, iterations, min_iter, min_pairs,
+ * pairs, used) (pypairs/tools/cyclone.py:253-257).  used_mask is uint8[n_cols].
+ */
+int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows,
+                    int64_t n_cols, int64_t ld, int32_t iterations, int32_t min_iter, int32_t min_pairs,
+                    const int64_t *pairs, int64_t n_pairs, const uint8_t *used_mask, double *out_scores);
+
+/*
+ * pp_perm_table -- the permutation stream on its own (validation / export):
+ * int32[iterations, n] for class `class_index` (ignored by MT19937, whose
+ * stream depends on (seed, n) only; numba/cpython/randomimpl.py:1929-1946).
+ */
+int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t class_index, int32_t n,
+                  int32_t iterations, int32_t *out_table);
+
+/*
+ * pp_dense_rank -- the prep stage on its own (tests, profiling): per kept cell,
+ * dense rank (ties share a rank, +0.0 == -0.0) of the kept genes.
+ * out_rank: host uint16[n_cells, n_genes]; out_max_rank: max over the matrix.
+ */
+int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                  int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int32_t *gene_cols,
+                  int64_t n_genes, uint16_t *out_rank, int32_t *out_max_rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYPAIRS_B200_H */

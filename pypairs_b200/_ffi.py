@@ -1,0 +1,255 @@
+"""ctypes binding of libpypairs_b200.so (include/pypairs_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no sm_100a device is
+present, every compute entry point raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpypairs_b200.so")
+
+PP_F32, PP_F64 = 0, 1
+PP_RNG_MT19937, PP_RNG_PHILOX, PP_RNG_TABLE = 0, 1, 2
+PP_ENAN = 4
+
+SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "pp_last_error", "pp_free",
+           "pp_get_timings", "pp_sandbag", "pp_cyclone", "pp_phase_scores", "pp_perm_table", "pp_dense_rank"]
+
+
+class Timings(ctypes.Structure):
+    _fields_ = [("h2d_ms", ctypes.c_float), ("prep_ms", ctypes.c_float), ("main_ms", ctypes.c_float),
+                ("post_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("n_planes", ctypes.c_int32),
+                ("n_launches", ctypes.c_int32), ("n_units", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class PyPairsB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "pypairs_b200 error {}: {}".format(code, msg))
+        self.code = code
+
+
+_lib = None
+_ctxs = {}
+
+
+def load():
+    """dlopen the library and declare every prototype of include/pypairs_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "pypairs_b200: {} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback.".format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i64, i32, u64 = c.c_void_p, c.c_int64, c.c_int32, c.c_uint64
+    lib.pp_version.restype = c.c_int
+    lib.pp_device_count.restype = c.c_int
+    lib.pp_ctx_create.argtypes = [c.c_int, c.POINTER(vp)]
+    lib.pp_ctx_destroy.argtypes = [vp]
+    lib.pp_ctx_destroy.restype = None
+    lib.pp_last_error.argtypes = [vp]
+    lib.pp_last_error.restype = c.c_char_p
+    lib.pp_free.argtypes = [vp]
+    lib.pp_free.restype = None
+    lib.pp_get_timings.argtypes = [vp, c.POINTER(Timings)]
+    lib.pp_sandbag.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i32, vp, i64, vp, i32, i32,
+                               c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp]
+    lib.pp_cyclone.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32,
+                               i32, u64, vp, vp, vp, vp]
+    lib.pp_phase_scores.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp]
+    lib.pp_perm_table.argtypes = [vp, i32, u64, i32, i32, i32, vp]
+    lib.pp_dense_rank.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i64, vp, c.POINTER(i32)]
+    _lib = lib
+    return lib
+
+
+def _current_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except ImportError:
+        pass
+    return -1
+
+
+def ctx(device=None):
+    """One context per device per process (streams, events, memory pool)."""
+    lib = load()
+    if device is None:
+        device = _current_device()
+    if device not in _ctxs:
+        h = ctypes.c_void_p()
+        rc = lib.pp_ctx_create(device, ctypes.byref(h))
+        if rc != 0:
+            raise PyPairsB200Error(rc, lib.pp_last_error(None).decode())
+        _ctxs[device] = h
+    return _ctxs[device]
+
+
+def check(rc, h):
+    if rc != 0:
+        raise PyPairsB200Error(rc, load().pp_last_error(h).decode())
+
+
+def timings(h):
+    t = Timings()
+    check(load().pp_get_timings(h, ctypes.byref(t)), h)
+    return t.as_dict()
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def matrix_arg(x):
+    """(keepalive, pointer, dtype code, is_device, n_rows, n_cols, ld) for an ndarray or a CUDA torch tensor.
+
+    float32 stays float32 (widening to the reference's float64 is exact and order preserving);
+    every other dtype is converted to float64 exactly as `data.astype(float)` does
+    (pypairs/tools/sandbag.py:122, cyclone.py:135).
+    """
+    if type(x).__module__.startswith("torch"):
+        import torch
+        if not x.is_cuda:
+            x = x.numpy()
+        else:
+            if x.dtype not in (torch.float32, torch.float64):
+                x = x.to(torch.float64)
+            if x.dim() != 2:
+                raise ValueError("expression matrix must be 2-D")
+            if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+                x = x.contiguous()
+            code = PP_F32 if x.dtype == torch.float32 else PP_F64
+            return x, ctypes.c_void_p(x.data_ptr()), code, 1, x.shape[0], x.shape[1], x.stride(0)
+    x = np.asarray(x)
+    if x.ndim != 2:
+        raise ValueError("expression matrix must be 2-D")
+    if x.dtype != np.float32 and x.dtype != np.float64:
+        x = x.astype(np.float64)
+    item = x.dtype.itemsize
+    if not (x.shape[1] == 0 or (x.strides[1] == item and x.strides[0] % item == 0 and x.strides[0] >= x.shape[1] * item)):
+        x = np.ascontiguousarray(x)
+    ld = x.strides[0] // item if x.shape[0] > 1 else x.shape[1]
+    code = PP_F32 if x.dtype == np.float32 else PP_F64
+    return x, ctypes.c_void_p(x.ctypes.data), code, 0, x.shape[0], x.shape[1], max(ld, x.shape[1])
+
+
+def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, device=None):
+    """-> (keys uint64[n], cls int32[n], timings dict[, probe_pos, probe_neg])"""
+    lib, h = load(), ctx(device)
+    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+    cell_rows = np.ascontiguousarray(cell_rows, dtype=np.int32)
+    class_sizes = np.ascontiguousarray(class_sizes, dtype=np.int64)
+    gene_cols = np.ascontiguousarray(gene_cols, dtype=np.int32)
+    thresholds = np.ascontiguousarray(thresholds, dtype=np.int64)
+    if len(thresholds) != len(class_sizes):
+        raise ValueError("thresholds and class_sizes differ in length")
+    ok, oc, on = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+    pp = ppos = pneg = None
+    n_probe = 0
+    if probe_pairs is not None:
+        pp = np.ascontiguousarray(probe_pairs, dtype=np.int64).reshape(-1, 2)
+        n_probe = len(pp)
+        ppos = np.zeros((n_probe, len(class_sizes)), dtype=np.int32)
+        pneg = np.zeros_like(ppos)
+    rc = lib.pp_sandbag(h, px, code, is_dev, n_rows, n_cols, ld, _ptr(cell_rows), len(cell_rows), _ptr(class_sizes),
+                        len(class_sizes), _ptr(gene_cols), len(gene_cols), _ptr(thresholds), shard, n_shards,
+                        ctypes.byref(ok), ctypes.byref(oc), ctypes.byref(on), _ptr(pp), n_probe, _ptr(ppos),
+                        _ptr(pneg))
+    check(rc, h)
+    n = on.value
+    if n:
+        keys = np.ctypeslib.as_array(ctypes.cast(ok, ctypes.POINTER(ctypes.c_uint64)), shape=(n,)).copy()
+        cls = np.ctypeslib.as_array(ctypes.cast(oc, ctypes.POINTER(ctypes.c_int32)), shape=(n,)).copy()
+    else:
+        keys, cls = np.empty(0, dtype=np.uint64), np.empty(0, dtype=np.int32)
+    lib.pp_free(ok)
+    lib.pp_free(oc)
+    del keep
+    if probe_pairs is not None:
+        return keys, cls, timings(h), ppos, pneg
+    return keys, cls, timings(h)
+
+
+_RNG = {"mt19937": PP_RNG_MT19937, "philox": PP_RNG_PHILOX, "table": PP_RNG_TABLE}
+
+
+def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,
+            perm_tables=None, row_begin=0, n_cells=None, want_observed=False, device=None):
+    """-> (scores float64[C, n_cells], timings[, obs_hits, obs_total])"""
+    lib, h = load(), ctx(device)
+    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+    if n_cells is None:
+        n_cells = n_rows - row_begin
+    nc = len(used_idx_list)
+    used_off = np.zeros(nc + 1, dtype=np.int64)
+    pair_off = np.zeros(nc + 1, dtype=np.int64)
+    for c in range(nc):
+        used_off[c + 1] = used_off[c] + len(used_idx_list[c])
+        pair_off[c + 1] = pair_off[c] + len(pairs_list[c])
+    used = np.ascontiguousarray(np.concatenate([np.asarray(u, dtype=np.int32).ravel() for u in used_idx_list])
+                                if nc else np.empty(0), dtype=np.int32)
+    pairs = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32).reshape(-1, 2) for p in pairs_list])
+                                 if nc else np.empty((0, 2)), dtype=np.int32)
+    tabs = None
+    if rng == "table":
+        if perm_tables is None:
+            raise ValueError("rng='table' needs perm_tables")
+        tabs = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32).ravel() for t in perm_tables]),
+                                    dtype=np.int32)
+    scores = np.empty((nc, n_cells), dtype=np.float64)
+    oh = np.empty((nc, n_cells), dtype=np.int32) if want_observed else None
+    ot = np.empty((nc, n_cells), dtype=np.int32) if want_observed else None
+    rc = lib.pp_cyclone(h, px, code, is_dev, n_rows, n_cols, ld, row_begin, n_cells, nc, _ptr(used), _ptr(used_off),
+                        _ptr(pairs), _ptr(pair_off), iterations, min_iter, min_pairs, _RNG[rng], seed, _ptr(tabs),
+                        _ptr(scores), _ptr(oh), _ptr(ot))
+    check(rc, h)
+    del keep
+    if want_observed:
+        return scores, timings(h), oh, ot
+    return scores, timings(h)
+
+
+def phase_scores(matrix, iterations, min_iter, min_pairs, pairs, used, device=None):
+    """Reference-kernel-shaped call: get_phase_scores(matrix, iterations, min_iter, min_pairs, pairs, used)
+    (pypairs/tools/cyclone.py:253-257)."""
+    lib, h = load(), ctx(device)
+    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(matrix)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+    used = np.ascontiguousarray(used, dtype=np.uint8)
+    if len(used) != n_cols:
+        raise ValueError("used mask length differs from the number of genes")
+    out = np.empty(n_rows, dtype=np.float64)
+    check(lib.pp_phase_scores(h, px, code, is_dev, n_rows, n_cols, ld, iterations, min_iter, min_pairs, _ptr(pairs),
+                              len(pairs), _ptr(used), _ptr(out)), h)
+    del keep
+    return out
+
+
+def perm_table(rng, seed, class_index, n, iterations, device=None):
+    lib, h = load(), ctx(device)
+    out = np.empty((iterations, n), dtype=np.int32)
+    check(lib.pp_perm_table(h, _RNG[rng], seed, class_index, n, iterations, _ptr(out)), h)
+    return out
+
+
+def dense_rank(x, cell_rows, gene_cols, device=None):
+    lib, h = load(), ctx(device)
+    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+    cell_rows = np.ascontiguousarray(cell_rows, dtype=np.int32)
+    gene_cols = np.ascontiguousarray(gene_cols, dtype=np.int32)
+    out = np.empty((len(cell_rows), len(gene_cols)), dtype=np.uint16)
+    mx = ctypes.c_int32()
+    check(lib.pp_dense_rank(h, px, code, is_dev, n_rows, n_cols, ld, _ptr(cell_rows), len(cell_rows), _ptr(gene_cols),
+                            len(gene_cols), _ptr(out), ctypes.byref(mx)), h)
+    del keep
+    return out, mx.value

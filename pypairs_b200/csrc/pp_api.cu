@@ -1,0 +1,131 @@
+// pp_api.cu -- context management and the small C-ABI entry points (include/pypairs_b200.h).
+#include <stdarg.h>
+
+#include "pp_common.cuh"
+
+thread_local std::string g_pp_err;
+
+int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_pp_err = buf;
+    return code;
+}
+
+PP_API int pp_version(void) { return PP_ABI_VERSION; }
+
+PP_API int pp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+PP_API int pp_ctx_create(int device, pp_ctx **out) {
+    if (!out) return pp_fail(nullptr, PP_EINVAL, "pp_ctx_create: out is NULL");
+    *out = nullptr;
+    pp_ctx *ctx = nullptr;  // PP_CUDA reports through g_pp_err while ctx is NULL
+    int n = 0;
+    PP_CUDA(cudaGetDeviceCount(&n));
+    if (n == 0) return pp_fail(nullptr, PP_ECUDA, "pp_ctx_create: no CUDA device");
+    if (device < 0) PP_CUDA(cudaGetDevice(&device));
+    if (device >= n) return pp_fail(nullptr, PP_EINVAL, "pp_ctx_create: device %d of %d", device, n);
+    cudaDeviceProp prop;
+    PP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return pp_fail(nullptr, PP_ECUDA, "pp_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+    PP_CUDA(cudaSetDevice(device));
+    pp_ctx *c = new pp_ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) {
+        // keep freed blocks in the pool: repeated calls re-use them instead of hitting the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thresh = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+        }
+    }
+    if (e != cudaSuccess) {
+        delete c;
+        return pp_fail(nullptr, PP_ECUDA, "pp_ctx_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return PP_OK;
+}
+
+PP_API void pp_ctx_destroy(pp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+PP_API const char *pp_last_error(pp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_pp_err.c_str(); }
+
+PP_API void pp_free(void *p) { free(p); }
+
+PP_API int pp_get_timings(pp_ctx *ctx, pp_timings *out) {
+    if (!ctx || !out) return pp_fail(ctx, PP_EINVAL, "pp_get_timings: NULL argument");
+    *out = ctx->tm;
+    return PP_OK;
+}
+
+PP_API int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                         int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int32_t *gene_cols,
+                         int64_t n_genes, uint16_t *out_rank, int32_t *out_max_rank) {
+    if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
+    if (!x || !cell_rows || !gene_cols || !out_rank) return pp_fail(ctx, PP_EINVAL, "pp_dense_rank: NULL argument");
+    if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_dense_rank: bad x_dtype");
+    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols || n_cells < 0 || n_genes < 0)
+        return pp_fail(ctx, PP_EINVAL, "pp_dense_rank: bad shape");
+    for (int64_t i = 0; i < n_cells; ++i)
+        if (cell_rows[i] >= n_rows) return pp_fail(ctx, PP_EINVAL, "pp_dense_rank: cell_rows out of range");
+    for (int64_t g = 0; g < n_genes; ++g)
+        if (gene_cols[g] < 0 || gene_cols[g] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_dense_rank: gene_cols out of range");
+    if (out_max_rank) *out_max_rank = 0;
+    if (n_cells == 0 || n_genes == 0) return PP_OK;
+    PP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->launches = 0;
+    const size_t esz = x_dtype == PP_F64 ? 8 : 4;
+    DevBuf d_x, d_rows, d_cols, d_rank, d_flags;
+    const void *dx = x;
+    if (!x_is_device) {
+        PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
+        PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
+        dx = d_x.p;
+    }
+    PP_CUDA(d_rows.alloc(sizeof(int32_t) * n_cells, st));
+    PP_CUDA(cudaMemcpyAsync(d_rows.p, cell_rows, sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_cols.alloc(sizeof(int32_t) * n_genes, st));
+    PP_CUDA(cudaMemcpyAsync(d_cols.p, gene_cols, sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_rank.alloc(sizeof(uint16_t) * n_cells * n_genes, st));
+    PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
+    PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
+    int rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_cols.as<int32_t>(), n_genes,
+                            d_rank.as<uint16_t>(), n_genes, d_flags.as<int32_t>());
+    if (rc) return rc;
+    int32_t flags[4];
+    PP_CUDA(cudaMemcpyAsync(out_rank, d_rank.p, sizeof(uint16_t) * n_cells * n_genes, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_dense_rank: NaN in the expression matrix");
+    if (out_max_rank) *out_max_rank = flags[0];
+    return PP_OK;
+}

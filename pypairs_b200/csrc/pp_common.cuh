@@ -1,0 +1,132 @@
+// pp_common.cuh -- shared declarations of the pypairs_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pypairs_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pypairs_b200 is written for sm_100a (B200) only"
+#endif
+
+#define PP_API extern "C" __attribute__((visibility("default")))
+
+struct pp_ctx {
+    int device = 0;
+    int n_sm = 0;
+    int smem_optin = 0;
+    cudaStream_t stream = nullptr;   // compute stream
+    cudaStream_t copy_stream = nullptr;  // H2D prefetch stream
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    pp_timings tm = {};
+    int launches = 0;
+};
+
+extern thread_local std::string g_pp_err;  // errors raised without a ctx
+
+int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...);
+
+#define PP_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return pp_fail(ctx, PP_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,     \
+                           cudaGetErrorString(e__));                                               \
+    } while (0)
+
+#define PP_CHECK_LAUNCH()                                                                          \
+    do {                                                                                           \
+        ctx->launches++;                                                                           \
+        PP_CUDA(cudaGetLastError());                                                               \
+    } while (0)
+
+// RAII device buffer on the ctx stream (stream-ordered allocator keeps repeated calls cheap).
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    cudaError_t alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream;
+        bytes = n;
+        if (n == 0) n = 16;
+        return cudaMallocAsync(&p, n, stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lop3_gt(uint32_t a, uint32_t b, uint32_t g) {
+    // (a & ~b) | (~(a ^ b) & g) : "a > b" carried from the less significant planes
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xB2;" : "=r"(r) : "r"(a), "r"(b), "r"(g));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_lt(uint32_t a, uint32_t b, uint32_t l) {
+    // (~a & b) | (~(a ^ b) & l)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x8E;" : "=r"(r) : "r"(a), "r"(b), "r"(l));
+    return r;
+}
+#endif
+
+// ---- internal entry points (one per .cu) --------------------------------------------------------
+// Rank transform: for each slot s < n_slots (cell_rows[s] < 0 marks a padding slot: all ranks 0),
+// rank[s * rank_ld + g] = dense rank of x[cell_rows[s], gene_cols[g]] among that cell's kept genes.
+int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const int32_t *d_cell_rows,
+                   int64_t n_slots, const int32_t *d_gene_cols, int64_t n_genes, uint16_t *d_rank,
+                   int64_t rank_ld, int32_t *d_flags /* [0]=max rank (atomicMax), [1]=NaN seen */);

@@ -1,0 +1,489 @@
+// pp_cyclone.cu -- B200 permutation-null scoring (replaces get_phase_scores /
+// get_sample_score_guv / get_proportion, pypairs/tools/cyclone.py:201-257).
+//
+// What the reference does per cell and class (cyclone.py:223-249): reseed MT19937 with
+// settings.seed, score the observed marker pairs, then `iterations` times shuffle the
+// cell's used-gene vector IN PLACE (cumulatively) and re-score.  Because every cell
+// reseeds (:226), all cells of a class see the same permutation sequence, a function of
+// (seed, n_used, iterations) only.  We therefore build, once per class, the table
+//     T[k][p] = (perm_k[pair_p.0], perm_k[pair_p.1])      k = 0 (identity) .. iterations
+// and the k-th null score of ANY cell is the observed score evaluated through T[k] on the
+// un-permuted vector.  T is shared by all cells (L2 resident, 4 B per pair evaluation per
+// 64 cells), cells sit in the lanes of a warp so an index is a broadcast and a gather of
+// v[gene] is a conflict-free shared-memory row read.
+//
+// Data layout
+//   rank  u16 [n_cells][U]      per-cell dense ranks over the union of all classes' used
+//                               genes (pp_rank.cu); order and ties inside any class subset
+//                               are preserved, so every `a != b`, `a > b` is bit-exact
+//   tile  u32 smem [U][32]      one CTA = 64 cells: lane l holds cell l (low half) and cell
+//                               l + 32 (high half) of the tile
+//   T     u32 [iters+1][P_c]    union positions (lo16 | hi16) per class
+// Scores: hits_k/total_k < hits_0/total_0 is decided by exact integer cross
+// multiplication (counts < 2^16), NaN rules of get_proportion (:217-218) applied to both
+// sides; score = below / iterations as one IEEE double division (:246).
+#include <algorithm>
+#include <map>
+#include <math.h>
+
+#include "pp_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// MT19937 exactly as Numba drives it (numba/cpython/randomimpl.py:109-171, 454-521,
+// 1929-1946; numba_rnd_init = init_genrand).  Host side: the stream is strictly serial and
+// tiny (about 1.6e6 draws per class).
+// ------------------------------------------------------------------------------------------
+struct Mt {
+    uint32_t mt[624];
+    int idx;
+    void seed(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    void refill() {
+        for (int k = 0; k < 624; ++k) {
+            uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+            mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        idx = 0;
+    }
+    uint32_t next() {
+        if (idx >= 624) refill();
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+};
+
+void mt_perm_table(uint32_t seed, int n, int iters, uint16_t *out) {
+    Mt g;
+    g.seed(seed);
+    std::vector<uint16_t> a(n > 0 ? n : 1);
+    for (int i = 0; i < n; ++i) a[i] = (uint16_t)i;
+    for (int k = 0; k < iters; ++k) {
+        for (int i = n - 1; i > 0; --i) {
+            // randint(0, i+1): low bit_length(i) bits of one draw, rejected while >= i+1
+            const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+            uint32_t j;
+            do { j = g.next() & mask; } while (j > (uint32_t)i);
+            std::swap(a[i], a[j]);
+        }
+        std::copy(a.begin(), a.end(), out + (size_t)k * n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 permutation table on the device (our definition; CPU restatement in
+// oracle/pp_oracle.c:orc_perm_table_philox must match bit for bit).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1, uint32_t w[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+
+__global__ void philox_perm_kernel(uint16_t *__restrict__ table, int n, int iters, uint32_t k0, uint32_t k1,
+                                   uint32_t class_index) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= iters) return;
+    uint16_t *a = table + (size_t)k * n;
+    for (int i = 0; i < n; ++i) a[i] = (uint16_t)i;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int i = n - 1; i > 0; --i) {
+        const int d = n - 1 - i;
+        if ((d & 3) == 0) philox4x32_10((uint32_t)(d >> 2), (uint32_t)k, class_index, 0x50414952u, k0, k1, w);
+        const uint32_t j = __umulhi(w[d & 3], (uint32_t)(i + 1));
+        const uint16_t t = a[i];
+        a[i] = a[j];
+        a[j] = t;
+    }
+}
+
+// T[k][p] = (map[perm_{k-1}[p0]] | map[perm_{k-1}[p1]] << 16); k = 0 is the identity (observed)
+__global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int32_t *__restrict__ pairs,
+                                   const uint16_t *__restrict__ map, int n_used, int n_pairs, int iters,
+                                   uint32_t *__restrict__ T) {
+    const int k = blockIdx.y;
+    const uint16_t *pk = perm + (size_t)(k > 0 ? k - 1 : 0) * n_used;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
+        int i0 = pairs[2 * p], i1 = pairs[2 * p + 1];
+        if (k > 0) { i0 = pk[i0]; i1 = pk[i1]; }
+        T[(size_t)k * n_pairs + p] = (uint32_t)map[i0] | ((uint32_t)map[i1] << 16);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// score kernel
+// ------------------------------------------------------------------------------------------
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_WARPS = SCORE_THREADS / 32;
+constexpr int TILE_CELLS = 64;
+
+struct ClassDesc {
+    const uint32_t *T;  // [iters+1][n_pairs]
+    int32_t n_pairs;
+    int32_t pad;
+};
+
+struct ScoreParams {
+    const uint16_t *rank;  // [n_cells][rank_ld]
+    int64_t rank_ld;
+    int64_t n_cells;
+    int n_union;
+    int n_classes;
+    int iterations, min_iter, min_pairs;
+    const ClassDesc *classes;
+    double *scores;     // [n_classes][n_cells]
+    int32_t *obs_hits;  // [n_classes][n_cells]
+    int32_t *obs_total;
+};
+
+// counts of (a >= b) and (b >= a) for the two packed cells of a lane, over pairs [p0, p1) of T row
+__device__ __forceinline__ void eval_row(const uint32_t *__restrict__ tile, const uint32_t *__restrict__ Trow, int p0,
+                                         int p1, int lane, uint32_t &ge, uint32_t &le) {
+    ge = 0;
+    le = 0;
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int p = pb + lane;
+        const uint32_t tv = (p < p1) ? __ldg(Trow + p) : 0u;
+        const int cnt = min(32, p1 - pb);
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t t = __shfl_sync(0xffffffffu, tv, j);
+            const uint32_t a = tile[(t & 0xffffu) * 32 + lane];
+            const uint32_t b = tile[(t >> 16) * 32 + lane];
+            // ranks < 2^15: bit 15 / 31 of (x | 0x8000) - y is (x >= y), no borrow crosses halves
+            ge += (((a | 0x80008000u) - b) >> 15) & 0x00010001u;
+            le += (((b | 0x80008000u) - a) >> 15) & 0x00010001u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
+    extern __shared__ __align__(16) uint32_t tile[];  // [n_union][32]
+    __shared__ uint32_t s_ge[32], s_le[32];           // observed, packed halves
+    __shared__ uint32_t s_below[TILE_CELLS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t cell0 = (int64_t)blockIdx.x * TILE_CELLS;
+    const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
+
+    // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
+    {
+        const uint16_t *r_lo = P.rank + (c_lo < P.n_cells ? c_lo : 0) * P.rank_ld;
+        const uint16_t *r_hi = P.rank + (c_hi < P.n_cells ? c_hi : 0) * P.rank_ld;
+        for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
+            const uint32_t lo = (c_lo < P.n_cells) ? r_lo[g] : 0u;
+            const uint32_t hi = (c_hi < P.n_cells) ? r_hi[g] : 0u;
+            tile[g * 32 + lane] = lo | (hi << 16);
+        }
+    }
+
+    for (int cls = 0; cls < P.n_classes; ++cls) {
+        const ClassDesc cd = P.classes[cls];
+        const int np = cd.n_pairs;
+        if (tid < 32) s_ge[tid] = 0, s_le[tid] = 0;
+        if (tid < TILE_CELLS) s_below[tid] = 0;
+        __syncthreads();  // also orders the tile stores before the first gather
+        // ---- observed proportion: the pairs of row 0 split over the warps (<= 65535 pairs per class)
+        {
+            const int per = (np + SCORE_WARPS - 1) / SCORE_WARPS;
+            const int p0 = min(warp * per, np), p1 = min(p0 + per, np);
+            uint32_t ge, le;
+            eval_row(tile, cd.T, p0, p1, lane, ge, le);
+            atomicAdd(&s_ge[lane], ge);
+            atomicAdd(&s_le[lane], le);
+        }
+        __syncthreads();
+        const uint32_t oge = s_ge[lane], ole = s_le[lane];
+        // hits = #(a > b) = P - #(b >= a); total = #(a != b) = 2P - #(a >= b) - #(b >= a)
+        const int h0_lo = np - (int)(ole & 0xffffu), h0_hi = np - (int)(ole >> 16);
+        const int t0_lo = 2 * np - (int)(oge & 0xffffu) - (int)(ole & 0xffffu);
+        const int t0_hi = 2 * np - (int)(oge >> 16) - (int)(ole >> 16);
+        const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
+        const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
+        if (warp == 0) {
+            if (c_lo < P.n_cells) {
+                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.n_cells + c_lo] = h0_lo;
+                if (P.obs_total) P.obs_total[(int64_t)cls * P.n_cells + c_lo] = t0_lo;
+            }
+            if (c_hi < P.n_cells) {
+                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.n_cells + c_hi] = h0_hi;
+                if (P.obs_total) P.obs_total[(int64_t)cls * P.n_cells + c_hi] = t0_hi;
+            }
+        }
+        // ---- permutation null: iterations dealt round-robin to the warps
+        uint32_t below_lo = 0, below_hi = 0;
+        for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
+            uint32_t ge, le;
+            eval_row(tile, cd.T + (size_t)k * np, 0, np, lane, ge, le);
+            const int h_lo = np - (int)(le & 0xffffu), h_hi = np - (int)(le >> 16);
+            const int t_lo = 2 * np - (int)(ge & 0xffffu) - (int)(le & 0xffffu);
+            const int t_hi = 2 * np - (int)(ge >> 16) - (int)(le >> 16);
+            // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
+            if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) &&
+                (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
+                ++below_lo;
+            if (ok_hi && !(h_hi < P.min_pairs || t_hi == 0) &&
+                (long long)h_hi * t0_hi < (long long)h0_hi * t_hi)
+                ++below_hi;
+        }
+        atomicAdd(&s_below[lane], below_lo);
+        atomicAdd(&s_below[32 + lane], below_hi);
+        __syncthreads();
+        if (tid < TILE_CELLS && cell0 + tid < P.n_cells) {
+            // total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
+            double s = nan("");
+            if (P.iterations >= P.min_iter && P.iterations > 0) s = (double)s_below[tid] / (double)P.iterations;
+            P.scores[(int64_t)cls * P.n_cells + cell0 + tid] = s;
+        }
+        __syncthreads();
+    }
+}
+
+struct PermKey {
+    int mode;
+    uint64_t seed;
+    int cls;
+    int n;
+    int iters;
+    bool operator<(const PermKey &o) const {
+        if (mode != o.mode) return mode < o.mode;
+        if (seed != o.seed) return seed < o.seed;
+        if (cls != o.cls) return cls < o.cls;
+        if (n != o.n) return n < o.n;
+        return iters < o.iters;
+    }
+};
+// MT19937 tables depend on (seed, n, iters) only and cost ~10 ms of serial host time each:
+// keep the few a process ever needs.
+std::map<PermKey, std::vector<uint16_t>> g_perm_cache;
+
+const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
+    PermKey key{PP_RNG_MT19937, seed, 0, n, iters};
+    auto it = g_perm_cache.find(key);
+    if (it != g_perm_cache.end()) return it->second;
+    if (g_perm_cache.size() > 64) g_perm_cache.clear();
+    std::vector<uint16_t> &v = g_perm_cache[key];
+    v.resize((size_t)n * iters);
+    mt_perm_table(seed, n, iters, v.data());
+    return v;
+}
+
+}  // namespace
+
+PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t class_index, int32_t n,
+                         int32_t iterations, int32_t *out_table) {
+    if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
+    if (n < 0 || n > 65535 || iterations < 0 || !out_table) return pp_fail(ctx, PP_EINVAL, "pp_perm_table: bad argument");
+    const size_t cnt = (size_t)n * iterations;
+    if (cnt == 0) return PP_OK;
+    if (rng_mode == PP_RNG_MT19937) {
+        const std::vector<uint16_t> &t = mt_table_cached((uint32_t)seed, n, iterations);
+        for (size_t i = 0; i < cnt; ++i) out_table[i] = t[i];
+        return PP_OK;
+    }
+    if (rng_mode != PP_RNG_PHILOX) return pp_fail(ctx, PP_EINVAL, "pp_perm_table: rng_mode must be MT19937 or PHILOX");
+    PP_CUDA(cudaSetDevice(ctx->device));
+    DevBuf d;
+    PP_CUDA(d.alloc(cnt * 2, ctx->stream));
+    philox_perm_kernel<<<(iterations + 63) / 64, 64, 0, ctx->stream>>>(d.as<uint16_t>(), n, iterations, (uint32_t)seed,
+                                                                      (uint32_t)(seed >> 32), (uint32_t)class_index);
+    PP_CHECK_LAUNCH();
+    std::vector<uint16_t> h(cnt);
+    PP_CUDA(cudaMemcpyAsync(h.data(), d.p, cnt * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    PP_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < cnt; ++i) out_table[i] = h[i];
+    return PP_OK;
+}
+
+PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                      int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes, const int32_t *used_idx,
+                      const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off, int32_t iterations,
+                      int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
+                      const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits,
+                      int32_t *out_obs_total) {
+    if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
+    if (!x || !used_idx || !used_off || !pairs || !pair_off || !out_scores)
+        return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
+    if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: x_dtype must be PP_F32/PP_F64");
+    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad matrix shape");
+    if (row_begin < 0 || n_cells < 0 || row_begin + n_cells > n_rows) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad row range");
+    if (n_classes < 1) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: n_classes < 1");
+    if (iterations < 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: iterations < 0");
+    if (rng_mode < PP_RNG_MT19937 || rng_mode > PP_RNG_TABLE) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad rng_mode");
+    if (rng_mode == PP_RNG_TABLE && !perm_tables) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: PP_RNG_TABLE needs perm_tables");
+    ctx->tm = pp_timings();
+    ctx->launches = 0;
+    ctx->tm.n_units = n_cells;
+    if (n_cells == 0) return PP_OK;
+
+    // ---- union of used genes, per-class maps
+    std::vector<int32_t> uni;
+    for (int c = 0; c < n_classes; ++c) {
+        const int64_t u0 = used_off[c], u1 = used_off[c + 1], p0 = pair_off[c], p1 = pair_off[c + 1];
+        if (u1 < u0 || p1 < p0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: offsets must be non-decreasing");
+        if (p1 - p0 == 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: class %d has no marker pairs", c);
+        if (p1 - p0 > 32767) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 32767 marker pairs", c);
+        for (int64_t i = u0; i < u1; ++i) {
+            if (used_idx[i] < 0 || used_idx[i] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx out of range");
+            if (i > u0 && used_idx[i] <= used_idx[i - 1]) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx must ascend within a class");
+            uni.push_back(used_idx[i]);
+        }
+        for (int64_t i = 2 * p0; i < 2 * p1; ++i)
+            if (pairs[i] < 0 || pairs[i] >= u1 - u0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: pair index out of range in class %d", c);
+    }
+    std::sort(uni.begin(), uni.end());
+    uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+    const int U = (int)uni.size();
+    const size_t dyn_smem = (size_t)U * 32 * 4;
+    if (U > 32767 || dyn_smem + 1024 > (size_t)std::min(ctx->smem_optin, 227 * 1024))
+        return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: %d distinct marker genes exceed the shared-memory tile (max %d)", U,
+                       (std::min(ctx->smem_optin, 227 * 1024) - 1024) / 128);
+
+    PP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    PP_CUDA(cudaEventRecord(ctx->ev[0], st));
+    const size_t esz = x_dtype == PP_F64 ? 8 : 4;
+    DevBuf d_x, d_rows, d_uni, d_rank, d_flags, d_scores, d_oh, d_ot, d_cd;
+    const void *dx = (const uint8_t *)x + (size_t)row_begin * ld * esz;
+    if (!x_is_device) {
+        PP_CUDA(d_x.alloc((size_t)n_cells * ld * esz, st));
+        PP_CUDA(cudaMemcpyAsync(d_x.p, dx, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
+        dx = d_x.p;
+    }
+    PP_CUDA(cudaEventRecord(ctx->ev[1], st));
+    {
+        std::vector<int32_t> rows(n_cells);
+        for (int64_t i = 0; i < n_cells; ++i) rows[i] = (int32_t)i;
+        PP_CUDA(d_rows.alloc(sizeof(int32_t) * n_cells, st));
+        PP_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaStreamSynchronize(st));  // rows is a local
+    }
+    PP_CUDA(d_uni.alloc(sizeof(int32_t) * U, st));
+    PP_CUDA(cudaMemcpyAsync(d_uni.p, uni.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, st));
+    const int64_t rank_ld = (U + 7) & ~7;
+    PP_CUDA(d_rank.alloc(sizeof(uint16_t) * n_cells * rank_ld, st));
+    PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
+    PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
+    int rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_uni.as<int32_t>(), U,
+                            d_rank.as<uint16_t>(), rank_ld, d_flags.as<int32_t>());
+    if (rc) return rc;
+    PP_CUDA(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- per-class permutation + pair tables (host MT19937 work overlaps the rank kernel)
+    std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_pairs(n_classes), d_map(n_classes);
+    std::vector<ClassDesc> cds(n_classes);
+    const int32_t *ext = perm_tables;
+    for (int c = 0; c < n_classes; ++c) {
+        const int nu = (int)(used_off[c + 1] - used_off[c]);
+        const int np = (int)(pair_off[c + 1] - pair_off[c]);
+        std::vector<uint16_t> map(nu > 0 ? nu : 1);
+        for (int i = 0; i < nu; ++i)
+            map[i] = (uint16_t)(std::lower_bound(uni.begin(), uni.end(), used_idx[used_off[c] + i]) - uni.begin());
+        const size_t pcnt = (size_t)nu * iterations;
+        PP_CUDA(d_perm[c].alloc(pcnt * 2, st));
+        if (rng_mode == PP_RNG_PHILOX) {
+            if (pcnt) {
+                philox_perm_kernel<<<(iterations + 63) / 64, 64, 0, st>>>(d_perm[c].as<uint16_t>(), nu, iterations,
+                                                                         (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)c);
+                PP_CHECK_LAUNCH();
+            }
+        } else if (rng_mode == PP_RNG_MT19937) {
+            const std::vector<uint16_t> &t = mt_table_cached((uint32_t)seed, nu, iterations);
+            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, st));
+        } else {
+            std::vector<uint16_t> t(pcnt);
+            for (size_t i = 0; i < pcnt; ++i) {
+                if (ext[i] < 0 || ext[i] >= nu) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: perm_tables entry out of range (class %d)", c);
+                t[i] = (uint16_t)ext[i];
+            }
+            ext += pcnt;
+            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, st));
+            PP_CUDA(cudaStreamSynchronize(st));  // t is a local
+        }
+        PP_CUDA(d_pairs[c].alloc(sizeof(int32_t) * 2 * np, st));
+        PP_CUDA(cudaMemcpyAsync(d_pairs[c].p, pairs + 2 * pair_off[c], sizeof(int32_t) * 2 * np, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_map[c].alloc(sizeof(uint16_t) * map.size(), st));
+        PP_CUDA(cudaMemcpyAsync(d_map[c].p, map.data(), sizeof(uint16_t) * map.size(), cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaStreamSynchronize(st));  // map is a local
+        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(iterations + 1) * np, st));
+        dim3 grid((np + 255) / 256, iterations + 1);
+        build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_pairs[c].as<int32_t>(), d_map[c].as<uint16_t>(),
+                                                 nu, np, iterations, d_T[c].as<uint32_t>());
+        PP_CHECK_LAUNCH();
+        cds[c].T = d_T[c].as<uint32_t>();
+        cds[c].n_pairs = np;
+        cds[c].pad = 0;
+    }
+    PP_CUDA(d_cd.alloc(sizeof(ClassDesc) * n_classes, st));
+    PP_CUDA(cudaMemcpyAsync(d_cd.p, cds.data(), sizeof(ClassDesc) * n_classes, cudaMemcpyHostToDevice, st));
+    const size_t out_cnt = (size_t)n_classes * n_cells;
+    PP_CUDA(d_scores.alloc(sizeof(double) * out_cnt, st));
+    if (out_obs_hits) PP_CUDA(d_oh.alloc(sizeof(int32_t) * out_cnt, st));
+    if (out_obs_total) PP_CUDA(d_ot.alloc(sizeof(int32_t) * out_cnt, st));
+    PP_CUDA(cudaEventRecord(ctx->ev[3], st));
+
+    ScoreParams P;
+    P.rank = d_rank.as<uint16_t>();
+    P.rank_ld = rank_ld;
+    P.n_cells = n_cells;
+    P.n_union = U;
+    P.n_classes = n_classes;
+    P.iterations = iterations;
+    P.min_iter = min_iter;
+    P.min_pairs = min_pairs;
+    P.classes = d_cd.as<ClassDesc>();
+    P.scores = d_scores.as<double>();
+    P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
+    P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
+    PP_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    score_kernel<<<(unsigned)((n_cells + TILE_CELLS - 1) / TILE_CELLS), SCORE_THREADS, dyn_smem, st>>>(P);
+    PP_CHECK_LAUNCH();
+    PP_CUDA(cudaEventRecord(ctx->ev[4], st));
+    PP_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, sizeof(double) * out_cnt, cudaMemcpyDeviceToHost, st));
+    if (out_obs_hits) PP_CUDA(cudaMemcpyAsync(out_obs_hits, d_oh.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));
+    if (out_obs_total) PP_CUDA(cudaMemcpyAsync(out_obs_total, d_ot.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));
+    int32_t flags[4];
+    PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaEventRecord(ctx->ev[5], st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_cyclone: NaN in the expression matrix");
+    cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->tm.prep_ms, ctx->ev[1], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->tm.main_ms, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->tm.post_ms, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[5]);
+    ctx->tm.n_launches = ctx->launches;
+    return PP_OK;
+}
+
+PP_API int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows,
+                           int64_t n_cols, int64_t ld, int32_t iterations, int32_t min_iter, int32_t min_pairs,
+                           const int64_t *pairs, int64_t n_pairs, const uint8_t *used_mask, double *out_scores) {
+    if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
+    if (!pairs || !used_mask) return pp_fail(ctx, PP_EINVAL, "pp_phase_scores: NULL argument");
+    std::vector<int32_t> used;
+    for (int64_t g = 0; g < n_cols; ++g)
+        if (used_mask[g]) used.push_back((int32_t)g);
+    std::vector<int32_t> p32((size_t)2 * n_pairs);
+    for (int64_t i = 0; i < 2 * n_pairs; ++i) {
+        if (pairs[i] < 0 || pairs[i] >= (int64_t)used.size()) return pp_fail(ctx, PP_EINVAL, "pp_phase_scores: pair index out of range");
+        p32[i] = (int32_t)pairs[i];
+    }
+    const int64_t uoff[2] = {0, (int64_t)used.size()}, poff[2] = {0, n_pairs};
+    return pp_cyclone(ctx, x, x_dtype, x_is_device, n_rows, n_cols, ld, 0, n_rows, 1, used.data(), uoff, p32.data(), poff,
+                      iterations, min_iter, min_pairs, PP_RNG_MT19937, 2803, nullptr, out_scores, nullptr, nullptr);
+}

@@ -1,0 +1,223 @@
+// pp_rank.cu -- per-cell dense-rank transform (prep stage of both hot paths).
+//
+// Both reference kernels only ever compare two genes *within one cell*
+// (sandbag.py:179-182 `raw_data[g1,i] > raw_data[g2,i]`; cyclone.py:212-215
+// `a != b`, `a > b`).  Replacing each cell's values by their dense rank among
+// that cell's kept genes (ties share a rank, +0.0 == -0.0 as in IEEE `==`) keeps
+// every such comparison bit-exact while shrinking an element from a float64 to
+// <= 16 bits -- which is what lets the sandbag kernel run bit-sliced and the
+// cyclone kernel keep a cell tile in shared memory.
+//
+// One CTA per cell, persistent over cells.  Per cell:
+//   1. gather x[row, gene_cols[g]] -> order-preserving unsigned keys (+ u16 gene index)
+//   2. LSD radix sort, 8-bit digits, only over the key bytes that actually vary in this
+//      cell (count data stored as doubles varies in 2-3 bytes; float32 input in <= 4)
+//   3. head flags + scan -> dense rank, scattered back to gene order as u16
+// Keys live in a per-CTA global scratch (L2 resident: 32768 genes * 10 B * 2 buffers).
+#include <stdarg.h>
+
+#include "pp_common.cuh"
+
+namespace {
+
+constexpr int RANK_THREADS = 512;
+constexpr int RANK_WARPS = RANK_THREADS / 32;
+
+__device__ __forceinline__ uint32_t key_of(float v, bool &nan) {
+    v = v + 0.0f;  // -0.0 -> +0.0 so that the two zeros tie (IEEE ==)
+    nan = nan || (v != v);
+    uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t key_of(double v, bool &nan) {
+    v = v + 0.0;
+    nan = nan || (v != v);
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> { typedef uint32_t type; };
+template <> struct KeyOf<double> { typedef uint64_t type; };
+
+struct RankSmem {
+    uint32_t whist[RANK_WARPS][256];  // per-warp digit histogram -> running scatter offsets
+    uint32_t dig_total[256];
+    uint32_t wtot[RANK_WARPS];
+    unsigned long long vary[RANK_WARPS];
+    unsigned long long vary_all;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(RANK_THREADS)
+rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cell_rows, int64_t n_slots,
+            const int32_t *__restrict__ gene_cols, int n, uint16_t *__restrict__ rank_out, int64_t rank_ld,
+            uint8_t *__restrict__ scratch, size_t scratch_per_cta, int32_t *__restrict__ flags) {
+    typedef typename KeyOf<T>::type K;
+    __shared__ RankSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp-contiguous element ranges (multiples of 32 so every step is a full, aligned warp step)
+    const int per_warp = ((n + RANK_WARPS * 32 - 1) / (RANK_WARPS * 32)) * 32;
+    const int lo = min(warp * per_warp, n), hi = min(lo + per_warp, n);
+
+    uint8_t *my = scratch + (size_t)blockIdx.x * scratch_per_cta;
+    const size_t n_al = ((size_t)n + 15) & ~(size_t)15;
+    K *keyA = reinterpret_cast<K *>(my);
+    K *keyB = keyA + n_al;
+    uint16_t *idxA = reinterpret_cast<uint16_t *>(keyB + n_al);
+    uint16_t *idxB = idxA + n_al;
+
+    for (int64_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        uint16_t *out = rank_out + slot * rank_ld;
+        const int row = cell_rows[slot];
+        if (row < 0) {  // padding cell: ties in every gene
+            for (int g = tid; g < n; g += RANK_THREADS) out[g] = 0;
+            continue;
+        }
+        const T *xr = x + (int64_t)row * ld;
+        // ---- 1. gather + key transform, find the key bits that vary
+        bool nan = false;
+        K first = key_of(xr[gene_cols[0]], nan);
+        K vary = 0;
+        for (int g = tid; g < n; g += RANK_THREADS) {
+            K k = key_of(xr[gene_cols[g]], nan);
+            keyA[g] = k;
+            idxA[g] = (uint16_t)g;
+            vary |= (k ^ first);
+        }
+        if (nan) flags[1] = 1;
+        unsigned long long v64 = (unsigned long long)vary;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v64 |= __shfl_xor_sync(0xffffffffu, v64, o);
+        if (lane == 0) sm.vary[warp] = v64;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long a = 0;
+            for (int w = 0; w < RANK_WARPS; ++w) a |= sm.vary[w];
+            sm.vary_all = a;
+        }
+        __syncthreads();
+        const unsigned long long vary_all = sm.vary_all;
+
+        K *kin = keyA, *kout = keyB;
+        uint16_t *iin = idxA, *iout = idxB;
+        // ---- 2. LSD radix passes over varying bytes only
+        for (int byte = 0; byte < (int)sizeof(K); ++byte) {
+            if (((vary_all >> (8 * byte)) & 0xffull) == 0) continue;
+            const int shift = 8 * byte;
+            for (int i = tid; i < RANK_WARPS * 256; i += RANK_THREADS) (&sm.whist[0][0])[i] = 0;
+            __syncthreads();
+            for (int ib = lo; ib < hi; ib += 32) {
+                const int i = ib + lane;
+                const bool valid = i < hi;
+                uint32_t d = valid ? ((uint32_t)(kin[i] >> shift) & 255u) : (256u + lane);
+                uint32_t peers = __match_any_sync(0xffffffffu, d);
+                if (valid && lane == __ffs(peers) - 1) sm.whist[warp][d] += __popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();
+            // exclusive scan: digit-major, warp-minor
+            if (tid < 256) {
+                uint32_t s = 0;
+                for (int w = 0; w < RANK_WARPS; ++w) s += sm.whist[w][tid];
+                sm.dig_total[tid] = s;
+            }
+            __syncthreads();
+            if (warp == 0) {  // scan 256 totals with one warp, 8 per lane
+                uint32_t v[8], s = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] = sm.dig_total[lane * 8 + j]; s += v[j]; }
+                uint32_t incl = s;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                uint32_t run = incl - s;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { sm.dig_total[lane * 8 + j] = run; run += v[j]; }
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t run = sm.dig_total[tid];
+                for (int w = 0; w < RANK_WARPS; ++w) {
+                    uint32_t c = sm.whist[w][tid];
+                    sm.whist[w][tid] = run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            // stable scatter
+            for (int ib = lo; ib < hi; ib += 32) {
+                const int i = ib + lane;
+                const bool valid = i < hi;
+                K k = valid ? kin[i] : (K)0;
+                uint16_t ix = valid ? iin[i] : (uint16_t)0;
+                uint32_t d = valid ? ((uint32_t)(k >> shift) & 255u) : (256u + lane);
+                uint32_t peers = __match_any_sync(0xffffffffu, d);
+                uint32_t base = valid ? sm.whist[warp][d] : 0u;
+                uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+                if (valid) {
+                    kout[pos] = k;
+                    iout[pos] = ix;
+                }
+                __syncwarp();
+                if (valid && lane == __ffs(peers) - 1) sm.whist[warp][d] = base + __popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();  // scratch writes visible CTA-wide before the next pass reads them
+            K *tk = kin; kin = kout; kout = tk;
+            uint16_t *ti = iin; iin = iout; iout = ti;
+        }
+        // ---- 3. dense rank = number of distinct keys strictly below
+        uint32_t cnt = 0;
+        for (int ib = lo; ib < hi; ib += 32) {
+            const int i = ib + lane;
+            bool head = (i < hi) && (i > 0) && (kin[i] != kin[i - 1]);
+            cnt += __popc(__ballot_sync(0xffffffffu, head));
+        }
+        if (lane == 0) sm.wtot[warp] = cnt;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; ++w) base += sm.wtot[w];
+        for (int ib = lo; ib < hi; ib += 32) {
+            const int i = ib + lane;
+            bool head = (i < hi) && (i > 0) && (kin[i] != kin[i - 1]);
+            uint32_t b = __ballot_sync(0xffffffffu, head);
+            uint32_t r = base + __popc(b & (0xffffffffu >> (31 - lane)));
+            if (i < hi) out[iin[i]] = (uint16_t)r;
+            base += __popc(b);
+        }
+        if (warp == RANK_WARPS - 1 && lane == 0) {
+            uint32_t total = 0;
+            for (int w = 0; w < RANK_WARPS; ++w) total += sm.wtot[w];
+            atomicMax(&flags[0], (int)total);
+        }
+        __syncthreads();  // smem + scratch reused by the next cell
+    }
+}
+
+}  // namespace
+
+int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const int32_t *d_cell_rows,
+                   int64_t n_slots, const int32_t *d_gene_cols, int64_t n_genes, uint16_t *d_rank,
+                   int64_t rank_ld, int32_t *d_flags) {
+    if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "more than 65535 kept genes per cell (%lld)", (long long)n_genes);
+    if (n_slots == 0 || n_genes == 0) return PP_OK;
+    const size_t ksz = (x_dtype == PP_F64) ? 8 : 4;
+    const size_t n_al = ((size_t)n_genes + 15) & ~(size_t)15;
+    const size_t per_cta = 2 * n_al * ksz + 2 * n_al * 2;
+    int grid = (int)((n_slots < (int64_t)ctx->n_sm * 3) ? n_slots : (int64_t)ctx->n_sm * 3);
+    DevBuf scratch;
+    PP_CUDA(scratch.alloc(per_cta * (size_t)grid, ctx->stream));
+    if (x_dtype == PP_F64)
+        rank_kernel<double><<<grid, RANK_THREADS, 0, ctx->stream>>>(
+            (const double *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
+            scratch.as<uint8_t>(), per_cta, d_flags);
+    else
+        rank_kernel<float><<<grid, RANK_THREADS, 0, ctx->stream>>>(
+            (const float *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
+            scratch.as<uint8_t>(), per_cta, d_flags);
+    PP_CHECK_LAUNCH();
+    return PP_OK;
+}

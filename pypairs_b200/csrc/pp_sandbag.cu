@@ -1,0 +1,631 @@
+// pp_sandbag.cu -- B200 all-gene-pairs marker kernel (replaces check_pairs,
+// pypairs/tools/sandbag.py:160-199, and the np.where scan at :129).
+//
+// Data layout in HBM
+//   rank   u16 [32*W][G]     per-cell dense ranks, cells class-sorted, every class padded
+//                            to a multiple of 32 cells with all-tie cells (pp_rank.cu)
+//   planes u32 [NB][W][B][64] bit-sliced ranks: gene block nb (64 genes), cell word w (32
+//                            cells of ONE class), plane p (bit p of the rank); bit c of the
+//                            word belongs to cell 32*w + c.  A (gene block, run of words) is
+//                            one contiguous byte range -> one 1-D TMA bulk copy.
+// Pair kernel (pair_kernel): CTA tile = 128 a-genes x 64 b-genes, every thread owns an
+// 8x4 register tile of gene pairs and walks all cell words.  For one word the two
+// predicates of sandbag.py:179-182 are evaluated for 32 cells at once with the
+// LSB->MSB recurrences
+//        gt' = (a & ~b) | (~(a ^ b) & gt)        lt' = (~a & b) | (~(a ^ b) & lt)
+// -- one LOP3 per plane per predicate -- and accumulated per class with POPC.  Ties set
+// neither bit, padding cells tie everywhere, exactly the reference's "add to neither".
+// Thresholds (sandbag.py:184-190) are applied in-register at every class boundary and the
+// if/elif decision (:192-197) at the end; survivors are compacted with warp-aggregated
+// atomics and radix-sorted into the row-major order np.where would produce.
+#include <algorithm>
+
+#include "pp_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// bit-slice: rank[32W][G] -> planes[NB][W][B][64]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes, int n_words, int n_planes,
+                uint32_t *__restrict__ planes) {
+    const int w = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int g = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 32 + lane;  // this lane's gene
+    if (g - lane >= n_genes) return;
+    uint32_t r[32];
+    const uint16_t *src = rank + (int64_t)w * 32 * rank_ld + g;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) r[c] = (g < n_genes) ? (uint32_t)src[(int64_t)c * rank_ld] : 0u;
+    uint32_t *dst = planes + (((int64_t)(g >> 6) * n_words + w) * n_planes) * 64 + (g & 63);
+    for (int p = 0; p < n_planes; ++p) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) word |= ((r[c] >> p) & 1u) << c;
+        dst[(int64_t)p * 64] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pair kernel
+// ------------------------------------------------------------------------------------------
+constexpr int TI = 8, TJ = 4;          // per-thread pair tile
+constexpr int NTI = 16, NTJ = 16;      // thread grid
+constexpr int PAIR_THREADS = NTI * NTJ;  // 256
+constexpr int TILE_A = TI * NTI;       // 128 genes = 2 gene blocks
+constexpr int TILE_B = TJ * NTJ;       // 64 genes  = 1 gene block
+constexpr int STAGES = 3;
+static_assert(TILE_A == 128 && TILE_B == 64, "tile geometry is tied to the 64-gene block layout");
+
+struct Chunk {  // a run of cell words of one class
+    int32_t w_begin;
+    int32_t n_words;
+    int32_t class_end;  // class index if this chunk closes the class, else -1
+    int32_t pad;
+};
+
+struct PairParams {
+    const uint32_t *planes;
+    const Chunk *chunks;
+    const int2 *tiles;       // (ta, tb) per CTA
+    const int32_t *thr;      // per class, clipped to int32
+    unsigned long long *out; // compacted (key << 8 | class)
+    unsigned long long *out_count;
+    unsigned long long out_cap;
+    int n_genes, n_words, n_planes, n_chunks, n_classes, wc_max;
+};
+
+__global__ void __launch_bounds__(PAIR_THREADS, 1) pair_kernel(const PairParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ int32_t thr_s[256];
+
+    const int tid = threadIdx.x;
+    const int ti = tid / NTJ, tj = tid % NTJ;
+    const int2 tile = P.tiles[blockIdx.x];
+    const int B = P.n_planes;
+    const int blk_words = P.wc_max * B * 64;              // u32 per gene block per stage
+    const uint32_t stage_words = 3u * blk_words;
+    uint32_t *smem = reinterpret_cast<uint32_t *>(smem_raw);
+
+    for (int i = tid; i < P.n_classes; i += PAIR_THREADS) thr_s[i] = P.thr[i];
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int64_t blk_stride = (int64_t)P.n_words * B * 64;  // u32 per gene block in HBM
+    const uint32_t *gA0 = P.planes + (int64_t)(2 * tile.x) * blk_stride;
+    const uint32_t *gA1 = gA0 + blk_stride;
+    const uint32_t *gB = P.planes + (int64_t)tile.y * blk_stride;
+
+    auto issue = [&](int c) {  // thread 0 only
+        const Chunk ch = P.chunks[c];
+        const int s = c % STAGES;
+        uint32_t *dst = smem + (size_t)s * stage_words;
+        const uint32_t bytes = (uint32_t)ch.n_words * B * 64 * 4;
+        const int64_t off = (int64_t)ch.w_begin * B * 64;
+        mbar_arrive_expect_tx(&full_bar[s], 3 * bytes);
+        bulk_g2s(dst, gA0 + off, bytes, &full_bar[s]);
+        bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
+        bulk_g2s(dst + 2 * blk_words, gB + off, bytes, &full_bar[s]);
+    };
+    if (tid == 0)
+        for (int c = 0; c < STAGES - 1 && c < P.n_chunks; ++c) issue(c);
+
+    uint32_t acc[TI][TJ], st[TI][TJ];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j] = 0, st[i][j] = 0;
+
+    const int la = ti * TI;  // first local a-gene (0..127), never straddles a 64-gene block
+    const uint32_t a_off = (uint32_t)(la >> 6) * blk_words + (la & 63);
+    const uint32_t b_off = 2u * blk_words + tj * TJ;
+
+    for (int c = 0; c < P.n_chunks; ++c) {
+        __syncthreads();  // every thread is done with chunk c-1 -> its stage may be refilled
+        if (tid == 0 && c + STAGES - 1 < P.n_chunks) issue(c + STAGES - 1);
+        const int s = c % STAGES;
+        mbar_wait(&full_bar[s], (uint32_t)(c / STAGES) & 1u);
+        const Chunk ch = P.chunks[c];
+        const uint32_t *sa = smem + (size_t)s * stage_words + a_off;
+        const uint32_t *sb = smem + (size_t)s * stage_words + b_off;
+        for (int w = 0; w < ch.n_words; ++w) {
+            uint32_t gt[TI][TJ], lt[TI][TJ];
+            {
+                uint32_t a[TI], b[TJ];
+                const uint4 a0 = *reinterpret_cast<const uint4 *>(sa);
+                const uint4 a1 = *reinterpret_cast<const uint4 *>(sa + 4);
+                const uint4 b0 = *reinterpret_cast<const uint4 *>(sb);
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+                a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+                for (int i = 0; i < TI; ++i)
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) {
+                        gt[i][j] = a[i] & ~b[j];
+                        lt[i][j] = ~a[i] & b[j];
+                    }
+            }
+#pragma unroll 2
+            for (int p = 1; p < B; ++p) {
+                uint32_t a[TI], b[TJ];
+                const uint4 a0 = *reinterpret_cast<const uint4 *>(sa + p * 64);
+                const uint4 a1 = *reinterpret_cast<const uint4 *>(sa + p * 64 + 4);
+                const uint4 b0 = *reinterpret_cast<const uint4 *>(sb + p * 64);
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+                a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+                for (int i = 0; i < TI; ++i)
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) {
+                        gt[i][j] = lop3_gt(a[i], b[j], gt[i][j]);
+                        lt[i][j] = lop3_lt(a[i], b[j], lt[i][j]);
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j)
+                    acc[i][j] += ((uint32_t)__popc(lt[i][j]) << 16) + (uint32_t)__popc(gt[i][j]);
+            sa += B * 64;
+            sb += B * 64;
+        }
+        if (ch.class_end >= 0) {  // CTA-uniform: thresholds of sandbag.py:184-190 for this class
+            const uint32_t k = (uint32_t)ch.class_end;
+            const int32_t thr = thr_s[k];
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) {
+                    const int32_t pos = (int32_t)(acc[i][j] & 0xffffu), neg = (int32_t)(acc[i][j] >> 16);
+                    uint32_t s2 = st[i][j];
+                    if (pos >= thr) s2 = ((s2 & 0xff00ffffu) | (k << 16)) + 1u;
+                    if (neg >= thr) s2 = ((s2 & 0x00ffffffu) | (k << 24)) + 0x100u;
+                    st[i][j] = s2;
+                    acc[i][j] = 0;
+                }
+        }
+    }
+
+    // decision of sandbag.py:192-197 + warp-aggregated compaction
+    const int ga0 = tile.x * TILE_A + la, gb0 = tile.y * TILE_B + tj * TJ;
+    const uint32_t C = (uint32_t)P.n_classes;
+    const int lane = tid & 31;
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            const int ga = ga0 + i, gb = gb0 + j;
+            const uint32_t s2 = st[i][j];
+            const uint32_t nup = s2 & 0xffu, ndn = (s2 >> 8) & 0xffu;
+            unsigned long long key = 0;
+            bool emit = false;
+            if (ga < gb && gb < P.n_genes) {
+                if (nup == 1u) {
+                    if (ndn == C - 1u) {
+                        emit = true;
+                        key = (((unsigned long long)ga * P.n_genes + gb) << 8) | ((s2 >> 16) & 0xffu);
+                    }
+                } else if (ndn == 1u) {
+                    if (nup == C - 1u) {
+                        emit = true;
+                        key = (((unsigned long long)gb * P.n_genes + ga) << 8) | ((s2 >> 24) & 0xffu);
+                    }
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, emit);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(P.out_count, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+                if (emit && pos < P.out_cap) P.out[pos] = key;
+            }
+        }
+}
+
+// per-class counters of selected pairs straight from the planes (one warp per probe pair)
+__global__ void probe_kernel(const uint32_t *__restrict__ planes, const Chunk *__restrict__ chunks, int n_chunks,
+                             int n_words, int n_planes, int n_classes, const int64_t *__restrict__ pairs,
+                             int64_t n_probe, int32_t *__restrict__ pos_out, int32_t *__restrict__ neg_out) {
+    const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= n_probe) return;
+    const int g1 = (int)pairs[2 * q], g2 = (int)pairs[2 * q + 1];
+    const int64_t bs = (int64_t)n_words * n_planes * 64;
+    const uint32_t *pa = planes + (int64_t)(g1 >> 6) * bs + (g1 & 63);
+    const uint32_t *pb = planes + (int64_t)(g2 >> 6) * bs + (g2 & 63);
+    int pos = 0, neg = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const Chunk ch = chunks[c];
+        for (int w = ch.w_begin + lane; w < ch.w_begin + ch.n_words; w += 32) {
+            uint32_t gt = 0, lt = 0;
+            for (int p = 0; p < n_planes; ++p) {
+                const uint32_t a = pa[((int64_t)w * n_planes + p) * 64], b = pb[((int64_t)w * n_planes + p) * 64];
+                gt = lop3_gt(a, b, gt);
+                lt = lop3_lt(a, b, lt);
+            }
+            pos += __popc(gt);
+            neg += __popc(lt);
+        }
+        if (ch.class_end >= 0) {
+            for (int o = 16; o > 0; o >>= 1) {
+                pos += __shfl_xor_sync(0xffffffffu, pos, o);
+                neg += __shfl_xor_sync(0xffffffffu, neg, o);
+            }
+            if (lane == 0) {
+                pos_out[q * n_classes + ch.class_end] = pos;
+                neg_out[q * n_classes + ch.class_end] = neg;
+            }
+            pos = neg = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LSD radix sort of the compacted u64 keys (8-bit digits, 3 kernels per pass)
+// ------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;                        // per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 8192 keys per CTA
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist_kernel(const unsigned long long *__restrict__ in, int64_t n, int shift, uint32_t *__restrict__ hist,
+                 int n_blocks) {
+    __shared__ uint32_t h[256];
+    for (int i = threadIdx.x; i < 256; i += SORT_THREADS) h[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const int64_t i = base + it * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(in[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += SORT_THREADS) hist[(int64_t)i * n_blocks + blockIdx.x] = h[i];
+}
+
+// exclusive scan of hist[256 * n_blocks] in place (single CTA)
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *__restrict__ hist, int64_t total) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < total; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = (i < total) ? hist[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = wsum[lane], inc2 = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += t;
+            }
+            wsum[lane] = inc2 - s;
+        }
+        __syncthreads();
+        const uint32_t c = carry;
+        if (i < total) hist[i] = c + wsum[warp] + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = c + wsum[31] + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out, int64_t n,
+                    int shift, const uint32_t *__restrict__ hist, int n_blocks) {
+    __shared__ uint32_t whist[SORT_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    // warp-contiguous ranges keep the scatter stable
+    const int64_t lo = (int64_t)blockIdx.x * SORT_TILE + (int64_t)warp * (SORT_TILE / SORT_WARPS);
+    const int64_t hi = min(lo + SORT_TILE / SORT_WARPS, n);
+    for (int64_t ib = lo; ib < hi; ib += 32) {
+        const int64_t i = ib + lane;
+        const bool valid = i < hi;
+        const uint32_t d = valid ? ((uint32_t)(in[i] >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == __ffs(peers) - 1) whist[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid < 256) {
+        uint32_t run = hist[(int64_t)tid * n_blocks + blockIdx.x];
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t c = whist[w][tid];
+            whist[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int64_t ib = lo; ib < hi; ib += 32) {
+        const int64_t i = ib + lane;
+        const bool valid = i < hi;
+        const unsigned long long k = valid ? in[i] : 0ull;
+        const uint32_t d = valid ? ((uint32_t)(k >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t base = valid ? whist[warp][d] : 0u;
+        if (valid) out[base + __popc(peers & ((1u << lane) - 1u))] = k;
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) whist[warp][d] = base + __popc(peers);
+        __syncwarp();
+    }
+}
+
+int radix_sort_u64(pp_ctx *ctx, unsigned long long *d_a, unsigned long long *d_b, int64_t n, int lo_bit,
+                   int hi_bit, unsigned long long **sorted) {
+    *sorted = d_a;
+    if (n <= 1) return PP_OK;
+    const int n_blocks = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    DevBuf hist;
+    PP_CUDA(hist.alloc(sizeof(uint32_t) * 256 * (size_t)n_blocks, ctx->stream));
+    unsigned long long *in = d_a, *out = d_b;
+    for (int shift = lo_bit; shift < hi_bit; shift += 8) {
+        sort_hist_kernel<<<n_blocks, SORT_THREADS, 0, ctx->stream>>>(in, n, shift, hist.as<uint32_t>(), n_blocks);
+        PP_CHECK_LAUNCH();
+        sort_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist.as<uint32_t>(), (int64_t)256 * n_blocks);
+        PP_CHECK_LAUNCH();
+        sort_scatter_kernel<<<n_blocks, SORT_THREADS, 0, ctx->stream>>>(in, out, n, shift, hist.as<uint32_t>(),
+                                                                         n_blocks);
+        PP_CHECK_LAUNCH();
+        std::swap(in, out);
+    }
+    *sorted = in;
+    return PP_OK;
+}
+
+int bit_length64(uint64_t v) {
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+}  // namespace
+
+PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                      int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
+                      int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
+                      int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
+                      const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg) {
+    if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
+    if (!x || !cell_rows || !class_sizes || !gene_cols || !thresholds || !out_keys || !out_class || !out_n)
+        return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
+    if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: x_dtype must be PP_F32/PP_F64");
+    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad matrix shape");
+    if (n_classes < 1) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: n_classes < 1");
+    if (n_classes > 254) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 254 classes (%d)", n_classes);
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad shard %d/%d", shard, n_shards);
+    if (n_genes < 0 || n_cells < 0) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: negative size");
+    *out_keys = nullptr;
+    *out_class = nullptr;
+    *out_n = 0;
+    ctx->tm = pp_timings();
+    ctx->launches = 0;
+    int64_t total = 0;
+    for (int k = 0; k < n_classes; ++k) {
+        if (class_sizes[k] <= 0) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: class %d is empty", k);
+        if (class_sizes[k] > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: class %d has more than 65535 cells", k);
+        total += class_sizes[k];
+    }
+    if (total != n_cells) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: class_sizes do not sum to n_cells");
+    for (int64_t i = 0; i < n_cells; ++i)
+        if (cell_rows[i] < 0 || cell_rows[i] >= n_rows) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: cell_rows[%lld] out of range", (long long)i);
+    for (int64_t g = 0; g < n_genes; ++g)
+        if (gene_cols[g] < 0 || gene_cols[g] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: gene_cols[%lld] out of range", (long long)g);
+    if (n_genes < 2 || n_cells == 0) return PP_OK;  // no pairs
+    if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65535 kept genes");
+
+    PP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    PP_CUDA(cudaEventRecord(ctx->ev[0], st));
+
+    // ---- host-side layout tables: padded slots, chunks, tiles
+    std::vector<int32_t> slots;
+    std::vector<int32_t> class_w0(n_classes + 1, 0);
+    {
+        int64_t src = 0;
+        for (int k = 0; k < n_classes; ++k) {
+            const int64_t nk = class_sizes[k], wk = (nk + 31) / 32;
+            class_w0[k + 1] = class_w0[k] + (int32_t)wk;
+            for (int64_t i = 0; i < wk * 32; ++i) slots.push_back(i < nk ? cell_rows[src + i] : -1);
+            src += nk;
+        }
+    }
+    const int W = class_w0[n_classes];
+    const int64_t n_slots = (int64_t)W * 32;
+    const int NB = (int)((n_genes + 63) / 64);
+    const int NB_alloc = (NB + 1) & ~1;
+
+    // ---- device buffers
+    DevBuf d_x, d_slots, d_gene, d_rank, d_flags, d_planes, d_chunks, d_tiles, d_thr, d_out, d_out2, d_cnt;
+    const size_t esz = x_dtype == PP_F64 ? 8 : 4;
+    const void *dx = x;
+    if (!x_is_device) {
+        PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
+        PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
+        dx = d_x.p;
+    }
+    PP_CUDA(cudaEventRecord(ctx->ev[1], st));
+    PP_CUDA(d_slots.alloc(sizeof(int32_t) * n_slots, st));
+    PP_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_gene.alloc(sizeof(int32_t) * n_genes, st));
+    PP_CUDA(cudaMemcpyAsync(d_gene.p, gene_cols, sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_rank.alloc(sizeof(uint16_t) * n_slots * n_genes, st));
+    PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
+    PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
+
+    int rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
+                            d_rank.as<uint16_t>(), n_genes, d_flags.as<int32_t>());
+    if (rc) return rc;
+    int32_t flags[4];
+    PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    d_x.release();
+    if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
+    const int B = std::max(1, bit_length64((uint64_t)flags[0]));
+    ctx->tm.n_planes = B;
+
+    // ---- bit-slice
+    const size_t plane_words = (size_t)NB_alloc * W * B * 64;
+    PP_CUDA(d_planes.alloc(plane_words * 4, st));
+    PP_CUDA(cudaMemsetAsync(d_planes.p, 0, plane_words * 4, st));
+    {
+        dim3 grid(W, (unsigned)((n_genes + 255) / 256));
+        bitslice_kernel<<<grid, 256, 0, st>>>(d_rank.as<uint16_t>(), n_genes, (int)n_genes, W, B, d_planes.as<uint32_t>());
+        PP_CHECK_LAUNCH();
+    }
+    PP_CUDA(cudaEventRecord(ctx->ev[2], st));
+
+    // ---- chunks (runs of <= wc_max words inside one class)
+    const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 2048;
+    int wc_max = smem_budget / (STAGES * 3 * B * 64 * 4);
+    wc_max = std::max(1, std::min(wc_max, 8));
+    const size_t dyn_smem = (size_t)STAGES * 3 * wc_max * B * 64 * 4;
+    std::vector<Chunk> chunks;
+    for (int k = 0; k < n_classes; ++k)
+        for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc_max) {
+            Chunk c;
+            c.w_begin = w;
+            c.n_words = std::min(wc_max, class_w0[k + 1] - w);
+            c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
+            c.pad = 0;
+            chunks.push_back(c);
+        }
+    // ---- tiles of this shard: (ta, tb) with tb >= 2*ta (only those contain pairs g1 < g2)
+    const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB;
+    std::vector<int2> tiles;
+    int64_t t_index = 0, n_pairs_shard = 0;
+    for (int ta = 0; ta < TA; ++ta)
+        for (int tb = 2 * ta; tb < TB; ++tb, ++t_index) {
+            if (t_index % n_shards != shard) continue;
+            tiles.push_back(make_int2(ta, tb));
+            const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
+            const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
+            for (int64_t a = a0; a < a1; ++a) n_pairs_shard += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+        }
+    ctx->tm.n_units = n_pairs_shard;
+    std::vector<int32_t> thr32(n_classes);
+    for (int k = 0; k < n_classes; ++k)
+        thr32[k] = (int32_t)std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, thresholds[k]));
+
+    PP_CUDA(d_chunks.alloc(sizeof(Chunk) * chunks.size(), st));
+    PP_CUDA(cudaMemcpyAsync(d_chunks.p, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_tiles.alloc(sizeof(int2) * tiles.size(), st));
+    PP_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_thr.alloc(sizeof(int32_t) * n_classes, st));
+    PP_CUDA(cudaMemcpyAsync(d_thr.p, thr32.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_cnt.alloc(sizeof(unsigned long long), st));
+
+    unsigned long long cap = (unsigned long long)std::min<int64_t>(std::max<int64_t>(n_pairs_shard, 1),
+                                                                     std::max<int64_t>(1 << 22, n_pairs_shard / 16));
+    unsigned long long count = 0;
+    PP_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        PP_CUDA(d_out.alloc(sizeof(unsigned long long) * cap, st));
+        PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
+        if (!tiles.empty()) {
+            PairParams P;
+            P.planes = d_planes.as<uint32_t>();
+            P.chunks = d_chunks.as<Chunk>();
+            P.tiles = d_tiles.as<int2>();
+            P.thr = d_thr.as<int32_t>();
+            P.out = d_out.as<unsigned long long>();
+            P.out_count = d_cnt.as<unsigned long long>();
+            P.out_cap = cap;
+            P.n_genes = (int)n_genes;
+            P.n_words = W;
+            P.n_planes = B;
+            P.n_chunks = (int)chunks.size();
+            P.n_classes = n_classes;
+            P.wc_max = wc_max;
+            pair_kernel<<<(unsigned)tiles.size(), PAIR_THREADS, dyn_smem, st>>>(P);
+            PP_CHECK_LAUNCH();
+        }
+        PP_CUDA(cudaEventRecord(ctx->ev[3], st));
+        PP_CUDA(cudaMemcpyAsync(&count, d_cnt.p, sizeof(count), cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+        if (count <= cap) break;
+        if (attempt == 1) return pp_fail(ctx, PP_ECUDA, "pp_sandbag: compaction buffer overflow after resize");
+        cap = count;  // exact size known now; evaluate once more
+    }
+
+    // ---- optional probe counters
+    if (n_probe > 0 && probe_pairs && probe_pos && probe_neg) {
+        for (int64_t q = 0; q < n_probe; ++q)
+            if (probe_pairs[2 * q] < 0 || probe_pairs[2 * q + 1] >= n_genes || probe_pairs[2 * q] >= probe_pairs[2 * q + 1])
+                return pp_fail(ctx, PP_EINVAL, "pp_sandbag: probe pair %lld must satisfy 0 <= g1 < g2 < n_genes", (long long)q);
+        DevBuf d_pp, d_pos, d_neg;
+        const size_t cb = sizeof(int32_t) * n_probe * n_classes;
+        PP_CUDA(d_pp.alloc(sizeof(int64_t) * 2 * n_probe, st));
+        PP_CUDA(d_pos.alloc(cb, st));
+        PP_CUDA(d_neg.alloc(cb, st));
+        PP_CUDA(cudaMemcpyAsync(d_pp.p, probe_pairs, sizeof(int64_t) * 2 * n_probe, cudaMemcpyHostToDevice, st));
+        probe_kernel<<<(unsigned)((n_probe + 3) / 4), 128, 0, st>>>(d_planes.as<uint32_t>(), d_chunks.as<Chunk>(),
+                                                                   (int)chunks.size(), W, B, n_classes,
+                                                                   d_pp.as<int64_t>(), n_probe, d_pos.as<int32_t>(),
+                                                                   d_neg.as<int32_t>());
+        PP_CHECK_LAUNCH();
+        PP_CUDA(cudaMemcpyAsync(probe_pos, d_pos.p, cb, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaMemcpyAsync(probe_neg, d_neg.p, cb, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // ---- sort into np.where order and return
+    uint64_t *hk = nullptr;
+    int32_t *hc = nullptr;
+    if (count > 0) {
+        PP_CUDA(d_out2.alloc(sizeof(unsigned long long) * count, st));
+        unsigned long long *sorted = nullptr;
+        const int hi_bit = 8 + bit_length64((uint64_t)n_genes * (uint64_t)n_genes);
+        rc = radix_sort_u64(ctx, d_out.as<unsigned long long>(), d_out2.as<unsigned long long>(), (int64_t)count, 8,
+                            hi_bit, &sorted);
+        if (rc) return rc;
+        hk = (uint64_t *)malloc(sizeof(uint64_t) * count);
+        hc = (int32_t *)malloc(sizeof(int32_t) * count);
+        if (!hk || !hc) {
+            free(hk);
+            free(hc);
+            return pp_fail(ctx, PP_ENOMEM, "pp_sandbag: host allocation of %llu markers failed", count);
+        }
+        cudaError_t e = cudaMemcpyAsync(hk, sorted, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            free(hk);
+            free(hc);
+            return pp_fail(ctx, PP_ECUDA, "pp_sandbag: result copy failed: %s", cudaGetErrorString(e));
+        }
+        for (unsigned long long i = 0; i < count; ++i) {
+            hc[i] = (int32_t)(hk[i] & 0xffu);
+            hk[i] >>= 8;
+        }
+    }
+    PP_CUDA(cudaEventRecord(ctx->ev[4], st));
+    PP_CUDA(cudaEventSynchronize(ctx->ev[4]));
+    cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->tm.prep_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->tm.main_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->tm.post_ms, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[4]);
+    ctx->tm.n_launches = ctx->launches;
+    *out_keys = hk;
+    *out_class = hc;
+    *out_n = (int64_t)count;
+    return PP_OK;
+}

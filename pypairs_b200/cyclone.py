@@ -1,0 +1,122 @@
+"""pairs.cyclone -- permutation-null scoring; host side of pypairs/tools/cyclone.py:17-194.
+
+The host translates marker gene names to indices (filter_marker_pairs, cyclone.py:273-311) and
+builds the result DataFrame (cyclone.py:169-191); scoring of every cell against every class
+(get_phase_scores, cyclone.py:223-257) runs in the CUDA library behind pp_cyclone().
+"""
+import numpy as np
+from pandas import DataFrame
+
+from . import _dist, _ffi, datasets, log as logg, settings, utils
+
+
+def filter_marker_pairs(marker_pairs, gene_names):
+    """Per class (dict order): ascending used gene columns and the pairs re-indexed into that
+    compacted vector, keeping input order and duplicates, dropping pairs with an unknown gene;
+    with duplicated gene names the last column wins (cyclone.py:273-311).
+
+    Returns (pairs: dict class -> int32[P, 2], used: dict class -> bool[G]).
+    """
+    name_to_idx = {g: i for i, g in enumerate(gene_names)}
+    n = len(gene_names)
+    out_pairs, out_used = {}, {}
+    removed = 0
+    for cat, pairs in marker_pairs.items():
+        ia = np.fromiter((name_to_idx.get(p[0], -1) for p in pairs), dtype=np.int64, count=len(pairs))
+        ib = np.fromiter((name_to_idx.get(p[1], -1) for p in pairs), dtype=np.int64, count=len(pairs))
+        ok = (ia >= 0) & (ib >= 0)
+        removed += int((~ok).sum())
+        ia, ib = ia[ok], ib[ok]
+        used = np.zeros(n, dtype=bool)
+        used[ia] = True
+        used[ib] = True
+        new_idx = np.cumsum(used) - 1
+        out_pairs[cat] = np.stack([new_idx[ia], new_idx[ib]], axis=1).astype(np.int32).reshape(-1, 2)
+        out_used[cat] = used
+    logg.hint("translated marker pairs, {} removed".format(removed))
+    return out_pairs, out_used
+
+
+def scores_to_frame(scores, keys, sample_names):
+    """DataFrame epilogue of cyclone.py:169-181 with positional semantics.
+
+    max_class = first class with the largest score, 'N/A' unless the row sum is > 0;
+    cc_prediction (only for exactly {G1, S, G2M}) = 'S' if max(G1, G2M) < 0.5 else argmax(G1, G2M).
+    """
+    keys = list(keys)
+    df = DataFrame({k: scores[i] for i, k in enumerate(keys)}, columns=keys)
+    df.index = sample_names
+    vals = np.asarray(scores, dtype=np.float64).T.reshape(len(sample_names), len(keys))
+    allnan = np.all(np.isnan(vals), axis=1)
+    safe = np.where(np.isnan(vals), -np.inf, vals)
+    arg = np.argmax(safe, axis=1)  # first maximum, NaN skipped (DataFrame.idxmax)
+    row_sum = np.nansum(vals, axis=1)  # DataFrame.sum skips NaN
+    names = np.array(keys, dtype=object)
+    df["max_class"] = np.where(row_sum > 0, names[arg], "N/A").tolist() if len(keys) else []
+    if len(keys) == 3 and all(e in keys for e in ["G1", "S", "G2M"]):
+        sub = safe[:, [keys.index("G1"), keys.index("G2M")]]
+        sub_nan = np.all(np.isneginf(sub), axis=1)
+        mx = np.where(sub_nan, np.nan, sub.max(axis=1))
+        pick = np.array(["G1", "G2M"], dtype=object)[np.argmax(sub, axis=1)]
+        pred = np.where(mx < 0.5, "S", pick).astype(object)
+        pred[sub_nan] = np.nan  # NaN < 0.5 is False and idxmax of an all-NaN row is NaN
+        df["cc_prediction"] = pred.tolist()
+    del allnan
+    return df
+
+
+def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterations=1000, min_iter=100,
+            min_pairs=50, quantile_transform=False):
+    """Score each sample for each category of marker pairs.
+
+    Same signature, defaults and return value as pypairs.pairs.cyclone
+    (pypairs/tools/cyclone.py:17-26): a DataFrame indexed by sample with one score column per
+    category plus 'max_class' and, for the categories {G1, S, G2M}, 'cc_prediction'; for AnnData
+    input the columns are also written to ``data.obs['pypairs_<column>']``.
+
+    `settings.rng` selects the permutation stream ('mt19937' = bit-exact with the reference,
+    'philox' = device-generated).  Under torch.distributed the cells are sharded over the ranks
+    and every rank returns the complete frame.
+    """
+    logg.info("predicting category scores with cyclone", r=True)
+    if marker_pairs is None:
+        logg.hint("no marker pairs passed, using default cell cycle prediction marker")
+        marker_pairs = datasets.default_cc_marker()
+    raw, gene_names, sample_names = utils.parse_data(data, gene_names, sample_names)
+    pairs, used = filter_marker_pairs(marker_pairs, gene_names)
+    total = sum(len(p) for p in pairs.values())
+    for k, p in pairs.items():
+        if len(p) == 0:
+            logg.error("no genes present for marker pairs for category {}".format(k))
+    if total == 0:  # the reference logs and calls exit(1) here (cyclone.py:122-124)
+        logg.error("no genes present in marker pairs. aborting.")
+        raise SystemExit(1)
+    empty = [k for k, p in pairs.items() if len(p) == 0]
+    if empty:  # the reference's gufunc rejects the empty pair array of such a class
+        raise ValueError("no genes present for marker pairs for category {}".format(empty[0]))
+    logg.hint("received {} marker pairs".format(total))
+    if quantile_transform:
+        from sklearn.preprocessing import QuantileTransformer
+        raw = QuantileTransformer().fit_transform(np.asarray(raw, dtype=np.float64))
+
+    keys = list(pairs.keys())
+    rank, ws = _dist.world()
+    begin, end = _dist.cell_shard(raw.shape[0], rank, ws)
+    rng = settings.rng if settings.fix_seed else "philox"
+    seed = settings.seed if settings.fix_seed else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
+    if ws > 1 and not settings.fix_seed:  # all shards must share one stream
+        seed = int(_dist.allgather_varlen((np.array([seed], dtype=np.uint64),))[0][0])
+    local, tm = _ffi.cyclone(raw, [np.where(used[k])[0] for k in keys], [pairs[k] for k in keys], iterations, min_iter,
+                             min_pairs, rng=rng, seed=seed, row_begin=begin, n_cells=end - begin)
+    scores = _dist.allgather_columns(local, raw.shape[0]) if ws > 1 else local
+    df = scores_to_frame(scores, keys, sample_names)
+    if utils.is_anndata(data):
+        logg.hint('adding scores with key "pypairs_{category}" to `data.obs`"')
+        for name in df.columns:
+            data.obs["pypairs_{}".format(name)] = df[name].values
+    logg.info("finished", time_=True)
+    cyclone.last_timings = tm
+    return df
+
+
+cyclone.last_timings = None

@@ -1,0 +1,98 @@
+"""pairs.sandbag -- marker-pair discovery; host side of pypairs/tools/sandbag.py:15-157.
+
+The host only does mask / index arithmetic (gene and sample filtering, class sorting of cells,
+thresholds); the all-gene-pairs evaluation (check_pairs, sandbag.py:160-199) and the scan of the
+result matrix (:129) run in the CUDA library behind pp_sandbag().
+"""
+from math import ceil
+
+import numpy as np
+
+from . import _dist, _ffi, log as logg, utils
+
+
+def calc_thresholds(class_sizes, fraction):
+    """ceil(n_k * fraction) with the reference's float arithmetic (sandbag.py:212-217)."""
+    return np.array([ceil(int(n) * fraction) for n in class_sizes], dtype=np.int64)
+
+
+def prepare(data, annotation=None, gene_names=None, sample_names=None, fraction=0.65, filter_genes=None,
+            filter_samples=None):
+    """Everything sandbag.py:98-122 derives before calling the kernel, as index arrays.
+
+    Returns a dict with: raw (matrix as given), kept gene names, class names (non-empty, in order),
+    gene_cols (kept gene columns, ascending), cell_rows (kept samples, class-sorted),
+    class_sizes, thresholds.
+    """
+    raw, gene_names, sample_names, class_names, cats = utils.parse_data_and_annotation(
+        data, annotation, gene_names, sample_names)
+    gene_mask, sample_mask = utils.get_filter_masks(raw, gene_names, sample_names, cats, filter_genes, filter_samples)
+    kept_gene_names = np.array(gene_names)[gene_mask]
+    cats = cats[:, sample_mask]
+    rows_kept = np.where(sample_mask)[0]
+    # remove_empty_categories (sandbag.py:202-209)
+    nonempty = cats.sum(axis=1) > 0
+    cats = cats[nonempty]
+    class_names = np.array(class_names)[nonempty]
+    if cats.shape[0] == 0:
+        raise ValueError("no samples left in any category after filtering")
+    # the reference builds `cats` with np.where(categories.T)[1] (sandbag.py:120); a sample that sits
+    # in two classes silently misaligns that vector with the data rows -- refuse instead
+    if np.any(cats.sum(axis=0) != 1):
+        raise ValueError("every kept sample must belong to exactly one category")
+    class_sizes = cats.sum(axis=1).astype(np.int64)
+    thresholds = calc_thresholds(class_sizes, fraction)
+    cell_rows = np.concatenate([rows_kept[cats[k]] for k in range(cats.shape[0])]).astype(np.int32)
+    return {"raw": raw, "gene_names": kept_gene_names, "class_names": class_names,
+            "gene_cols": np.where(gene_mask)[0].astype(np.int32), "cell_rows": cell_rows,
+            "class_sizes": class_sizes, "thresholds": thresholds}
+
+
+def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
+    """Ascending keys == row-major np.where order (sandbag.py:129-140): dict key order is the order
+    of first appearance, tuples are (gene_names[row], gene_names[col]) as numpy strings."""
+    if len(keys) == 0:
+        return {}
+    rows = (keys // np.uint64(n_genes)).astype(np.int64)
+    cols = (keys % np.uint64(n_genes)).astype(np.int64)
+    a, b = gene_names[rows], gene_names[cols]
+    _, first = np.unique(cls, return_index=True)
+    out = {}
+    for k in cls[np.sort(first)]:
+        m = cls == k
+        out[class_names[k]] = list(zip(a[m], b[m]))
+    return out
+
+
+def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=0.65, filter_genes=None,
+            filter_samples=None):
+    """Calculate the pairs of genes serving as marker pairs for each category.
+
+    Same signature, defaults and return value as pypairs.pairs.sandbag
+    (pypairs/tools/sandbag.py:15-23): a dict mapping each category that has markers to a list of
+    (gene_high, gene_low) tuples in the reference's order.  `data` may be an AnnData (classes from
+    ``obs['category']`` unless `annotation` is given), a DataFrame, an ndarray / scipy-sparse matrix
+    with `gene_names` and `sample_names`, or a CUDA torch tensor.
+
+    Under torch.distributed (one process per GPU) the gene-pair tiles are sharded over the ranks
+    and every rank returns the complete dict.
+    """
+    logg.info("identifying marker pairs with sandbag", r=True)
+    logg.hint("sandbag running with fraction of {}".format(fraction))
+    p = prepare(data, annotation, gene_names, sample_names, fraction, filter_genes, filter_samples)
+    rank, ws = _dist.world()
+    keys, cls, tm = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
+                                 shard=rank, n_shards=ws)
+    if ws > 1:
+        keys, cls = _dist.allgather_varlen((keys, cls))
+        order = np.argsort(keys, kind="stable")
+        keys, cls = keys[order], cls[order]
+    out = markers_to_dict(keys, cls, len(p["gene_cols"]), p["gene_names"], p["class_names"])
+    logg.info("finished", time_=True)
+    logg.hint("found {} marker pairs ({})".format(len(keys), ", ".join(
+        "{}: {}".format(k, len(v)) for k, v in out.items())))
+    sandbag.last_timings = tm
+    return out
+
+
+sandbag.last_timings = None

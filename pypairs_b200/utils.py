@@ -1,0 +1,155 @@
+"""Host-side input normalisation with the semantics of pypairs/utils.py:207-385.
+
+Everything here is cheap index / mask logic; the expression matrix itself is never copied
+or filtered on the host -- the kernels gather the kept rows / columns on the device.
+"""
+import json
+
+import numpy as np
+from pandas import DataFrame
+from scipy.sparse import issparse
+
+try:  # anndata is optional; AnnData inputs are also recognised structurally
+    from anndata import AnnData as _AnnData
+except ImportError:  # pragma: no cover
+    _AnnData = None
+
+
+def is_anndata(data):
+    if _AnnData is not None and isinstance(data, _AnnData):
+        return True
+    return all(hasattr(data, a) for a in ("X", "obs", "obs_names", "var_names"))
+
+
+def is_cuda_tensor(data):
+    return type(data).__module__.startswith("torch") and getattr(data, "is_cuda", False)
+
+
+def _dense(x):
+    return x.toarray() if issparse(x) else x
+
+
+def parse_data(data, gene_names=None, sample_names=None):
+    """-> (raw_data [samples, genes], gene_names, sample_names); pypairs/utils.py:264-308.
+
+    Besides the reference's AnnData / DataFrame / ndarray / scipy-sparse inputs a CUDA torch
+    tensor is accepted (names required), so that matrices larger than host memory can be scored.
+    """
+    if is_anndata(data):
+        if sample_names is None:
+            sample_names = list(data.obs_names)
+        if gene_names is None:
+            gene_names = list(data.var_names)
+        raw = _dense(data.X)
+    elif isinstance(data, DataFrame):
+        if gene_names is None:
+            gene_names = list(data.columns)
+        if sample_names is None:
+            sample_names = list(data.index)
+        raw = _dense(data.values)
+    elif isinstance(data, np.ndarray) or issparse(data) or is_cuda_tensor(data):
+        if gene_names is None or sample_names is None:
+            raise ValueError("Provide gene names and sample names in ``gene_names`` and ``sample_names``")
+        raw = _dense(data)
+    else:
+        raise ValueError("data can only be of type AnnData, DataFrame or ndarray")
+    if len(raw.shape) != 2:
+        raise ValueError("data must be 2-dimensional (samples x genes)")
+    if raw.shape[0] != len(sample_names) or raw.shape[1] != len(gene_names):
+        raise ValueError("data of shape {} x {} does not match {} sample names x {} gene names".format(
+            raw.shape[0], raw.shape[1], len(sample_names), len(gene_names)))
+    return raw, gene_names, sample_names
+
+
+def to_boolean_mask(selected, names):
+    """Index / name / boolean selection -> boolean mask (pypairs/utils.py:311-339)."""
+    n = len(names)
+    if selected is None:
+        return np.ones(n, dtype=bool)
+    selected = np.array(selected)
+    if selected.size == 0:
+        return np.ones(n, dtype=bool)
+    if selected.dtype == bool:
+        if selected.shape != (n,):
+            raise ValueError("boolean selection has length {} but {} entries were expected".format(len(selected), n))
+        return selected
+    mask = np.zeros(n, dtype=bool)
+    if np.issubdtype(selected.dtype, np.integer):
+        mask[selected] = True
+    elif selected.dtype.type is np.str_:
+        mask = np.isin(np.asarray(names, dtype=str), selected)
+    else:
+        raise ValueError("Categories must be array-like of type bool, int or str")
+    return mask
+
+
+def parse_annotation(annotation, sample_names):
+    """{'class': [samples...]} -> (class names in dict order, bool[C, N]); pypairs/utils.py:243-261."""
+    names = np.array(list(annotation.keys()))
+    cats = np.zeros((len(names), len(sample_names)), dtype=bool)
+    for i, k in enumerate(annotation.keys()):
+        cats[i] = to_boolean_mask(np.array(annotation[k]), sample_names)
+    return names, cats
+
+
+def parse_data_and_annotation(data, annotation=None, gene_names=None, sample_names=None):
+    """pypairs/utils.py:207-240: classes from `annotation` (dict order) or, for AnnData without
+    annotation, from obs['category'] (np.unique -> sorted)."""
+    raw, gene_names, sample_names = parse_data(data, gene_names, sample_names)
+    if annotation:
+        names, cats = parse_annotation(annotation, sample_names)
+    elif is_anndata(data):
+        keys = data.obs_keys() if hasattr(data, "obs_keys") else list(data.obs.keys())
+        if "category" not in keys:
+            raise ValueError("Provide categories as data.var['category'] or in ``annotation``")
+        col = np.asarray(data.obs["category"])
+        names = np.unique(col)
+        cats = np.zeros((len(names), len(sample_names)), dtype=bool)
+        for i, name in enumerate(names):
+            cats[i] = np.isin(col, name)
+    else:
+        raise ValueError("Provide categories in ``annotation``")
+    return raw, gene_names, sample_names, names, cats
+
+
+def expressed_gene_mask(raw):
+    """~all(data == 0, axis=0) over ALL samples, before sample filtering (pypairs/utils.py:368)."""
+    if is_cuda_tensor(raw):
+        return (raw != 0).any(dim=0).cpu().numpy()
+    raw = np.asarray(raw)
+    out = np.zeros(raw.shape[1], dtype=bool)
+    step = max(1, (1 << 24) // max(1, raw.shape[1]))  # bounded temporaries on large matrices
+    for i in range(0, raw.shape[0], step):
+        out |= (raw[i:i + step] != 0).any(axis=0)
+    return out
+
+
+def get_filter_masks(raw, gene_names, sample_names, categories, filter_genes, filter_samples):
+    """(gene_mask, sample_mask) of pypairs/utils.py:364-385."""
+    gene_mask = np.logical_and(expressed_gene_mask(raw), to_boolean_mask(filter_genes, gene_names))
+    categorized = np.any(categories, axis=0)
+    sample_mask = np.logical_and(categorized, to_boolean_mask(filter_samples, sample_names))
+    return gene_mask, sample_mask
+
+
+def same_marker(a, b):
+    """Set equality per class, the comparator of the reference's tests (pypairs/utils.py:409-423)."""
+    if set(a.keys()) != set(b.keys()):
+        return False
+    for k in a:
+        if {tuple(p) for p in a[k]} != {tuple(p) for p in b[k]}:
+            return False
+    return True
+
+
+def export_marker(marker, fname):
+    """Marker dict -> JSON file (pypairs/utils.py:97-130 semantics: lists of 2-lists per class)."""
+    with open(fname, "w") as f:
+        json.dump({str(k): [[str(a), str(b)] for a, b in v] for k, v in marker.items()}, f)
+
+
+def load_marker(fname):
+    """JSON file -> marker dict of tuples (pypairs/utils.py:133-166)."""
+    with open(fname) as f:
+        d = json.load(f)
+    return {k: [tuple(p) for p in v] for k, v in d.items()}

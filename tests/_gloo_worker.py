@@ -1,0 +1,77 @@
+"""Worker of tests/test_host.py::test_two_rank_gloo_merge (one of two gloo ranks on CPU).
+
+The CUDA entry points are replaced by the CPU oracle HERE, in the test, to exercise the host-side
+sharding + all-gather logic of pairs.sandbag / pairs.cyclone without a GPU."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch.distributed as dist  # noqa: E402
+
+from oracle import oracle as orc  # noqa: E402
+from pypairs_b200 import _ffi, pairs, settings  # noqa: E402
+
+settings.verbosity = 0
+calls = {"sandbag": [], "cyclone": []}
+
+
+def fake_sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, **kw):
+    calls["sandbag"].append((shard, n_shards))
+    cats = np.concatenate([np.full(n, k) for k, n in enumerate(class_sizes)])
+    res = orc.check_pairs(np.asarray(x, dtype=np.float64)[np.asarray(cell_rows)][:, np.asarray(gene_cols)], cats,
+                          np.asarray(thresholds))
+    r, c = np.where(res != -1)
+    keys = (r * len(gene_cols) + c).astype(np.uint64)
+    sel = ((r // 7 + c // 5) % n_shards) == shard  # some tile-like split of the pair space
+    return keys[sel], res[r, c].astype(np.int32)[sel], {}
+
+
+def fake_cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,
+                 perm_tables=None, row_begin=0, n_cells=None, **kw):
+    calls["cyclone"].append((row_begin, n_cells))
+    x = np.asarray(x, dtype=np.float64)[row_begin:row_begin + n_cells]
+    out = []
+    for u, p in zip(used_idx_list, pairs_list):
+        used = np.zeros(x.shape[1], dtype=bool)
+        used[u] = True
+        out.append(orc.phase_scores(x, iterations, min_iter, min_pairs, p, used, seed=seed))
+    return np.stack(out), {}
+
+
+def main():
+    rng = np.random.default_rng(5)
+    n, g = 61, 40
+    lab = rng.integers(0, 3, n)
+    x = rng.poisson(3.0 * np.exp(rng.normal(0, 1, g))[None, :] * np.where(lab[:, None] == (np.arange(g) % 3)[None, :], 3, 1)
+                    ).astype(np.float64)
+    x[:, 0] += 1
+    sn = ["s{}".format(i) for i in range(n)]
+    gn = ["g{}".format(i) for i in range(g)]
+    ann = {k: np.where(lab == i)[0].tolist() for i, k in enumerate(["G1", "S", "G2M"])}
+    mk = {"G1": [(gn[i], gn[(i * 3 + 1) % g]) for i in range(30)], "S": [(gn[(i * 5) % g], gn[(i + 7) % g]) for i in range(25)],
+          "G2M": [(gn[(i * 7) % g], gn[(i * 2 + 3) % g]) for i in range(28)]}
+
+    _ffi.sandbag, _ffi.cyclone = fake_sandbag, fake_cyclone
+    single_m = pairs.sandbag(x, ann, gn, sn, fraction=0.6)           # before init: world size 1
+    single_s = pairs.cyclone(x, mk, gn, sn, iterations=60, min_iter=10, min_pairs=2)
+    assert calls["sandbag"][-1] == (0, 1) and calls["cyclone"][-1] == (0, n)
+
+    dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    rank = dist.get_rank()
+    multi_m = pairs.sandbag(x, ann, gn, sn, fraction=0.6)
+    multi_s = pairs.cyclone(x, mk, gn, sn, iterations=60, min_iter=10, min_pairs=2)
+    assert calls["sandbag"][-1] == (rank, 2)
+    assert calls["cyclone"][-1] == ((0, 31) if rank == 0 else (31, 30))
+    assert list(multi_m.items()) == list(single_m.items())           # same lists, same order, same key order
+    assert sum(len(v) for v in multi_m.values()) > 0
+    assert multi_s.equals(single_s)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("GLOO_OK rank", rank)
+
+
+if __name__ == "__main__":
+    main()

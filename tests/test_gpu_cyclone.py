@@ -1,0 +1,165 @@
+"""GPU parity: pp_cyclone / pp_phase_scores (through the C ABI) vs reference goldens and the CPU oracle."""
+import numpy as np
+import pytest
+
+from conftest import CYCLONE_CASE_NAMES
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ffi():
+    from pypairs_b200 import _ffi
+    return _ffi
+
+
+def default_setup(rng, n_cells, n_genes, kind="poisson", dtype=np.float32):
+    from pypairs_b200 import datasets
+    markers = datasets.default_cc_marker()
+    genes = sorted({a for v in markers.values() for p in v for a in p})
+    names = genes + ["X{}".format(i) for i in range(n_genes - len(genes))]
+    rng.shuffle(names)
+    if kind == "poisson":
+        x = rng.poisson(2.0, (n_cells, n_genes)).astype(dtype)
+    else:
+        x = rng.lognormal(0.0, 1.0, (n_cells, n_genes)).astype(dtype)
+    return markers, names, x
+
+
+@pytest.mark.parametrize("name", CYCLONE_CASE_NAMES)
+def test_golden_cases(cyclone_cases, name):
+    """Scores of the reference's Numba kernels, bit for bit (MT19937 replay), incl. the NaN / 0.0 quirks."""
+    from pypairs_b200.cyclone import filter_marker_pairs
+    npz, meta = cyclone_cases
+    m = meta[name]
+    x = npz[name + "_x"]
+    markers = {k: [tuple(p) for p in v] for k, v in m["markers"].items()}
+    pairs, used = filter_marker_pairs(markers, m["gene_names"])
+    ks = m["classes"]
+    for k in ks:
+        assert np.array_equal(pairs[k], npz["{}_pairs_{}".format(name, k)])
+        assert np.array_equal(used[k], npz["{}_used_{}".format(name, k)])
+    sc, tm, oh, ot = _ffi().cyclone(x, [np.where(used[k])[0] for k in ks], [pairs[k] for k in ks], m["iterations"],
+                                    m["min_iter"], m["min_pairs"], want_observed=True)
+    for i, k in enumerate(ks):
+        assert np.array_equal(sc[i], npz["{}_score_{}".format(name, k)], equal_nan=True), k
+        _, eh, et = orc.phase_scores(x, 1, 1, 1, pairs[k], used[k], return_observed=True)
+        assert np.array_equal(oh[i], eh) and np.array_equal(ot[i], et)  # observed (hits, total) exact
+        # reference-kernel-shaped single-class entry point
+        one = _ffi().phase_scores(x, m["iterations"], m["min_iter"], m["min_pairs"], pairs[k], used[k])
+        assert np.array_equal(one, sc[i], equal_nan=True)
+
+
+def test_perm_tables(mt_golden):
+    import hashlib
+    f = _ffi()
+    for n, info in mt_golden["tables"].items():
+        if "rows" in info:
+            assert f.perm_table("mt19937", 99, 0, 7, 6).tolist() == info["rows"]
+        else:
+            t = f.perm_table("mt19937", 2803, 0, int(n), 1000)
+            assert hashlib.sha256(t.astype("<i8").tobytes()).hexdigest() == info["sha256_int64le_1000xn"]
+    for seed, cls, n, it in [(2803, 0, 1195, 40), (2**40 + 5, 2, 17, 100), (1, 1, 1, 3), (7, 0, 2, 9)]:
+        assert np.array_equal(f.perm_table("philox", seed, cls, n, it), orc.perm_table_philox(seed, cls, n, it))
+
+
+@pytest.mark.parametrize("kind,dtype", [("poisson", np.float32), ("lognormal", np.float64)])
+def test_default_markers_vs_oracle(kind, dtype):
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(42)
+    markers, names, x = default_setup(rng, 150, 2500, kind, dtype)
+    x[7] = x[6]
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    sc, tm = _ffi().cyclone(x, u, p, 1000, 100, 50)
+    for i, k in enumerate(ks):
+        ref = orc.phase_scores(x, 1000, 100, 50, pairs[k], used[k])
+        assert np.array_equal(sc[i], ref, equal_nan=True), k
+    assert np.array_equal(sc[:, 6], sc[:, 7])
+    # cells are independent: a permuted matrix gives permuted scores; a row range gives that slice
+    perm = rng.permutation(150)
+    sc2, _ = _ffi().cyclone(x[perm], u, p, 1000, 100, 50)
+    assert np.array_equal(sc2, sc[:, perm], equal_nan=True)
+    sc3, _ = _ffi().cyclone(x, u, p, 1000, 100, 50, row_begin=33, n_cells=70)
+    assert np.array_equal(sc3, sc[:, 33:103], equal_nan=True)
+    # validation mode: the reference's exported permutation tables give the same scores
+    tabs = [orc.perm_table(2803, len(ui), 1000) for ui in u]
+    sc4, _ = _ffi().cyclone(x, u, p, 1000, 100, 50, rng="table", perm_tables=tabs)
+    assert np.array_equal(sc4, sc, equal_nan=True)
+
+
+def test_philox_mode():
+    """Bit-exact against the CPU restatement of the same Philox stream; statistically equivalent to MT19937."""
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(43)
+    markers, names, x = default_setup(rng, 512, 2000, "lognormal", np.float32)
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    sp, _ = _ffi().cyclone(x, u, p, 1000, 100, 50, rng="philox", seed=2803)
+    sm, _ = _ffi().cyclone(x, u, p, 1000, 100, 50, rng="mt19937", seed=2803)
+    for i, k in enumerate(ks):
+        tab = orc.perm_table_philox(2803, i, len(u[i]), 1000)
+        ref = orc.phase_scores_table(x, tab, 100, 50, pairs[k], used[k])
+        assert np.array_equal(sp[i], ref, equal_nan=True)
+    d = np.abs(sp - sm)
+    bound = 4.0 * np.sqrt(2.0 * sm * (1.0 - sm) / 1000.0) + 1e-3 + 1.0 / 1000.0
+    assert d.mean() <= 0.02                      # north-star tolerance, stated as the mean |delta score|
+    assert np.mean(d <= bound) >= 0.999          # per-cell z-bound (two independent 1000-draw nulls)
+    print("philox vs mt19937: mean |d| {:.4f}, max |d| {:.4f}, within 0.02: {:.3f}".format(
+        d.mean(), d.max(), np.mean(d <= 0.02)))
+
+
+def test_api_frame_and_anndata():
+    from pandas import DataFrame
+    from pypairs_b200 import pairs
+    rng = np.random.default_rng(44)
+    markers, names, x = default_setup(rng, 40, 1700, "poisson", np.float64)
+    sn = ["c{}".format(i) for i in range(40)]
+    df = pairs.cyclone(DataFrame(x, index=sn, columns=names))  # marker_pairs=None -> default_cc_marker
+    assert list(df.columns) == ["G1", "S", "G2M", "max_class", "cc_prediction"] and list(df.index) == sn
+    pr, us = orc.filter_marker_pairs(markers, names)
+    ref = {k: orc.phase_scores(x, 1000, 100, 50, pr[k], us[k]) for k in ["G1", "S", "G2M"]}
+    exp = orc.cyclone_epilogue(ref, sn)
+    for k in ["G1", "S", "G2M"]:
+        assert np.array_equal(df[k].values, exp[k].values, equal_nan=True)
+    assert list(df["max_class"]) == list(exp["max_class"])
+    assert [str(v) for v in df["cc_prediction"]] == [str(v) for v in exp["cc_prediction"]]
+
+    class FakeAnnData:
+        def __init__(self):
+            self.X = x
+            self.obs = DataFrame(index=sn)
+            self.obs_names = sn
+            self.var_names = names
+
+    ad = FakeAnnData()
+    df2 = pairs.cyclone(ad, markers, iterations=200, min_iter=10, min_pairs=1)
+    assert all("pypairs_" + c in ad.obs.columns for c in df2.columns)
+    assert np.array_equal(ad.obs["pypairs_G1"].values, df2["G1"].values, equal_nan=True)
+    with pytest.raises(SystemExit):
+        pairs.cyclone(x, {"A": [("nope", "nada")]}, names, sn)
+
+
+def test_full_size_slice_properties():
+    """cfg2 shape (20k genes) on 4096 device-generated cells: oracle on a row subset + invariants."""
+    import torch
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(45)
+    markers, names, _ = default_setup(rng, 1, 20000)
+    gen = torch.Generator(device="cuda").manual_seed(20262)
+    x = torch.poisson(torch.full((4096, 20000), 2.0, device="cuda"), generator=gen).to(torch.float32)
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    sc, tm = _ffi().cyclone(x, u, p, 1000, 100, 50)
+    assert np.all((sc >= 0) & (sc <= 1)) and np.all(sc * 1000 == np.round(sc * 1000))
+    rows = np.sort(rng.choice(4096, 48, replace=False))
+    xs = x[torch.from_numpy(rows).cuda()].cpu().numpy()
+    for i, k in enumerate(ks):
+        assert np.array_equal(sc[i, rows], orc.phase_scores(xs, 1000, 100, 50, pairs[k], used[k]))
+    print("cfg2 slice 4096 cells: score kernel {:.1f} ms, prep {:.1f} ms".format(tm["main_ms"], tm["prep_ms"]))

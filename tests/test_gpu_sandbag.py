@@ -1,0 +1,237 @@
+"""GPU parity: pp_sandbag (through the C ABI) vs reference goldens and the CPU oracle."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import SANDBAG_CASE_NAMES
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _ffi():
+    from pypairs_b200 import _ffi
+    return _ffi
+
+
+def run_kernel(x, cats, n_classes, thr, **kw):
+    order = np.argsort(cats, kind="stable")
+    sizes = np.bincount(cats, minlength=n_classes)
+    return _ffi().sandbag(x, order, sizes, np.arange(x.shape[1]), thr, **kw)
+
+
+def synth(rng, n, g, c, frac_de=0.1, dtype=np.float64):
+    lab = rng.integers(0, c, n)
+    lab[:c] = np.arange(c)
+    base = rng.normal(0.0, 1.5, g)
+    de = rng.random(g) < frac_de
+    de_class = rng.integers(0, c, g)
+    sign = rng.choice([-1.0, 1.0], g)
+    lam = np.tile(3.0 * np.exp(base), (n, 1))
+    eff = np.where(de, 2.0 ** (2.0 * sign), 1.0)
+    lam = np.where(lab[:, None] == de_class[None, :], lam * eff[None, :], lam)
+    return rng.poisson(lam).astype(dtype), lab.astype(np.int64)
+
+
+def test_dense_rank_matches_numpy():
+    rng = np.random.default_rng(1)
+    for dtype in (np.float64, np.float32):
+        x = rng.poisson(3.0, (37, 700)).astype(dtype)
+        x[0] = rng.normal(size=700).astype(dtype)          # all distinct, negative values
+        x[1] = 5.0                                          # constant
+        x[2, ::2] = -0.0                                    # signed zeros tie
+        x[2, 1::2] = 0.0
+        x[3] = np.linspace(1.0, 1.0 + 1e-12, 700) if dtype == np.float64 else x[3]  # float32-colliding doubles
+        rows = np.array([5, 0, 1, 2, 3, 36, 20], dtype=np.int32)
+        cols = np.sort(rng.choice(700, 333, replace=False)).astype(np.int32)
+        got, mx = _ffi().dense_rank(x, rows, cols)
+        sub = x[rows][:, cols]
+        exp = np.stack([np.unique(r, return_inverse=True)[1] for r in sub])
+        assert np.array_equal(got, exp.astype(np.uint16))
+        assert mx == exp.max()
+
+
+@pytest.mark.parametrize("name", SANDBAG_CASE_NAMES)
+def test_golden_cases(sandbag_cases, name):
+    c = sandbag_cases
+    x, cats, thr = c[name + "_x"], c[name + "_cats"], c[name + "_thr"]
+    g = x.shape[1]
+    keys, cls, tm = run_kernel(x, cats, len(thr), thr)
+    assert np.array_equal(keys, c[name + "_rows"].astype(np.uint64) * np.uint64(g) + c[name + "_cols"].astype(np.uint64))
+    assert np.array_equal(cls, c[name + "_cls"])
+    # float32 copy of integer counts must give the same answer
+    keys32, cls32, _ = run_kernel(x.astype(np.float32) if name != "c3_f65" else x, cats, len(thr), thr)
+    assert np.array_equal(keys32, keys) and np.array_equal(cls32, cls)
+
+
+def test_minref_api(sandbag_minref):
+    """The reference's own KAT (tests/test_sandbag.py:26-113) through pairs.sandbag: lists AND key order."""
+    from pypairs_b200 import pairs, utils
+    m = sandbag_minref
+    x = np.array(m["matrix_genes_by_samples"]).T
+    for frac_s, ref in m["results"].items():
+        got = pairs.sandbag(x, m["annotation"], m["gene_names"], m["sample_names"], fraction=float(frac_s))
+        assert [[str(k), [[str(a), str(b)] for a, b in v]] for k, v in got.items()] == ref
+    got = pairs.sandbag(x, m["annotation"], m["gene_names"], m["sample_names"])
+    ref65 = {k: [tuple(p) for p in v] for k, v in m["results"]["0.65"]}
+    assert utils.same_marker(got, ref65)
+
+
+def test_api_inputs(sandbag_api):
+    """DataFrame / ndarray, annotation as int / str / bool, filters, class order, emptied class."""
+    from pandas import DataFrame
+    from pypairs_b200 import pairs
+    a = sandbag_api
+    x = np.array(a["x"])
+    sn, gn, lab = a["sample_names"], a["gene_names"], np.array(a["labels"])
+    names3 = ["G1", "S", "G2M"]
+    ann = {"int": {k: np.where(lab == i)[0].tolist() for i, k in enumerate(names3)},
+           "str": {k: [sn[j] for j in np.where(lab == i)[0]] for i, k in enumerate(names3)},
+           "bool": {k: (lab == i).tolist() for i, k in enumerate(names3)}}
+    ann["int_rev"] = {k: ann["int"][k] for k in ["G2M", "G1", "S"]}
+    ann["int_empty"] = dict(ann["int"], EMPTY=[58])
+    for run in a["runs"]:
+        kw = dict(run["kwargs"])
+        annotation = ann[kw.pop("annotation")]
+        if kw.pop("dataframe", False):
+            got = pairs.sandbag(DataFrame(x, index=sn, columns=gn), annotation, **kw)
+        else:
+            got = pairs.sandbag(x, annotation, gn, sn, **kw)
+        assert [[str(k), [[str(p), str(q)] for p, q in v]] for k, v in got.items()] == run["result"], run["tag"]
+
+
+def test_anndata_duck_type(sandbag_api):
+    """AnnData path: classes from obs['category'] are np.unique-sorted (utils.py:219-226)."""
+    from pandas import DataFrame
+    from pypairs_b200 import pairs
+    a = sandbag_api
+    x = np.array(a["x"])
+    lab = np.array(a["labels"])
+    keep = lab >= 0
+    names = np.array(["G1", "S", "G2M"])
+
+    class FakeAnnData:
+        def __init__(self):
+            self.X = x[keep]
+            self.obs = DataFrame({"category": names[lab[keep]]}, index=np.array(a["sample_names"])[keep])
+            self.obs_names = list(self.obs.index)
+            self.var_names = a["gene_names"]
+
+        def obs_keys(self):
+            return list(self.obs.columns)
+
+    got = pairs.sandbag(FakeAnnData(), fraction=0.65)
+    ann_sorted = {k: np.where(names[lab[keep]] == k)[0].tolist() for k in sorted(names)}
+    exp = pairs.sandbag(x[keep], ann_sorted, a["gene_names"], list(np.array(a["sample_names"])[keep]), fraction=0.65)
+    assert list(got.items()) == list(exp.items())
+
+
+@pytest.mark.parametrize("n,g,c,frac,dtype", [
+    (500, 600, 3, 0.65, np.float64), (333, 450, 10, 0.65, np.float32), (1000, 300, 2, 0.6, np.float64),
+    (64, 129, 1, 0.7, np.float64), (97, 257, 4, 0.5, np.float32), (2100, 200, 3, 0.65, np.float64)])
+def test_random_vs_oracle(n, g, c, frac, dtype):
+    rng = np.random.default_rng(n * 7 + g)
+    x, lab = synth(rng, n, g, c, dtype=dtype)
+    sizes = np.bincount(lab, minlength=c)
+    thr = orc.calc_thresholds(sizes, frac)
+    probes = np.sort(rng.integers(0, g, (200, 2)), axis=1)
+    probes = probes[probes[:, 0] < probes[:, 1]]
+    keys, cls, tm, ppos, pneg = run_kernel(x, lab, c, thr, probe_pairs=probes)
+    rr, cc, kk = orc.sandbag_arrays(x, lab, c, frac)
+    assert np.array_equal(keys, (rr * g + cc).astype(np.uint64))
+    assert np.array_equal(cls, kk.astype(np.int32))
+    epos, eneg = orc.pair_counts(x, lab, c, probes)
+    assert np.array_equal(ppos, epos) and np.array_equal(pneg, eneg)  # per-class num_pos / num_neg bit-exact
+
+
+def test_continuous_values_need_many_planes():
+    """Tie-free doubles: every gene of a cell has its own rank -> 12 planes at 4000 genes."""
+    rng = np.random.default_rng(5)
+    n, g, c = 150, 4000, 3
+    lab = rng.integers(0, c, n)
+    x = rng.lognormal(0, 1, (n, g)) * np.where(rng.random((1, g)) < 0.05, 1.0 + lab[:, None], 1.0)
+    sizes = np.bincount(lab, minlength=c)
+    thr = orc.calc_thresholds(sizes, 0.65)
+    keys, cls, tm = run_kernel(x, lab, c, thr)
+    assert tm["n_planes"] == 12
+    sub = 400  # oracle on the first 400 genes; restricting genes never changes a pair's decision
+    rr, cc, kk = orc.sandbag_arrays(x[:, :sub], lab, c, 0.65)
+    rows, cols = (keys // np.uint64(g)).astype(np.int64), (keys % np.uint64(g)).astype(np.int64)
+    m = (rows < sub) & (cols < sub)
+    assert np.array_equal(rows[m], rr) and np.array_equal(cols[m], cc) and np.array_equal(cls[m], kk.astype(np.int32))
+
+
+def test_cell_order_and_shards_do_not_matter():
+    rng = np.random.default_rng(11)
+    x, lab = synth(rng, 400, 500, 3)
+    thr = orc.calc_thresholds(np.bincount(lab, minlength=3), 0.65)
+    keys, cls, _ = run_kernel(x, lab, 3, thr)
+    perm = rng.permutation(400)
+    keys2, cls2, _ = run_kernel(x[perm], lab[perm], 3, thr)
+    assert np.array_equal(keys, keys2) and np.array_equal(cls, cls2)
+    parts = [run_kernel(x, lab, 3, thr, shard=s, n_shards=3) for s in range(3)]
+    allk = np.concatenate([p[0] for p in parts])
+    allc = np.concatenate([p[1] for p in parts])
+    o = np.argsort(allk, kind="stable")
+    assert np.array_equal(allk[o], keys) and np.array_equal(allc[o], cls)
+    assert sum(p[2]["n_units"] for p in parts) == 500 * 499 // 2
+
+
+def test_errors():
+    f = _ffi()
+    x = np.ones((4, 5))
+    with pytest.raises(f.PyPairsB200Error):
+        f.sandbag(x, [0, 1, 9], [2, 1], np.arange(5), [1, 1])       # row out of range
+    with pytest.raises(f.PyPairsB200Error):
+        f.sandbag(x, [0, 1, 2], [2, 2], np.arange(5), [1, 1])       # sizes do not sum
+    xn = x.copy()
+    xn[1, 2] = np.nan
+    with pytest.raises(f.PyPairsB200Error) as e:
+        f.sandbag(xn, [0, 1, 2], [2, 1], np.arange(5), [1, 1])
+    assert e.value.code == f.PP_ENAN
+    keys, cls, _ = f.sandbag(x, [0, 1, 2], [2, 1], np.arange(1), [1, 1])  # single gene: no pairs
+    assert len(keys) == 0
+
+
+def test_device_tensor_input():
+    import torch
+    rng = np.random.default_rng(3)
+    x, lab = synth(rng, 200, 300, 3, dtype=np.float32)
+    thr = orc.calc_thresholds(np.bincount(lab, minlength=3), 0.65)
+    keys, cls, _ = run_kernel(x, lab, 3, thr)
+    keys2, cls2, tm = run_kernel(torch.from_numpy(x).cuda(), lab, 3, thr)
+    assert np.array_equal(keys, keys2) and np.array_equal(cls, cls2)
+    assert tm["h2d_ms"] < 1.0
+
+
+def test_full_size_properties():
+    """cfg3 shape (20k genes x 10k cells, 3 classes): size-independent checks + oracle on a gene subset."""
+    import torch
+    g, n, c = 20000, 10000, 3
+    gen = torch.Generator(device="cuda").manual_seed(20263)
+    lab = torch.randint(0, c, (n,), generator=gen, device="cuda")
+    base = torch.randn(g, generator=gen, device="cuda") * 1.5
+    de = torch.rand(g, generator=gen, device="cuda") < 0.02
+    de_class = torch.randint(0, c, (g,), generator=gen, device="cuda")
+    sign = torch.where(torch.rand(g, generator=gen, device="cuda") < 0.5, -1.0, 1.0)
+    eff = torch.where(de, torch.pow(2.0, 2.0 * sign), torch.ones_like(sign))
+    lam = 3.0 * torch.exp(base)[None, :] * torch.where(lab[:, None] == de_class[None, :], eff[None, :], 1.0)
+    x = torch.poisson(lam, generator=gen).to(torch.float32)
+    x[:, 0] += 1.0
+    lab_h = lab.cpu().numpy().astype(np.int64)
+    thr = orc.calc_thresholds(np.bincount(lab_h, minlength=c), 0.65)
+    keys, cls, tm = run_kernel(x, lab_h, c, thr)
+    assert np.all(keys[1:] > keys[:-1])                       # sorted, unique == np.where order
+    rows, cols = (keys // np.uint64(g)).astype(np.int64), (keys % np.uint64(g)).astype(np.int64)
+    assert np.all(rows != cols) and cls.min() >= 0 and cls.max() < c
+    assert tm["n_units"] == g * (g - 1) // 2
+    sub = np.sort(np.random.default_rng(0).choice(g, 250, replace=False))
+    xs = x[:, torch.from_numpy(sub).cuda()].cpu().numpy().astype(np.float64)
+    rr, cc, kk = orc.sandbag_arrays(xs, lab_h, c, 0.65)
+    pos = {int(v): i for i, v in enumerate(sub)}
+    m = np.isin(rows, sub) & np.isin(cols, sub)
+    got = sorted((pos[int(r)], pos[int(q)], int(k)) for r, q, k in zip(rows[m], cols[m], cls[m]))
+    assert got == sorted(zip(rr.tolist(), cc.tolist(), kk.tolist()))
+    print("cfg3 full size: {} markers, {} planes, kernel {:.1f} ms, prep {:.1f} ms".format(
+        len(keys), tm["n_planes"], tm["main_ms"], tm["prep_ms"]))

@@ -1,0 +1,181 @@
+"""CPU-only tests: host-side logic against the reference goldens, the C-ABI surface, multi-rank merge (gloo)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as orc
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports exactly what include/pypairs_b200.h declares."""
+    import __graft_entry__ as g
+    g.build()
+    from pypairs_b200 import _ffi
+    lib = _ffi.load()
+    header = open(os.path.join(ROOT, "include", "pypairs_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(pp_[a-z_0-9]+)\s*\(", header)))
+    assert declared == sorted(_ffi.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.pp_version() == 1
+    h = ctypes.c_void_p()
+    if lib.pp_device_count() == 0:  # no compute without a GPU: creation fails loudly, no fallback
+        assert lib.pp_ctx_create(0, ctypes.byref(h)) != 0
+        assert len(lib.pp_last_error(None)) > 0
+        with pytest.raises(_ffi.PyPairsB200Error):
+            _ffi.sandbag(np.ones((4, 4)), [0, 1], [1, 1], np.arange(4), [1, 1])
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pypairs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "libpp_oracle" not in src, f
+
+
+def _emulated_sandbag(monkeypatch):
+    """Route _ffi.sandbag to the CPU oracle so the HOST logic can be checked without a GPU (tests only)."""
+    from pypairs_b200 import _ffi
+
+    def fake(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, **kw):
+        x = np.asarray(x, dtype=np.float64)
+        cats = np.concatenate([np.full(n, k) for k, n in enumerate(class_sizes)])
+        res = orc.check_pairs(x[np.asarray(cell_rows)][:, np.asarray(gene_cols)], cats, np.asarray(thresholds))
+        r, c = np.where(res != -1)
+        keys = (r * len(gene_cols) + c).astype(np.uint64)
+        cls = res[r, c].astype(np.int32)
+        sel = (np.arange(len(keys)) % n_shards) == shard
+        return keys[sel], cls[sel], {}
+
+    monkeypatch.setattr(_ffi, "sandbag", fake)
+
+
+def test_sandbag_host_logic_vs_reference(monkeypatch, sandbag_api, sandbag_minref):
+    from pandas import DataFrame
+    from pypairs_b200 import pairs
+    _emulated_sandbag(monkeypatch)
+    a = sandbag_api
+    x = np.array(a["x"])
+    sn, gn, lab = a["sample_names"], a["gene_names"], np.array(a["labels"])
+    names3 = ["G1", "S", "G2M"]
+    ann = {"int": {k: np.where(lab == i)[0].tolist() for i, k in enumerate(names3)},
+           "str": {k: [sn[j] for j in np.where(lab == i)[0]] for i, k in enumerate(names3)},
+           "bool": {k: (lab == i).tolist() for i, k in enumerate(names3)}}
+    ann["int_rev"] = {k: ann["int"][k] for k in ["G2M", "G1", "S"]}
+    ann["int_empty"] = dict(ann["int"], EMPTY=[58])
+    for run in a["runs"]:
+        kw = dict(run["kwargs"])
+        annotation = ann[kw.pop("annotation")]
+        if kw.pop("dataframe", False):
+            got = pairs.sandbag(DataFrame(x, index=sn, columns=gn), annotation, **kw)
+        else:
+            got = pairs.sandbag(x, annotation, gn, sn, **kw)
+        assert [[str(k), [[str(p), str(q)] for p, q in v]] for k, v in got.items()] == run["result"], run["tag"]
+        assert all(type(k) is np.str_ for k in got.keys())  # keys and names are numpy strings (S8)
+    m = sandbag_minref
+    xm = np.array(m["matrix_genes_by_samples"]).T
+    for frac_s, ref in m["results"].items():
+        got = pairs.sandbag(xm, m["annotation"], m["gene_names"], m["sample_names"], fraction=float(frac_s))
+        assert [[str(k), [[str(p), str(q)] for p, q in v]] for k, v in got.items()] == ref
+
+
+def test_sandbag_input_errors(monkeypatch):
+    from pypairs_b200 import pairs
+    _emulated_sandbag(monkeypatch)
+    x = np.arange(20.0).reshape(4, 5)
+    with pytest.raises(ValueError):
+        pairs.sandbag(x, {"a": [0, 1]})                                    # names required for ndarray
+    with pytest.raises(ValueError):
+        pairs.sandbag(x, None, list("abcde"), list("wxyz"))               # annotation required
+    with pytest.raises(ValueError):
+        pairs.sandbag(x, {"a": [0, 1], "b": [1, 2]}, list("abcde"), list("wxyz"))  # sample in two classes
+    with pytest.raises(ValueError):
+        pairs.sandbag(x, {"a": [0.5]}, list("abcde"), list("wxyz"))       # float annotation
+    with pytest.raises(ValueError):
+        pairs.sandbag("nope", {"a": [0]})
+
+
+def test_to_boolean_mask_matches_reference_cases():
+    """pypairs/tests/test_utils.py: int / str / None / [] / bool selections."""
+    from pypairs_b200.utils import to_boolean_mask
+    names = ["a", "b", "c", "d"]
+    assert to_boolean_mask([0, 3], names).tolist() == [True, False, False, True]
+    assert to_boolean_mask(["b", "d"], names).tolist() == [False, True, False, True]
+    assert to_boolean_mask(None, names).tolist() == [True] * 4
+    assert to_boolean_mask([], names).tolist() == [True] * 4
+    assert to_boolean_mask([True, False, True, False], names).tolist() == [True, False, True, False]
+    assert to_boolean_mask(2, names).tolist() == [False, False, True, False]
+    with pytest.raises(ValueError):
+        to_boolean_mask([0.5], names)
+
+
+def test_filter_marker_pairs_vs_reference(cyclone_cases):
+    from pypairs_b200.cyclone import filter_marker_pairs
+    npz, meta = cyclone_cases
+    for name, m in meta.items():
+        markers = {k: [tuple(p) for p in v] for k, v in m["markers"].items()}
+        pairs, used = filter_marker_pairs(markers, m["gene_names"])
+        assert list(pairs.keys()) == m["classes"]
+        for k in m["classes"]:
+            assert np.array_equal(pairs[k], npz["{}_pairs_{}".format(name, k)])
+            assert np.array_equal(used[k], npz["{}_used_{}".format(name, k)])
+
+
+def test_cyclone_epilogue_rules():
+    """max_class / 'N/A' and cc_prediction rules of cyclone.py:171-181 on hand-built score tables."""
+    from pypairs_b200.cyclone import scores_to_frame
+    sc = np.array([[0.1, 0.9, np.nan, 0.0, np.nan, 0.4, 0.5],
+                   [0.2, 0.1, np.nan, 0.0, 0.3, 0.9, 0.5],
+                   [0.7, 0.95, np.nan, 0.0, 0.2, 0.45, 0.5]])
+    df = scores_to_frame(sc, ["G1", "S", "G2M"], list("abcdefg"))
+    assert list(df["max_class"]) == ["G2M", "G2M", "N/A", "N/A", "S", "S", "G1"]
+    assert [str(v) for v in df["cc_prediction"]] == ["G2M", "G2M", "nan", "S", "S", "S", "G1"]
+    exp = orc.cyclone_epilogue({"G1": sc[0], "S": sc[1], "G2M": sc[2]}, list("abcdefg"))
+    assert list(exp["max_class"]) == list(df["max_class"])
+    assert [str(v) for v in exp["cc_prediction"]] == [str(v) for v in df["cc_prediction"]]
+    df2 = scores_to_frame(sc[:2], ["alpha", "beta"], list("abcdefg"))
+    assert list(df2.columns) == ["alpha", "beta", "max_class"]
+
+
+def test_default_marker_fixture(golden_dir):
+    from pypairs_b200 import datasets
+    d = datasets.default_cc_marker()
+    assert {k: len(v) for k, v in d.items()} == {"G1": 2575, "S": 4097, "G2M": 1470}
+    assert len({g for v in d.values() for p in v for g in p}) == 1479
+    assert d["G1"][:3] == [["PSMC6", "PTEN"], ["PSMC6", "TOP2A"], ["PSMC6", "MDM2"]]
+    if os.path.exists("/root/reference/pypairs/datasets/leng15_default_markers.json"):
+        assert d == json.load(open("/root/reference/pypairs/datasets/leng15_default_markers.json"))
+
+
+def test_cell_shard_partition():
+    from pypairs_b200._dist import cell_shard
+    for n in (0, 1, 7, 64, 1000003):
+        for ws in (1, 2, 3, 8):
+            spans = [cell_shard(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def test_two_rank_gloo_merge():
+    """world_size 2 on CPU (gloo): sharded sandbag merge and sharded cyclone gather give the 1-rank answer.
+    The kernels are emulated by the oracle inside the worker (tests only)."""
+    port = 29500 + os.getpid() % 2000
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
+    procs = []
+    for r in range(2):
+        e = dict(env, RANK=str(r))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_worker.py")], env=e,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, cwd=ROOT))
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert all("GLOO_OK" in o for o in outs), "\n".join(outs)
