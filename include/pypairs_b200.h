@@ -161,6 +161,14 @@ int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int6
                   int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int32_t *gene_cols,
                   int64_t n_genes, uint16_t *out_rank, int32_t *out_max_rank);
 
+/*
+ * pp_alu_peak -- roofline denominator for the bit-sliced / packed-integer kernels: measured
+ * throughput of independent 32-bit LOP3 instructions on this device, in lane-operations per
+ * second (threads x instructions / time), best of `repeats` launches.  Also returns the SM
+ * count.  (MEASURED_PEAKS.json only carries HBM and tensor peaks.)
+ */
+int pp_alu_peak(pp_ctx *ctx, int32_t repeats, double *out_lop3_lane_ops_per_s, int32_t *out_n_sm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,3 +80,14 @@ def allgather_columns(local, n_total):
         b, e = cell_shard(n_total, r, ws)
         cols.append(p[:, :e - b].cpu().numpy())
     return np.concatenate(cols, axis=1)
+
+
+def allgather_names(names):
+    """Concatenate every rank's list of sample names in rank order."""
+    import torch.distributed as dist
+    rank, ws = world()
+    if ws == 1:
+        return list(names)
+    parts = [None] * ws
+    dist.all_gather_object(parts, list(names))
+    return [n for p in parts for n in p]

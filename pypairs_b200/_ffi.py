@@ -16,7 +16,7 @@ PP_RNG_MT19937, PP_RNG_PHILOX, PP_RNG_TABLE = 0, 1, 2
 PP_ENAN = 4
 
 SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "pp_last_error", "pp_free",
-           "pp_get_timings", "pp_sandbag", "pp_cyclone", "pp_phase_scores", "pp_perm_table", "pp_dense_rank"]
+           "pp_get_timings", "pp_sandbag", "pp_cyclone", "pp_phase_scores", "pp_perm_table", "pp_dense_rank", "pp_alu_peak"]
 
 
 class Timings(ctypes.Structure):
@@ -67,6 +67,7 @@ def load():
     lib.pp_phase_scores.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp]
     lib.pp_perm_table.argtypes = [vp, i32, u64, i32, i32, i32, vp]
     lib.pp_dense_rank.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i64, vp, c.POINTER(i32)]
+    lib.pp_alu_peak.argtypes = [vp, i32, c.POINTER(c.c_double), c.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -253,3 +254,11 @@ def dense_rank(x, cell_rows, gene_cols, device=None):
                             len(gene_cols), _ptr(out), ctypes.byref(mx)), h)
     del keep
     return out, mx.value
+
+
+def alu_peak(repeats=5, device=None):
+    """Measured LOP3 lane-operations per second of the device and its SM count."""
+    lib, h = load(), ctx(device)
+    v, n = ctypes.c_double(), ctypes.c_int32()
+    check(lib.pp_alu_peak(h, repeats, ctypes.byref(v), ctypes.byref(n)), h)
+    return v.value, n.value

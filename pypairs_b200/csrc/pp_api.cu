@@ -1,6 +1,8 @@
 // pp_api.cu -- context management and the small C-ABI entry points (include/pypairs_b200.h).
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "pp_common.cuh"
 
 thread_local std::string g_pp_err;
@@ -127,5 +129,49 @@ PP_API int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_devic
     PP_CUDA(cudaStreamSynchronize(st));
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_dense_rank: NaN in the expression matrix");
     if (out_max_rank) *out_max_rank = flags[0];
+    return PP_OK;
+}
+
+// ---- integer-ALU peak micro-benchmark -----------------------------------------------------------
+namespace {
+constexpr int PEAK_ITERS = 4096, PEAK_CHAINS = 16;
+__global__ void __launch_bounds__(256) alu_peak_kernel(uint32_t *out, uint32_t seed) {
+    uint32_t v[PEAK_CHAINS];
+    const uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = ~seed + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < PEAK_CHAINS; ++i) v[i] = a + i;
+    for (int it = 0; it < PEAK_ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < PEAK_CHAINS; ++i) v[i] = lop3_gt(a, v[(i + 1) % PEAK_CHAINS], v[i]) ^ 0u;
+#pragma unroll
+        for (int i = 0; i < PEAK_CHAINS; ++i) v[i] = lop3_lt(v[i], b, v[(i + 5) % PEAK_CHAINS]);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < PEAK_CHAINS; ++i) r ^= v[i];
+    if (r == 0x12345u) out[0] = r;  // keeps the chains alive
+}
+}  // namespace
+
+PP_API int pp_alu_peak(pp_ctx *ctx, int32_t repeats, double *out_lop3_lane_ops_per_s, int32_t *out_n_sm) {
+    if (!ctx || !out_lop3_lane_ops_per_s) return pp_fail(ctx, PP_EINVAL, "pp_alu_peak: NULL argument");
+    PP_CUDA(cudaSetDevice(ctx->device));
+    DevBuf d;
+    PP_CUDA(d.alloc(16, ctx->stream));
+    const int blocks = ctx->n_sm * 8;
+    double best = 0;
+    for (int r = 0; r < repeats + 1; ++r) {
+        PP_CUDA(cudaEventRecord(ctx->ev[6], ctx->stream));
+        alu_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(d.as<uint32_t>(), 0x9e3779b9u + r);
+        PP_CHECK_LAUNCH();
+        PP_CUDA(cudaEventRecord(ctx->ev[7], ctx->stream));
+        PP_CUDA(cudaEventSynchronize(ctx->ev[7]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+        const double ops = (double)blocks * 256 * (double)PEAK_ITERS * PEAK_CHAINS * 2;
+        if (r > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    *out_lop3_lane_ops_per_s = best;
+    if (out_n_sm) *out_n_sm = ctx->n_sm;
     return PP_OK;
 }

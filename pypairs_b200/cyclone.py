@@ -66,13 +66,17 @@ def scores_to_frame(scores, keys, sample_names):
 
 
 def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterations=1000, min_iter=100,
-            min_pairs=50, quantile_transform=False):
+            min_pairs=50, quantile_transform=False, *, local_shard=False):
     """Score each sample for each category of marker pairs.
 
     Same signature, defaults and return value as pypairs.pairs.cyclone
     (pypairs/tools/cyclone.py:17-26): a DataFrame indexed by sample with one score column per
     category plus 'max_class' and, for the categories {G1, S, G2M}, 'cc_prediction'; for AnnData
     input the columns are also written to ``data.obs['pypairs_<column>']``.
+
+    `local_shard=True` (keyword-only extension, torch.distributed only): `data` holds just this
+    rank's cells -- for matrices that do not fit one host -- and the frame covers all ranks' cells
+    in rank order.
 
     `settings.rng` selects the permutation stream ('mt19937' = bit-exact with the reference,
     'philox' = device-generated).  Under torch.distributed the cells are sharded over the ranks
@@ -101,14 +105,20 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
 
     keys = list(pairs.keys())
     rank, ws = _dist.world()
-    begin, end = _dist.cell_shard(raw.shape[0], rank, ws)
+    begin, end = (0, raw.shape[0]) if local_shard else _dist.cell_shard(raw.shape[0], rank, ws)
     rng = settings.rng if settings.fix_seed else "philox"
     seed = settings.seed if settings.fix_seed else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
     if ws > 1 and not settings.fix_seed:  # all shards must share one stream
         seed = int(_dist.allgather_varlen((np.array([seed], dtype=np.uint64),))[0][0])
     local, tm = _ffi.cyclone(raw, [np.where(used[k])[0] for k in keys], [pairs[k] for k in keys], iterations, min_iter,
                              min_pairs, rng=rng, seed=seed, row_begin=begin, n_cells=end - begin)
-    scores = _dist.allgather_columns(local, raw.shape[0]) if ws > 1 else local
+    if ws > 1 and local_shard:
+        scores = np.stack(_dist.allgather_varlen(tuple(local[c] for c in range(len(keys)))))
+        sample_names = _dist.allgather_names(sample_names)
+    elif ws > 1:
+        scores = _dist.allgather_columns(local, raw.shape[0])
+    else:
+        scores = local
     df = scores_to_frame(scores, keys, sample_names)
     if utils.is_anndata(data):
         logg.hint('adding scores with key "pypairs_{category}" to `data.obs`"')
