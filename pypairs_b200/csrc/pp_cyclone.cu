@@ -24,6 +24,7 @@
 // sides; score = below / iterations as one IEEE double division (:246).
 #include <algorithm>
 #include <map>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "pp_common.cuh"
@@ -112,29 +113,39 @@ __global__ void philox_perm_kernel(uint16_t *__restrict__ table, int n, int iter
     }
 }
 
-// T[k][p] = (map[perm_{k-1}[p0]] | map[perm_{k-1}[p1]] << 16); k = 0 is the identity (observed)
+// T[k][p] = byte offsets (128 * union position) of the two genes pair p compares in iteration k
+// (k = 0: identity = the observed pairs).  Rows are padded to a multiple of 64 pairs with (0, 0)
+// entries: a padding pair compares a gene with itself, i.e. is a tie, and ties are counted on
+// both sides of the (>=, <=) bookkeeping, so they cancel exactly (see score_kernel).
 __global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int32_t *__restrict__ pairs,
-                                   const uint16_t *__restrict__ map, int n_used, int n_pairs, int iters,
-                                   uint32_t *__restrict__ T) {
+                                   const uint16_t *__restrict__ map, int n_used, int n_pairs, int n_pairs_pad,
+                                   uint2 *__restrict__ T) {
     const int k = blockIdx.y;
     const uint16_t *pk = perm + (size_t)(k > 0 ? k - 1 : 0) * n_used;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x) {
-        int i0 = pairs[2 * p], i1 = pairs[2 * p + 1];
-        if (k > 0) { i0 = pk[i0]; i1 = pk[i1]; }
-        T[(size_t)k * n_pairs + p] = (uint32_t)map[i0] | ((uint32_t)map[i1] << 16);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs_pad; p += gridDim.x * blockDim.x) {
+        uint2 e = make_uint2(0u, 0u);
+        if (p < n_pairs) {
+            int i0 = pairs[2 * p], i1 = pairs[2 * p + 1];
+            if (k > 0) { i0 = pk[i0]; i1 = pk[i1]; }
+            e = make_uint2((uint32_t)map[i0] * 128u, (uint32_t)map[i1] * 128u);
+        }
+        T[(size_t)k * n_pairs_pad + p] = e;
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // score kernel
 // ------------------------------------------------------------------------------------------
-constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_THREADS = 512;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int TILE_CELLS = 64;
+constexpr int CHUNK_PAIRS = 64;                   // 64 pairs * 8 B = 512 B = one 16-byte cp.async per lane
+constexpr int STAGE_BYTES = 2 * CHUNK_PAIRS * 8;  // double buffer per warp
+constexpr uint32_t RANK_BIAS = 0x04000400u;       // ranks are stored as normal positive fp16 bit patterns
 
 struct ClassDesc {
-    const uint32_t *T;  // [iters+1][n_pairs]
-    int32_t n_pairs;
+    const uint2 *T;  // [iters+1][n_pairs_pad]
+    int32_t n_pairs_pad;
     int32_t pad;
 };
 
@@ -151,32 +162,75 @@ struct ScoreParams {
     int32_t *obs_total;
 };
 
-// counts of (a >= b) and (b >= a) for the two packed cells of a lane, over pairs [p0, p1) of T row
-__device__ __forceinline__ void eval_row(const uint32_t *__restrict__ tile, const uint32_t *__restrict__ Trow, int p0,
-                                         int p1, int lane, uint32_t &ge, uint32_t &le) {
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// per-half (x >= y) on fp16 bit patterns -> 0xFFFF / 0x0000 per half (SASS HSET2.GE)
+__device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) {
+    return __hge2_mask(*reinterpret_cast<const __half2 *>(&x), *reinterpret_cast<const __half2 *>(&y));
+}
+
+// Accumulate, for the two cells packed in this lane, -(mask of a >= b) and -(mask of b >= a) over the
+// chunks first, first + stride, ... < n_chunks of one table row.  Chunks are staged into this warp's
+// private double buffer with cp.async so that each 16-byte shared load broadcasts two pairs.
+__device__ __forceinline__ void eval_row(uint32_t tile_lane, const uint2 *__restrict__ Trow, int first, int stride,
+                                         int n_chunks, uint4 *stage, int lane, uint32_t &ge, uint32_t &le) {
     ge = 0;
     le = 0;
-    for (int pb = p0; pb < p1; pb += 32) {
-        const int p = pb + lane;
-        const uint32_t tv = (p < p1) ? __ldg(Trow + p) : 0u;
-        const int cnt = min(32, p1 - pb);
-        for (int j = 0; j < cnt; ++j) {
-            const uint32_t t = __shfl_sync(0xffffffffu, tv, j);
-            const uint32_t a = tile[(t & 0xffffu) * 32 + lane];
-            const uint32_t b = tile[(t >> 16) * 32 + lane];
-            // ranks < 2^15: bit 15 / 31 of (x | 0x8000) - y is (x >= y), no borrow crosses halves
-            ge += (((a | 0x80008000u) - b) >> 15) & 0x00010001u;
-            le += (((b | 0x80008000u) - a) >> 15) & 0x00010001u;
+    if (first >= n_chunks) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(Trow) + lane;  // 32 lanes x 16 B = one chunk
+    cp_async16(stage + lane, src + (size_t)first * 32);
+    cp_async_commit();
+    int buf = 0;
+    for (int c = first; c < n_chunks; c += stride) {
+        if (c + stride < n_chunks) {
+            cp_async16(stage + (buf ^ 1) * 32 + lane, src + (size_t)(c + stride) * 32);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
+        __syncwarp();
+        const uint4 *sb = stage + buf * 32;
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+            const uint4 v = sb[q];  // broadcast: two pairs
+            const uint32_t a0 = lds32(tile_lane + v.x), b0 = lds32(tile_lane + v.y);
+            const uint32_t a1 = lds32(tile_lane + v.z), b1 = lds32(tile_lane + v.w);
+            ge -= ge_mask(a0, b0);
+            le -= ge_mask(b0, a0);
+            ge -= ge_mask(a1, b1);
+            le -= ge_mask(b1, a1);
+        }
+        __syncwarp();  // every lane is done with `buf` before it is refilled
+        buf ^= 1;
     }
 }
 
+// acc = sum of -(mask): a true low half adds 1 to the low field and -1 to the high field, a true high
+// half adds 1 to the high field  =>  lo16 = n_lo, hi16 = n_hi - n_lo (mod 2^16); counts <= 65535.
+__device__ __forceinline__ void unpack_counts(uint32_t acc, int &n_lo, int &n_hi) {
+    n_lo = (int)(acc & 0xffffu);
+    n_hi = (int)(((acc >> 16) + (uint32_t)n_lo) & 0xffffu);
+}
+
 __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
-    extern __shared__ __align__(16) uint32_t tile[];  // [n_union][32]
-    __shared__ uint32_t s_ge[32], s_le[32];           // observed, packed halves
+    extern __shared__ __align__(128) uint8_t smem_dyn[];
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_dyn);  // [n_union][32] packed fp16-pattern ranks
+    __shared__ uint32_t s_ge[32], s_le[32];                   // observed accumulators (packed)
     __shared__ uint32_t s_below[TILE_CELLS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (size_t)P.n_union * 128 + (size_t)warp * STAGE_BYTES);
     const int64_t cell0 = (int64_t)blockIdx.x * TILE_CELLS;
     const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
 
@@ -187,31 +241,31 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
             const uint32_t lo = (c_lo < P.n_cells) ? r_lo[g] : 0u;
             const uint32_t hi = (c_hi < P.n_cells) ? r_hi[g] : 0u;
-            tile[g * 32 + lane] = lo | (hi << 16);
+            tile[g * 32 + lane] = (lo | (hi << 16)) + RANK_BIAS;
         }
     }
+    const uint32_t tile_lane = smem_u32(tile) + lane * 4;
 
     for (int cls = 0; cls < P.n_classes; ++cls) {
         const ClassDesc cd = P.classes[cls];
-        const int np = cd.n_pairs;
+        const int np = cd.n_pairs_pad, n_chunks = np / CHUNK_PAIRS;
         if (tid < 32) s_ge[tid] = 0, s_le[tid] = 0;
         if (tid < TILE_CELLS) s_below[tid] = 0;
         __syncthreads();  // also orders the tile stores before the first gather
-        // ---- observed proportion: the pairs of row 0 split over the warps (<= 65535 pairs per class)
+        // ---- observed proportion (row 0): chunks dealt to the warps, packed accumulators summed mod 2^32
         {
-            const int per = (np + SCORE_WARPS - 1) / SCORE_WARPS;
-            const int p0 = min(warp * per, np), p1 = min(p0 + per, np);
             uint32_t ge, le;
-            eval_row(tile, cd.T, p0, p1, lane, ge, le);
+            eval_row(tile_lane, cd.T, warp, SCORE_WARPS, n_chunks, stage, lane, ge, le);
             atomicAdd(&s_ge[lane], ge);
             atomicAdd(&s_le[lane], le);
         }
         __syncthreads();
-        const uint32_t oge = s_ge[lane], ole = s_le[lane];
-        // hits = #(a > b) = P - #(b >= a); total = #(a != b) = 2P - #(a >= b) - #(b >= a)
-        const int h0_lo = np - (int)(ole & 0xffffu), h0_hi = np - (int)(ole >> 16);
-        const int t0_lo = 2 * np - (int)(oge & 0xffffu) - (int)(ole & 0xffffu);
-        const int t0_hi = 2 * np - (int)(oge >> 16) - (int)(ole >> 16);
+        int oge_lo, oge_hi, ole_lo, ole_hi;
+        unpack_counts(s_ge[lane], oge_lo, oge_hi);
+        unpack_counts(s_le[lane], ole_lo, ole_hi);
+        // hits = #(a > b) = P - #(b >= a); total = #(a != b) = 2P - #(a >= b) - #(b >= a)   (P incl. padding ties)
+        const int h0_lo = np - ole_lo, h0_hi = np - ole_hi;
+        const int t0_lo = 2 * np - oge_lo - ole_lo, t0_hi = 2 * np - oge_hi - ole_hi;
         const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
         const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
         if (warp == 0) {
@@ -228,16 +282,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         uint32_t below_lo = 0, below_hi = 0;
         for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
             uint32_t ge, le;
-            eval_row(tile, cd.T + (size_t)k * np, 0, np, lane, ge, le);
-            const int h_lo = np - (int)(le & 0xffffu), h_hi = np - (int)(le >> 16);
-            const int t_lo = 2 * np - (int)(ge & 0xffffu) - (int)(le & 0xffffu);
-            const int t_hi = 2 * np - (int)(ge >> 16) - (int)(le >> 16);
+            eval_row(tile_lane, cd.T + (size_t)k * np, 0, 1, n_chunks, stage, lane, ge, le);
+            int ge_lo, ge_hi, le_lo, le_hi;
+            unpack_counts(ge, ge_lo, ge_hi);
+            unpack_counts(le, le_lo, le_hi);
+            const int h_lo = np - le_lo, h_hi = np - le_hi;
+            const int t_lo = 2 * np - ge_lo - le_lo, t_hi = 2 * np - ge_hi - le_hi;
             // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
-            if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) &&
-                (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
+            if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) && (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
                 ++below_lo;
-            if (ok_hi && !(h_hi < P.min_pairs || t_hi == 0) &&
-                (long long)h_hi * t0_hi < (long long)h0_hi * t_hi)
+            if (ok_hi && !(h_hi < P.min_pairs || t_hi == 0) && (long long)h_hi * t0_hi < (long long)h0_hi * t_hi)
                 ++below_hi;
         }
         atomicAdd(&s_below[lane], below_lo);
@@ -336,7 +390,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         const int64_t u0 = used_off[c], u1 = used_off[c + 1], p0 = pair_off[c], p1 = pair_off[c + 1];
         if (u1 < u0 || p1 < p0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: offsets must be non-decreasing");
         if (p1 - p0 == 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: class %d has no marker pairs", c);
-        if (p1 - p0 > 32767) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 32767 marker pairs", c);
+        if (p1 - p0 > 65472) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 65472 marker pairs", c);
         for (int64_t i = u0; i < u1; ++i) {
             if (used_idx[i] < 0 || used_idx[i] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx out of range");
             if (i > u0 && used_idx[i] <= used_idx[i - 1]) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx must ascend within a class");
@@ -348,10 +402,10 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     std::sort(uni.begin(), uni.end());
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
     const int U = (int)uni.size();
-    const size_t dyn_smem = (size_t)U * 32 * 4;
-    if (U > 32767 || dyn_smem + 1024 > (size_t)std::min(ctx->smem_optin, 227 * 1024))
+    const size_t dyn_smem = (size_t)U * 128 + (size_t)SCORE_WARPS * STAGE_BYTES;
+    if (U > 30000 || dyn_smem + 1024 > (size_t)std::min(ctx->smem_optin, 227 * 1024))
         return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: %d distinct marker genes exceed the shared-memory tile (max %d)", U,
-                       (std::min(ctx->smem_optin, 227 * 1024) - 1024) / 128);
+                       (std::min(ctx->smem_optin, 227 * 1024) - 1024 - SCORE_WARPS * STAGE_BYTES) / 128);
 
     PP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -419,13 +473,14 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         PP_CUDA(d_map[c].alloc(sizeof(uint16_t) * map.size(), st));
         PP_CUDA(cudaMemcpyAsync(d_map[c].p, map.data(), sizeof(uint16_t) * map.size(), cudaMemcpyHostToDevice, st));
         PP_CUDA(cudaStreamSynchronize(st));  // map is a local
-        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(iterations + 1) * np, st));
-        dim3 grid((np + 255) / 256, iterations + 1);
+        const int np_pad = (np + CHUNK_PAIRS - 1) / CHUNK_PAIRS * CHUNK_PAIRS;
+        PP_CUDA(d_T[c].alloc(sizeof(uint2) * (size_t)(iterations + 1) * np_pad, st));
+        dim3 grid((np_pad + 255) / 256, iterations + 1);
         build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_pairs[c].as<int32_t>(), d_map[c].as<uint16_t>(),
-                                                 nu, np, iterations, d_T[c].as<uint32_t>());
+                                                 nu, np, np_pad, d_T[c].as<uint2>());
         PP_CHECK_LAUNCH();
-        cds[c].T = d_T[c].as<uint32_t>();
-        cds[c].n_pairs = np;
+        cds[c].T = d_T[c].as<uint2>();
+        cds[c].n_pairs_pad = np_pad;
         cds[c].pad = 0;
     }
     PP_CUDA(d_cd.alloc(sizeof(ClassDesc) * n_classes, st));
