@@ -97,6 +97,12 @@ int pp_get_timings(pp_ctx *ctx, pp_timings *out);
  *              shard, ascending (== the reference's row-major np.where order,
  *              sandbag.py:129).  row/col index the KEPT genes.
  * out_class    *out_class = malloc'ed int32[n]: result[row, col].
+ * drop_unexpressed  != 0: gene_cols are CANDIDATES; the library first drops every
+ *              candidate whose column is zero in ALL n_rows rows of x (the
+ *              reference's ~np.all(data == 0, axis=0), utils.py:368, evaluated
+ *              before sample filtering) and returns the kept columns in
+ *              *out_kept_genes (malloc'ed int32[*out_n_kept]); row/col of the
+ *              keys then index that kept list.
  * probe_pairs  optional [n_probe,2] int64 (g1 < g2, kept-gene indices): the
  *              library writes num_pos / num_neg (sandbag.py:175-182) of those
  *              pairs to probe_pos / probe_neg [n_probe, n_classes] int32.
@@ -105,7 +111,8 @@ int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t
                int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
                int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
                int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
-               const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg);
+               const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
+               int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept);
 
 /*
  * pp_cyclone -- replaces the per-class loop over get_phase_scores

@@ -61,7 +61,8 @@ def load():
     lib.pp_free.restype = None
     lib.pp_get_timings.argtypes = [vp, c.POINTER(Timings)]
     lib.pp_sandbag.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i32, vp, i64, vp, i32, i32,
-                               c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp]
+                               c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp, i32, c.POINTER(vp),
+                               c.POINTER(i64)]
     lib.pp_cyclone.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32,
                                i32, u64, vp, vp, vp, vp]
     lib.pp_phase_scores.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp]
@@ -144,8 +145,12 @@ def matrix_arg(x):
     return x, ctypes.c_void_p(x.ctypes.data), code, 0, x.shape[0], x.shape[1], max(ld, x.shape[1])
 
 
-def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, device=None):
-    """-> (keys uint64[n], cls int32[n], timings dict[, probe_pos, probe_neg])"""
+def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, device=None,
+            drop_unexpressed=False):
+    """-> (keys uint64[n], cls int32[n], timings dict[, probe_pos, probe_neg][, kept_gene_cols])
+
+    drop_unexpressed=True: `gene_cols` are candidates, genes that are zero in every row of x are dropped on
+    the device and the kept columns are returned as the last element (keys index the kept list)."""
     lib, h = load(), ctx(device)
     keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
     cell_rows = np.ascontiguousarray(cell_rows, dtype=np.int32)
@@ -162,10 +167,16 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
         n_probe = len(pp)
         ppos = np.zeros((n_probe, len(class_sizes)), dtype=np.int32)
         pneg = np.zeros_like(ppos)
+    kg, kn = ctypes.c_void_p(), ctypes.c_int64()
     rc = lib.pp_sandbag(h, px, code, is_dev, n_rows, n_cols, ld, _ptr(cell_rows), len(cell_rows), _ptr(class_sizes),
                         len(class_sizes), _ptr(gene_cols), len(gene_cols), _ptr(thresholds), shard, n_shards,
                         ctypes.byref(ok), ctypes.byref(oc), ctypes.byref(on), _ptr(pp), n_probe, _ptr(ppos),
-                        _ptr(pneg))
+                        _ptr(pneg), 1 if drop_unexpressed else 0, ctypes.byref(kg), ctypes.byref(kn))
+    kept = None
+    if kg.value:
+        kept = np.ctypeslib.as_array(ctypes.cast(kg, ctypes.POINTER(ctypes.c_int32)), shape=(max(kn.value, 1),))[
+            :kn.value].copy()
+        lib.pp_free(kg)
     check(rc, h)
     n = on.value
     if n:
@@ -176,9 +187,12 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
     lib.pp_free(ok)
     lib.pp_free(oc)
     del keep
+    out = (keys, cls, timings(h))
     if probe_pairs is not None:
-        return keys, cls, timings(h), ppos, pneg
-    return keys, cls, timings(h)
+        out = out + (ppos, pneg)
+    if drop_unexpressed:
+        out = out + (kept if kept is not None else np.empty(0, dtype=np.int32),)
+    return out
 
 
 _RNG = {"mt19937": PP_RNG_MT19937, "philox": PP_RNG_PHILOX, "table": PP_RNG_TABLE}

@@ -152,7 +152,9 @@ struct ClassDesc {
 struct ScoreParams {
     const uint16_t *rank;  // [n_cells][rank_ld]
     int64_t rank_ld;
-    int64_t n_cells;
+    int64_t n_cells;  // cells of this launch
+    int64_t out_ld;   // cells of the whole call (row length of scores / obs_*)
+    int64_t out_off;  // first cell of this launch within the call
     int n_union;
     int n_classes;
     int iterations, min_iter, min_pairs;
@@ -270,12 +272,12 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
         if (warp == 0) {
             if (c_lo < P.n_cells) {
-                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.n_cells + c_lo] = h0_lo;
-                if (P.obs_total) P.obs_total[(int64_t)cls * P.n_cells + c_lo] = t0_lo;
+                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_lo] = h0_lo;
+                if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_lo] = t0_lo;
             }
             if (c_hi < P.n_cells) {
-                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.n_cells + c_hi] = h0_hi;
-                if (P.obs_total) P.obs_total[(int64_t)cls * P.n_cells + c_hi] = t0_hi;
+                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_hi] = h0_hi;
+                if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_hi] = t0_hi;
             }
         }
         // ---- permutation null: iterations dealt round-robin to the warps
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
             // total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
             double s = nan("");
             if (P.iterations >= P.min_iter && P.iterations > 0) s = (double)s_below[tid] / (double)P.iterations;
-            P.scores[(int64_t)cls * P.n_cells + cell0 + tid] = s;
+            P.scores[(int64_t)cls * P.out_ld + P.out_off + cell0 + tid] = s;
         }
         __syncthreads();
     }
@@ -412,18 +414,17 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
     const size_t esz = x_dtype == PP_F64 ? 8 : 4;
     DevBuf d_x, d_rows, d_uni, d_rank, d_flags, d_scores, d_oh, d_ot, d_cd;
-    const void *dx = (const uint8_t *)x + (size_t)row_begin * ld * esz;
-    if (!x_is_device) {
-        PP_CUDA(d_x.alloc((size_t)n_cells * ld * esz, st));
-        PP_CUDA(cudaMemcpyAsync(d_x.p, dx, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
-        dx = d_x.p;
-    }
-    PP_CUDA(cudaEventRecord(ctx->ev[1], st));
+    const uint8_t *x0 = (const uint8_t *)x + (size_t)row_begin * ld * esz;
+    // Host input is streamed in chunks of one full wave of 64-cell tiles: H2D of chunk i+1 (copy stream)
+    // overlaps rank + score of chunk i (compute stream).  Device input is processed in one launch.
+    const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
+    const bool pipelined = !x_is_device && n_cells > wave_cells;
+    const int64_t chunk_cells = pipelined ? wave_cells : n_cells;
     {
-        std::vector<int32_t> rows(n_cells);
-        for (int64_t i = 0; i < n_cells; ++i) rows[i] = (int32_t)i;
-        PP_CUDA(d_rows.alloc(sizeof(int32_t) * n_cells, st));
-        PP_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, st));
+        std::vector<int32_t> rows(chunk_cells);
+        for (int64_t i = 0; i < chunk_cells; ++i) rows[i] = (int32_t)i;
+        PP_CUDA(d_rows.alloc(sizeof(int32_t) * chunk_cells, st));
+        PP_CUDA(cudaMemcpyAsync(d_rows.p, rows.data(), sizeof(int32_t) * chunk_cells, cudaMemcpyHostToDevice, st));
         PP_CUDA(cudaStreamSynchronize(st));  // rows is a local
     }
     PP_CUDA(d_uni.alloc(sizeof(int32_t) * U, st));
@@ -432,10 +433,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(d_rank.alloc(sizeof(uint16_t) * n_cells * rank_ld, st));
     PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
     PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
-    int rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_uni.as<int32_t>(), U,
-                            d_rank.as<uint16_t>(), rank_ld, d_flags.as<int32_t>());
-    if (rc) return rc;
-    PP_CUDA(cudaEventRecord(ctx->ev[2], st));
+    int rc = PP_OK;
 
     // ---- per-class permutation + pair tables (host MT19937 work overlaps the rank kernel)
     std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_pairs(n_classes), d_map(n_classes);
@@ -489,12 +487,11 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(d_scores.alloc(sizeof(double) * out_cnt, st));
     if (out_obs_hits) PP_CUDA(d_oh.alloc(sizeof(int32_t) * out_cnt, st));
     if (out_obs_total) PP_CUDA(d_ot.alloc(sizeof(int32_t) * out_cnt, st));
-    PP_CUDA(cudaEventRecord(ctx->ev[3], st));
+    PP_CUDA(cudaEventRecord(ctx->ev[1], st));  // tables enqueued
 
     ScoreParams P;
-    P.rank = d_rank.as<uint16_t>();
     P.rank_ld = rank_ld;
-    P.n_cells = n_cells;
+    P.out_ld = n_cells;
     P.n_union = U;
     P.n_classes = n_classes;
     P.iterations = iterations;
@@ -505,9 +502,84 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
     P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
     PP_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    score_kernel<<<(unsigned)((n_cells + TILE_CELLS - 1) / TILE_CELLS), SCORE_THREADS, dyn_smem, st>>>(P);
-    PP_CHECK_LAUNCH();
-    PP_CUDA(cudaEventRecord(ctx->ev[4], st));
+    float score_ms = 0.f, copy_ms = 0.f;
+    if (!pipelined) {
+        const void *dx = x0;
+        if (!x_is_device) {
+            PP_CUDA(d_x.alloc((size_t)n_cells * ld * esz, st));
+            PP_CUDA(cudaEventRecord(ctx->ev[6], st));
+            PP_CUDA(cudaMemcpyAsync(d_x.p, x0, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
+            PP_CUDA(cudaEventRecord(ctx->ev[7], st));
+            dx = d_x.p;
+        }
+        rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_uni.as<int32_t>(), U,
+                            d_rank.as<uint16_t>(), rank_ld, d_flags.as<int32_t>());
+        if (rc) return rc;
+        PP_CUDA(cudaEventRecord(ctx->ev[3], st));
+        P.rank = d_rank.as<uint16_t>();
+        P.n_cells = n_cells;
+        P.out_off = 0;
+        score_kernel<<<(unsigned)((n_cells + TILE_CELLS - 1) / TILE_CELLS), SCORE_THREADS, dyn_smem, st>>>(P);
+        PP_CHECK_LAUNCH();
+        PP_CUDA(cudaEventRecord(ctx->ev[4], st));
+    } else {
+        DevBuf d_buf[2];
+        cudaEvent_t ev_copied[2], ev_free[2], ev_c0, ev_c1;
+        std::vector<cudaEvent_t> ev_s;
+        for (int b = 0; b < 2; ++b) {
+            PP_CUDA(d_buf[b].alloc((size_t)chunk_cells * ld * esz, st));
+            PP_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
+            PP_CUDA(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
+        }
+        PP_CUDA(cudaEventCreate(&ev_c0));
+        PP_CUDA(cudaEventCreate(&ev_c1));
+        PP_CUDA(cudaEventRecord(ctx->ev[3], st));
+        PP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[3], 0));  // buffers exist before the first copy
+        PP_CUDA(cudaEventRecord(ev_c0, ctx->copy_stream));
+        int i = 0;
+        for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, ++i) {
+            const int b = i & 1;
+            const int64_t nc = std::min(chunk_cells, n_cells - c0);
+            if (i >= 2) PP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev_free[b], 0));
+            PP_CUDA(cudaMemcpyAsync(d_buf[b].p, x0 + (size_t)c0 * ld * esz, (size_t)nc * ld * esz, cudaMemcpyHostToDevice,
+                                    ctx->copy_stream));
+            PP_CUDA(cudaEventRecord(ev_copied[b], ctx->copy_stream));
+            PP_CUDA(cudaStreamWaitEvent(st, ev_copied[b], 0));
+            rc = pp_rank_launch(ctx, d_buf[b].p, x_dtype, ld, d_rows.as<int32_t>(), nc, d_uni.as<int32_t>(), U,
+                                d_rank.as<uint16_t>() + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            if (rc) return rc;
+            PP_CUDA(cudaEventRecord(ev_free[b], st));
+            cudaEvent_t e0, e1;
+            PP_CUDA(cudaEventCreate(&e0));
+            PP_CUDA(cudaEventCreate(&e1));
+            ev_s.push_back(e0);
+            ev_s.push_back(e1);
+            P.rank = d_rank.as<uint16_t>() + c0 * rank_ld;
+            P.n_cells = nc;
+            P.out_off = c0;
+            PP_CUDA(cudaEventRecord(e0, st));
+            score_kernel<<<(unsigned)((nc + TILE_CELLS - 1) / TILE_CELLS), SCORE_THREADS, dyn_smem, st>>>(P);
+            PP_CHECK_LAUNCH();
+            PP_CUDA(cudaEventRecord(e1, st));
+        }
+        PP_CUDA(cudaEventRecord(ev_c1, ctx->copy_stream));
+        PP_CUDA(cudaEventRecord(ctx->ev[4], st));
+        PP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        PP_CUDA(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
+        for (size_t j = 0; j + 1 < ev_s.size(); j += 2) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev_s[j], ev_s[j + 1]);
+            score_ms += ms;
+        }
+        for (cudaEvent_t e : ev_s) cudaEventDestroy(e);
+        for (int b = 0; b < 2; ++b) {
+            cudaEventDestroy(ev_copied[b]);
+            cudaEventDestroy(ev_free[b]);
+        }
+        cudaEventDestroy(ev_c0);
+        cudaEventDestroy(ev_c1);
+    }
     PP_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, sizeof(double) * out_cnt, cudaMemcpyDeviceToHost, st));
     if (out_obs_hits) PP_CUDA(cudaMemcpyAsync(out_obs_hits, d_oh.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));
     if (out_obs_total) PP_CUDA(cudaMemcpyAsync(out_obs_total, d_ot.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));
@@ -516,9 +588,18 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(cudaEventRecord(ctx->ev[5], st));
     PP_CUDA(cudaStreamSynchronize(st));
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_cyclone: NaN in the expression matrix");
-    cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ctx->tm.prep_ms, ctx->ev[1], ctx->ev[3]);
-    cudaEventElapsedTime(&ctx->tm.main_ms, ctx->ev[3], ctx->ev[4]);
+    if (pipelined) {  // copies overlap compute: h2d = copy-stream span, main = sum of the score launches
+        ctx->tm.h2d_ms = copy_ms;
+        ctx->tm.main_ms = score_ms;
+        cudaEventElapsedTime(&ctx->tm.prep_ms, ctx->ev[0], ctx->ev[1]);
+    } else {
+        float t_tab = 0.f, t_rank = 0.f;
+        if (!x_is_device) cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[6], ctx->ev[7]);
+        cudaEventElapsedTime(&t_tab, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&t_rank, ctx->ev[1], ctx->ev[3]);
+        ctx->tm.prep_ms = t_tab + t_rank - ctx->tm.h2d_ms;
+        cudaEventElapsedTime(&ctx->tm.main_ms, ctx->ev[3], ctx->ev[4]);
+    }
     cudaEventElapsedTime(&ctx->tm.post_ms, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[5]);
     ctx->tm.n_launches = ctx->launches;

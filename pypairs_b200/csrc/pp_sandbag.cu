@@ -25,6 +25,22 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------
+// nz[g] = 1 if any row of column g is != 0  (the reference's ~np.all(data == 0, axis=0), utils.py:368)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+col_nonzero_kernel(const T *__restrict__ x, int64_t ld, int64_t n_rows, int64_t n_cols, uint8_t *__restrict__ nz) {
+    const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_cols) return;
+    bool any = false;
+    for (int64_t r0 = (int64_t)blockIdx.y * 64; r0 < n_rows && !any; r0 += (int64_t)gridDim.y * 64) {
+        const int64_t r1 = min(r0 + 64, n_rows);
+        for (int64_t r = r0; r < r1; ++r) any |= (x[r * ld + g] != (T)0);
+    }
+    if (any) nz[g] = 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // bit-slice: rank[32W][G] -> planes[NB][W][B][64]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -403,7 +419,8 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
                       int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
                       int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
                       int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
-                      const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg) {
+                      const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
+                      int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
     if (!x || !cell_rows || !class_sizes || !gene_cols || !thresholds || !out_keys || !out_class || !out_n)
         return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
@@ -429,12 +446,51 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         if (cell_rows[i] < 0 || cell_rows[i] >= n_rows) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: cell_rows[%lld] out of range", (long long)i);
     for (int64_t g = 0; g < n_genes; ++g)
         if (gene_cols[g] < 0 || gene_cols[g] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: gene_cols[%lld] out of range", (long long)g);
-    if (n_genes < 2 || n_cells == 0) return PP_OK;  // no pairs
-    if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65535 kept genes");
+    if (drop_unexpressed && (!out_kept_genes || !out_n_kept))
+        return pp_fail(ctx, PP_EINVAL, "pp_sandbag: drop_unexpressed needs out_kept_genes / out_n_kept");
+    if (out_kept_genes) *out_kept_genes = nullptr;
+    if (out_n_kept) *out_n_kept = 0;
 
     PP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
+    DevBuf d_x, d_slots, d_gene, d_rank, d_flags, d_planes, d_chunks, d_tiles, d_thr, d_out, d_out2, d_cnt;
+    const size_t esz = x_dtype == PP_F64 ? 8 : 4;
+    const void *dx = x;
+    if (!x_is_device) {
+        PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
+        PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
+        dx = d_x.p;
+    }
+    PP_CUDA(cudaEventRecord(ctx->ev[1], st));
+
+    // ---- optional: drop genes that are zero in ALL rows of x (utils.py:368, before sample filtering)
+    std::vector<int32_t> kept;
+    if (drop_unexpressed) {
+        DevBuf d_nz;
+        PP_CUDA(d_nz.alloc((size_t)n_cols, st));
+        PP_CUDA(cudaMemsetAsync(d_nz.p, 0, (size_t)n_cols, st));
+        dim3 grid((unsigned)((n_cols + 255) / 256), (unsigned)std::min<int64_t>((n_rows + 63) / 64, 65535));
+        if (x_dtype == PP_F64)
+            col_nonzero_kernel<double><<<grid, 256, 0, st>>>((const double *)dx, ld, n_rows, n_cols, d_nz.as<uint8_t>());
+        else
+            col_nonzero_kernel<float><<<grid, 256, 0, st>>>((const float *)dx, ld, n_rows, n_cols, d_nz.as<uint8_t>());
+        PP_CHECK_LAUNCH();
+        std::vector<uint8_t> nz((size_t)n_cols);
+        PP_CUDA(cudaMemcpyAsync(nz.data(), d_nz.p, (size_t)n_cols, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+        for (int64_t g = 0; g < n_genes; ++g)
+            if (nz[gene_cols[g]]) kept.push_back(gene_cols[g]);
+        gene_cols = kept.data();
+        n_genes = (int64_t)kept.size();
+        int32_t *hk = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(n_genes, 1));
+        if (!hk) return pp_fail(ctx, PP_ENOMEM, "pp_sandbag: host allocation failed");
+        std::copy(kept.begin(), kept.end(), hk);
+        *out_kept_genes = hk;
+        *out_n_kept = n_genes;
+    }
+    if (n_genes < 2 || n_cells == 0) return PP_OK;  // no pairs
+    if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65535 kept genes");
 
     // ---- host-side layout tables: padded slots, chunks, tiles
     std::vector<int32_t> slots;
@@ -453,16 +509,6 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     const int NB = (int)((n_genes + 63) / 64);
     const int NB_alloc = (NB + 1) & ~1;
 
-    // ---- device buffers
-    DevBuf d_x, d_slots, d_gene, d_rank, d_flags, d_planes, d_chunks, d_tiles, d_thr, d_out, d_out2, d_cnt;
-    const size_t esz = x_dtype == PP_F64 ? 8 : 4;
-    const void *dx = x;
-    if (!x_is_device) {
-        PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
-        PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
-        dx = d_x.p;
-    }
-    PP_CUDA(cudaEventRecord(ctx->ev[1], st));
     PP_CUDA(d_slots.alloc(sizeof(int32_t) * n_slots, st));
     PP_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
     PP_CUDA(d_gene.alloc(sizeof(int32_t) * n_genes, st));

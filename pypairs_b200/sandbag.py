@@ -20,14 +20,16 @@ def prepare(data, annotation=None, gene_names=None, sample_names=None, fraction=
             filter_samples=None):
     """Everything sandbag.py:98-122 derives before calling the kernel, as index arrays.
 
-    Returns a dict with: raw (matrix as given), kept gene names, class names (non-empty, in order),
-    gene_cols (kept gene columns, ascending), cell_rows (kept samples, class-sorted),
-    class_sizes, thresholds.
+    Returns a dict with: raw (matrix as given), all gene names, class names (non-empty, in order),
+    gene_cols (candidate gene columns after `filter_genes`, ascending -- the all-zero-gene test of
+    utils.py:368 needs a pass over the matrix and is done on the device), cell_rows (kept samples,
+    class-sorted), class_sizes, thresholds.
     """
     raw, gene_names, sample_names, class_names, cats = utils.parse_data_and_annotation(
         data, annotation, gene_names, sample_names)
-    gene_mask, sample_mask = utils.get_filter_masks(raw, gene_names, sample_names, cats, filter_genes, filter_samples)
-    kept_gene_names = np.array(gene_names)[gene_mask]
+    gene_mask = utils.to_boolean_mask(filter_genes, gene_names)
+    sample_mask = np.logical_and(np.any(cats, axis=0), utils.to_boolean_mask(filter_samples, sample_names))
+    kept_gene_names = np.array(gene_names)
     cats = cats[:, sample_mask]
     rows_kept = np.where(sample_mask)[0]
     # remove_empty_categories (sandbag.py:202-209)
@@ -55,12 +57,13 @@ def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
         return {}
     rows = (keys // np.uint64(n_genes)).astype(np.int64)
     cols = (keys % np.uint64(n_genes)).astype(np.int64)
-    a, b = gene_names[rows], gene_names[cols]
+    names = np.empty(len(gene_names), dtype=object)  # the np.str_ scalars `gene_names[g]` yields, made once
+    names[:] = [gene_names[i] for i in range(len(gene_names))]
     _, first = np.unique(cls, return_index=True)
     out = {}
     for k in cls[np.sort(first)]:
         m = cls == k
-        out[class_names[k]] = list(zip(a[m], b[m]))
+        out[class_names[k]] = list(zip(names[rows[m]].tolist(), names[cols[m]].tolist()))
     return out
 
 
@@ -81,13 +84,13 @@ def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=
     logg.hint("sandbag running with fraction of {}".format(fraction))
     p = prepare(data, annotation, gene_names, sample_names, fraction, filter_genes, filter_samples)
     rank, ws = _dist.world()
-    keys, cls, tm = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
-                                 shard=rank, n_shards=ws)
+    keys, cls, tm, kept = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
+                                       shard=rank, n_shards=ws, drop_unexpressed=True)
     if ws > 1:
         keys, cls = _dist.allgather_varlen((keys, cls))
         order = np.argsort(keys, kind="stable")
         keys, cls = keys[order], cls[order]
-    out = markers_to_dict(keys, cls, len(p["gene_cols"]), p["gene_names"], p["class_names"])
+    out = markers_to_dict(keys, cls, len(kept), p["gene_names"][kept], p["class_names"])
     logg.info("finished", time_=True)
     logg.hint("found {} marker pairs ({})".format(len(keys), ", ".join(
         "{}: {}".format(k, len(v)) for k, v in out.items())))

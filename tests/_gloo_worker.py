@@ -20,13 +20,16 @@ calls = {"sandbag": [], "cyclone": []}
 
 def fake_sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, **kw):
     calls["sandbag"].append((shard, n_shards))
+    x = np.asarray(x, dtype=np.float64)
+    gene_cols = np.asarray(gene_cols)
+    if kw.get("drop_unexpressed"):
+        gene_cols = gene_cols[(x != 0).any(axis=0)[gene_cols]]
     cats = np.concatenate([np.full(n, k) for k, n in enumerate(class_sizes)])
-    res = orc.check_pairs(np.asarray(x, dtype=np.float64)[np.asarray(cell_rows)][:, np.asarray(gene_cols)], cats,
-                          np.asarray(thresholds))
+    res = orc.check_pairs(x[np.asarray(cell_rows)][:, gene_cols], cats, np.asarray(thresholds))
     r, c = np.where(res != -1)
     keys = (r * len(gene_cols) + c).astype(np.uint64)
     sel = ((r // 7 + c // 5) % n_shards) == shard  # some tile-like split of the pair space
-    return keys[sel], res[r, c].astype(np.int32)[sel], {}
+    return keys[sel], res[r, c].astype(np.int32)[sel], {}, gene_cols.astype(np.int32)
 
 
 def fake_cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,

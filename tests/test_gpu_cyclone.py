@@ -163,3 +163,27 @@ def test_full_size_slice_properties():
     for i, k in enumerate(ks):
         assert np.array_equal(sc[i, rows], orc.phase_scores(xs, 1000, 100, 50, pairs[k], used[k]))
     print("cfg2 slice 4096 cells: score kernel {:.1f} ms, prep {:.1f} ms".format(tm["main_ms"], tm["prep_ms"]))
+
+
+def test_host_input_is_streamed_in_chunks():
+    """Host matrices larger than one wave of tiles take the copy/compute-overlapped path: same scores."""
+    import torch
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(46)
+    markers, names, _ = default_setup(rng, 1, 1700)
+    n = 148 * 64 * 2 + 777
+    x = rng.poisson(2.0, (n, 1700)).astype(np.float32)
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    s_host, tm_h, oh, ot = _ffi().cyclone(x, u, p, 40, 10, 5, want_observed=True)
+    s_dev, tm_d, oh2, ot2 = _ffi().cyclone(torch.from_numpy(x).cuda(), u, p, 40, 10, 5, want_observed=True)
+    assert np.array_equal(s_host, s_dev, equal_nan=True)
+    assert np.array_equal(oh, oh2) and np.array_equal(ot, ot2)
+    pin = torch.from_numpy(x).pin_memory()
+    s_pin, _ = _ffi().cyclone(pin.numpy(), u, p, 40, 10, 5)
+    assert np.array_equal(s_pin, s_dev, equal_nan=True)
+    rows = np.sort(rng.choice(n, 40, replace=False))
+    for i, k in enumerate(ks):
+        assert np.array_equal(s_host[i, rows], orc.phase_scores(x[rows], 40, 10, 5, pairs[k], used[k]))

@@ -48,13 +48,16 @@ def _emulated_sandbag(monkeypatch):
 
     def fake(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, **kw):
         x = np.asarray(x, dtype=np.float64)
+        gene_cols = np.asarray(gene_cols)
+        if kw.get("drop_unexpressed"):
+            gene_cols = gene_cols[(x != 0).any(axis=0)[gene_cols]]
         cats = np.concatenate([np.full(n, k) for k, n in enumerate(class_sizes)])
-        res = orc.check_pairs(x[np.asarray(cell_rows)][:, np.asarray(gene_cols)], cats, np.asarray(thresholds))
+        res = orc.check_pairs(x[np.asarray(cell_rows)][:, gene_cols], cats, np.asarray(thresholds))
         r, c = np.where(res != -1)
         keys = (r * len(gene_cols) + c).astype(np.uint64)
         cls = res[r, c].astype(np.int32)
         sel = (np.arange(len(keys)) % n_shards) == shard
-        return keys[sel], cls[sel], {}
+        return keys[sel], cls[sel], {}, gene_cols.astype(np.int32)
 
     monkeypatch.setattr(_ffi, "sandbag", fake)
 
