@@ -113,23 +113,103 @@ __global__ void philox_perm_kernel(uint16_t *__restrict__ table, int n, int iter
     }
 }
 
-// T[k][p] = byte offsets (128 * union position) of the two genes pair p compares in iteration k
-// (k = 0: identity = the observed pairs).  Rows are padded to a multiple of 64 pairs with (0, 0)
-// entries: a padding pair compares a gene with itself, i.e. is a tie, and ties are counted on
-// both sides of the (>=, <=) bookkeeping, so they cancel exactly (see score_kernel).
-__global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int32_t *__restrict__ pairs,
-                                   const uint16_t *__restrict__ map, int n_used, int n_pairs, int n_pairs_pad,
-                                   uint2 *__restrict__ T) {
+// Star layout.  The pairs of a class are regrouped (host, once per call) into "stars": a hub gene and
+// all still-uncovered pairs that have it on one fixed side (greedy max-degree cover; the default
+// markers need 653 hubs for 8 142 pairs).  The kernel then loads the hub once per star and one value
+// per pair instead of two.  The stream of a class is a sequence of 4-slot vectors:
+//     [hub o1 o2 o3] [o4 o5 o6 o7] ... [.. hub hub]      (a star; padded with the hub itself)
+// every slot is compared against the current hub; hub and padding slots are ties and ties are counted
+// on both sides of the (>=, <=) bookkeeping, so they cancel exactly.  Section A holds the stars whose
+// hub is the FIRST gene of its pairs, section B those whose hub is the SECOND gene (roles of the two
+// counters swap); both are padded to whole 128-slot chunks and every chunk restarts its hub, so a chunk
+// is self-contained.  E[k][s] = byte offset (128 * union position) of slot s under permutation k
+// (k = 0: identity = observed).
+constexpr int CHUNK_SLOTS = 128;                  // 128 slots * 4 B = 512 B = one 16-byte cp.async per lane
+constexpr int STAGE_BYTES = 2 * CHUNK_SLOTS * 4;  // double buffer per warp
+
+struct StarLayout {
+    std::vector<int32_t> slot_src;     // class-compact gene index of every slot
+    std::vector<uint32_t> start_mask;  // per chunk: bit q set = vector q starts a star (slot 4q is a hub)
+    int n_chunks_a = 0, n_chunks = 0;
+};
+
+StarLayout build_star_layout(const int32_t *pairs, int np, int nu) {
+    std::vector<std::vector<int>> adj[2];
+    adj[0].resize(nu);
+    adj[1].resize(nu);
+    for (int i = 0; i < np; ++i) {
+        adj[0][pairs[2 * i]].push_back(i);
+        adj[1][pairs[2 * i + 1]].push_back(i);
+    }
+    std::vector<int> deg[2];
+    for (int sd = 0; sd < 2; ++sd) {
+        deg[sd].resize(nu);
+        for (int g = 0; g < nu; ++g) deg[sd][g] = (int)adj[sd][g].size();
+    }
+    std::vector<char> covered(np, 0);
+    struct Star { int hub, side; std::vector<int> others; };
+    std::vector<Star> stars;
+    for (;;) {
+        int best = 0, bg = -1, bs = 0;
+        for (int sd = 0; sd < 2; ++sd)
+            for (int g = 0; g < nu; ++g)
+                if (deg[sd][g] > best) { best = deg[sd][g]; bg = g; bs = sd; }
+        if (bg < 0) break;
+        Star st;
+        st.hub = bg;
+        st.side = bs;
+        for (int i : adj[bs][bg]) {
+            if (covered[i]) continue;
+            covered[i] = 1;
+            const int other = pairs[2 * i + (bs == 0 ? 1 : 0)];
+            st.others.push_back(other);
+            deg[1 - bs][other] -= 1;  // the pair leaves the other endpoint's opposite-side star
+        }
+        deg[bs][bg] = 0;
+        stars.push_back(st);
+    }
+    StarLayout L;
+    auto pad_to_chunk = [&]() {
+        while (L.slot_src.size() % CHUNK_SLOTS) {
+            if (L.slot_src.size() % 4 == 0) {
+                const size_t s = L.slot_src.size();
+                L.start_mask[s / CHUNK_SLOTS] |= 1u << ((s % CHUNK_SLOTS) / 4);
+            }
+            L.slot_src.push_back(0);  // gene 0 against itself: ties
+        }
+    };
+    auto emit_hub = [&](int hub) {
+        const size_t s = L.slot_src.size();
+        if (s % CHUNK_SLOTS == 0) L.start_mask.push_back(0u);
+        L.start_mask[s / CHUNK_SLOTS] |= 1u << ((s % CHUNK_SLOTS) / 4);
+        L.slot_src.push_back(hub);
+    };
+    for (int side = 0; side < 2; ++side) {
+        for (const Star &st : stars) {
+            if (st.side != side) continue;
+            emit_hub(st.hub);
+            for (int o : st.others) {
+                if (L.slot_src.size() % CHUNK_SLOTS == 0) emit_hub(st.hub);  // chunks are self-contained
+                L.slot_src.push_back(o);
+            }
+            while (L.slot_src.size() % 4) L.slot_src.push_back(st.hub);
+        }
+        pad_to_chunk();
+        if (side == 0) L.n_chunks_a = (int)(L.slot_src.size() / CHUNK_SLOTS);
+    }
+    L.n_chunks = (int)(L.slot_src.size() / CHUNK_SLOTS);
+    return L;
+}
+
+__global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int32_t *__restrict__ slot_src,
+                                   const uint16_t *__restrict__ map, int n_used, int n_slots,
+                                   uint32_t *__restrict__ E) {
     const int k = blockIdx.y;
     const uint16_t *pk = perm + (size_t)(k > 0 ? k - 1 : 0) * n_used;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs_pad; p += gridDim.x * blockDim.x) {
-        uint2 e = make_uint2(0u, 0u);
-        if (p < n_pairs) {
-            int i0 = pairs[2 * p], i1 = pairs[2 * p + 1];
-            if (k > 0) { i0 = pk[i0]; i1 = pk[i1]; }
-            e = make_uint2((uint32_t)map[i0] * 128u, (uint32_t)map[i1] * 128u);
-        }
-        T[(size_t)k * n_pairs_pad + p] = e;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
+        int g = slot_src[s];
+        if (k > 0) g = pk[g];
+        E[(size_t)k * n_slots + s] = (uint32_t)map[g] * 128u;
     }
 }
 
@@ -139,14 +219,12 @@ __global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int3
 constexpr int SCORE_THREADS = 512;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int TILE_CELLS = 64;
-constexpr int CHUNK_PAIRS = 64;                   // 64 pairs * 8 B = 512 B = one 16-byte cp.async per lane
-constexpr int STAGE_BYTES = 2 * CHUNK_PAIRS * 8;  // double buffer per warp
-constexpr uint32_t RANK_BIAS = 0x04000400u;       // ranks are stored as normal positive fp16 bit patterns
+constexpr uint32_t RANK_BIAS = 0x04000400u;  // ranks are stored as normal positive fp16 bit patterns
 
 struct ClassDesc {
-    const uint2 *T;  // [iters+1][n_pairs_pad]
-    int32_t n_pairs_pad;
-    int32_t pad;
+    const uint32_t *E;           // [iters+1][n_slots]
+    const uint32_t *start_mask;  // [n_chunks]
+    int32_t n_slots, n_chunks, n_chunks_a, pad;
 };
 
 struct ScoreParams {
@@ -181,20 +259,21 @@ __device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) {
     return __hge2_mask(*reinterpret_cast<const __half2 *>(&x), *reinterpret_cast<const __half2 *>(&y));
 }
 
-// Accumulate, for the two cells packed in this lane, -(mask of a >= b) and -(mask of b >= a) over the
-// chunks first, first + stride, ... < n_chunks of one table row.  Chunks are staged into this warp's
-// private double buffer with cp.async so that each 16-byte shared load broadcasts two pairs.
-__device__ __forceinline__ void eval_row(uint32_t tile_lane, const uint2 *__restrict__ Trow, int first, int stride,
-                                         int n_chunks, uint4 *stage, int lane, uint32_t &ge, uint32_t &le) {
-    ge = 0;
-    le = 0;
-    if (first >= n_chunks) return;
-    const uint4 *src = reinterpret_cast<const uint4 *>(Trow) + lane;  // 32 lanes x 16 B = one chunk
+// For the two cells packed in this lane accumulate X -= mask(hub >= v), Y -= mask(v >= hub) over the slots
+// of chunks first, first + stride, ... < last of one table row.  Chunks are staged into this warp's private
+// double buffer with cp.async; one broadcast LDS.128 fetches four slot offsets.
+__device__ __forceinline__ void eval_chunks(uint32_t tile_lane, const uint32_t *__restrict__ Erow,
+                                            const uint32_t *__restrict__ start_mask, int first, int stride, int last,
+                                            uint4 *stage, int lane, uint32_t &X, uint32_t &Y) {
+    if (first >= last) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(Erow) + lane;  // 32 lanes x 16 B = one chunk
     cp_async16(stage + lane, src + (size_t)first * 32);
     cp_async_commit();
     int buf = 0;
-    for (int c = first; c < n_chunks; c += stride) {
-        if (c + stride < n_chunks) {
+    uint32_t h = 0;
+    for (int c = first; c < last; c += stride) {
+        const uint32_t sm = __ldg(start_mask + c);
+        if (c + stride < last) {
             cp_async16(stage + (buf ^ 1) * 32 + lane, src + (size_t)(c + stride) * 32);
             cp_async_commit();
             cp_async_wait<1>();
@@ -205,17 +284,37 @@ __device__ __forceinline__ void eval_row(uint32_t tile_lane, const uint2 *__rest
         const uint4 *sb = stage + buf * 32;
 #pragma unroll 8
         for (int q = 0; q < 32; ++q) {
-            const uint4 v = sb[q];  // broadcast: two pairs
-            const uint32_t a0 = lds32(tile_lane + v.x), b0 = lds32(tile_lane + v.y);
-            const uint32_t a1 = lds32(tile_lane + v.z), b1 = lds32(tile_lane + v.w);
-            ge -= ge_mask(a0, b0);
-            le -= ge_mask(b0, a0);
-            ge -= ge_mask(a1, b1);
-            le -= ge_mask(b1, a1);
+            const uint4 v = sb[q];  // broadcast: four slots
+            const uint32_t e0 = lds32(tile_lane + v.x), e1 = lds32(tile_lane + v.y);
+            const uint32_t e2 = lds32(tile_lane + v.z), e3 = lds32(tile_lane + v.w);
+            if ((sm >> q) & 1u) h = e0;  // warp-uniform: this vector opens a star
+            X -= ge_mask(h, e0);
+            Y -= ge_mask(e0, h);
+            X -= ge_mask(h, e1);
+            Y -= ge_mask(e1, h);
+            X -= ge_mask(h, e2);
+            Y -= ge_mask(e2, h);
+            X -= ge_mask(h, e3);
+            Y -= ge_mask(e3, h);
         }
         __syncwarp();  // every lane is done with `buf` before it is refilled
         buf ^= 1;
     }
+}
+
+// One table row: section A counts (ge, le) directly, section B (hub = second gene) with the roles swapped.
+__device__ __forceinline__ void eval_row(uint32_t tile_lane, const uint32_t *__restrict__ Erow, const ClassDesc &cd,
+                                         int first, int stride, uint4 *stage, int lane, uint32_t &ge, uint32_t &le) {
+    ge = 0;
+    le = 0;
+    eval_chunks(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, ge, le);
+    int fb = first;  // first chunk of this warp's stride pattern inside section B
+    if (stride > 1) {
+        while (fb < cd.n_chunks_a) fb += stride;
+    } else {
+        fb = cd.n_chunks_a;
+    }
+    eval_chunks(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, le, ge);
 }
 
 // acc = sum of -(mask): a true low half adds 1 to the low field and -1 to the high field, a true high
@@ -250,14 +349,14 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
 
     for (int cls = 0; cls < P.n_classes; ++cls) {
         const ClassDesc cd = P.classes[cls];
-        const int np = cd.n_pairs_pad, n_chunks = np / CHUNK_PAIRS;
+        const int np = cd.n_slots;  // slots = pairs + ties (hubs, padding); ties cancel below
         if (tid < 32) s_ge[tid] = 0, s_le[tid] = 0;
         if (tid < TILE_CELLS) s_below[tid] = 0;
         __syncthreads();  // also orders the tile stores before the first gather
         // ---- observed proportion (row 0): chunks dealt to the warps, packed accumulators summed mod 2^32
         {
             uint32_t ge, le;
-            eval_row(tile_lane, cd.T, warp, SCORE_WARPS, n_chunks, stage, lane, ge, le);
+            eval_row(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane, ge, le);
             atomicAdd(&s_ge[lane], ge);
             atomicAdd(&s_le[lane], le);
         }
@@ -265,7 +364,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         int oge_lo, oge_hi, ole_lo, ole_hi;
         unpack_counts(s_ge[lane], oge_lo, oge_hi);
         unpack_counts(s_le[lane], ole_lo, ole_hi);
-        // hits = #(a > b) = P - #(b >= a); total = #(a != b) = 2P - #(a >= b) - #(b >= a)   (P incl. padding ties)
+        // hits = #(a > b) = S - #(b >= a); total = #(a != b) = 2S - #(a >= b) - #(b >= a)   (S = slots incl. ties)
         const int h0_lo = np - ole_lo, h0_hi = np - ole_hi;
         const int t0_lo = 2 * np - oge_lo - ole_lo, t0_hi = 2 * np - oge_hi - ole_hi;
         const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
@@ -284,7 +383,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         uint32_t below_lo = 0, below_hi = 0;
         for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
             uint32_t ge, le;
-            eval_row(tile_lane, cd.T + (size_t)k * np, 0, 1, n_chunks, stage, lane, ge, le);
+            eval_row(tile_lane, cd.E + (size_t)k * np, cd, 0, 1, stage, lane, ge, le);
             int ge_lo, ge_hi, le_lo, le_hi;
             unpack_counts(ge, ge_lo, ge_hi);
             unpack_counts(le, le_lo, le_hi);
@@ -392,7 +491,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         const int64_t u0 = used_off[c], u1 = used_off[c + 1], p0 = pair_off[c], p1 = pair_off[c + 1];
         if (u1 < u0 || p1 < p0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: offsets must be non-decreasing");
         if (p1 - p0 == 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: class %d has no marker pairs", c);
-        if (p1 - p0 > 65472) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 65472 marker pairs", c);
+        if (p1 - p0 > 60000) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 60000 marker pairs", c);
         for (int64_t i = u0; i < u1; ++i) {
             if (used_idx[i] < 0 || used_idx[i] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx out of range");
             if (i > u0 && used_idx[i] <= used_idx[i - 1]) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx must ascend within a class");
@@ -436,7 +535,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     int rc = PP_OK;
 
     // ---- per-class permutation + pair tables (host MT19937 work overlaps the rank kernel)
-    std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_pairs(n_classes), d_map(n_classes);
+    std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_src(n_classes), d_mask(n_classes), d_map(n_classes);
     std::vector<ClassDesc> cds(n_classes);
     const int32_t *ext = perm_tables;
     for (int c = 0; c < n_classes; ++c) {
@@ -466,19 +565,28 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, st));
             PP_CUDA(cudaStreamSynchronize(st));  // t is a local
         }
-        PP_CUDA(d_pairs[c].alloc(sizeof(int32_t) * 2 * np, st));
-        PP_CUDA(cudaMemcpyAsync(d_pairs[c].p, pairs + 2 * pair_off[c], sizeof(int32_t) * 2 * np, cudaMemcpyHostToDevice, st));
         PP_CUDA(d_map[c].alloc(sizeof(uint16_t) * map.size(), st));
         PP_CUDA(cudaMemcpyAsync(d_map[c].p, map.data(), sizeof(uint16_t) * map.size(), cudaMemcpyHostToDevice, st));
         PP_CUDA(cudaStreamSynchronize(st));  // map is a local
-        const int np_pad = (np + CHUNK_PAIRS - 1) / CHUNK_PAIRS * CHUNK_PAIRS;
-        PP_CUDA(d_T[c].alloc(sizeof(uint2) * (size_t)(iterations + 1) * np_pad, st));
-        dim3 grid((np_pad + 255) / 256, iterations + 1);
-        build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_pairs[c].as<int32_t>(), d_map[c].as<uint16_t>(),
-                                                 nu, np, np_pad, d_T[c].as<uint2>());
+        const StarLayout L = build_star_layout(pairs + 2 * pair_off[c], np, nu);
+        const int n_slots = (int)L.slot_src.size();
+        if (n_slots > 65535)
+            return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d needs %d comparison slots (max 65535)", c, n_slots);
+        PP_CUDA(d_src[c].alloc(sizeof(int32_t) * n_slots, st));
+        PP_CUDA(cudaMemcpyAsync(d_src[c].p, L.slot_src.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_mask[c].alloc(sizeof(uint32_t) * L.n_chunks, st));
+        PP_CUDA(cudaMemcpyAsync(d_mask[c].p, L.start_mask.data(), sizeof(uint32_t) * L.n_chunks, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaStreamSynchronize(st));  // L is a local
+        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(iterations + 1) * n_slots, st));
+        dim3 grid((n_slots + 255) / 256, iterations + 1);
+        build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_src[c].as<int32_t>(), d_map[c].as<uint16_t>(),
+                                                 nu, n_slots, d_T[c].as<uint32_t>());
         PP_CHECK_LAUNCH();
-        cds[c].T = d_T[c].as<uint2>();
-        cds[c].n_pairs_pad = np_pad;
+        cds[c].E = d_T[c].as<uint32_t>();
+        cds[c].start_mask = d_mask[c].as<uint32_t>();
+        cds[c].n_slots = n_slots;
+        cds[c].n_chunks = L.n_chunks;
+        cds[c].n_chunks_a = L.n_chunks_a;
         cds[c].pad = 0;
     }
     PP_CUDA(d_cd.alloc(sizeof(ClassDesc) * n_classes, st));
