@@ -219,7 +219,6 @@ __global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int3
 constexpr int SCORE_THREADS = 512;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int TILE_CELLS = 64;
-constexpr uint32_t RANK_BIAS = 0x04000400u;  // ranks are stored as normal positive fp16 bit patterns
 
 struct ClassDesc {
     const uint32_t *E;           // [iters+1][n_slots]
@@ -254,17 +253,19 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// per-half (x >= y) on fp16 bit patterns -> 0xFFFF / 0x0000 per half (SASS HSET2.GE)
-__device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) {
-    return __hge2_mask(*reinterpret_cast<const __half2 *>(&x), *reinterpret_cast<const __half2 *>(&y));
-}
+// Ranks live in the tile as integer-valued fp16 numbers (exact up to 2048 > the 1 680-gene tile limit), two
+// cells per 32-bit word.  Per slot two statistics are taken against the hub h, on two different pipes:
+//   X: (h >= v) as a 0xFFFF/0 mask per half   -- HSET2.GE (ALU pipe) + one 32-bit integer accumulate
+//   Z: (h >  v) as clamp(h - v, 0, 1) in fp16 -- HADD2.SAT + HADD2 (FMA pipe), flushed to integers per chunk
+__device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<const __half2 *>(&x); }
+__device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) { return __hge2_mask(as_h2(x), as_h2(y)); }
 
-// For the two cells packed in this lane accumulate X -= mask(hub >= v), Y -= mask(v >= hub) over the slots
-// of chunks first, first + stride, ... < last of one table row.  Chunks are staged into this warp's private
+// For the two cells packed in this lane accumulate X -= mask(hub >= v) and Z += (hub > v) over the slots of
+// chunks first, first + stride, ... < last of one table row.  Chunks are staged into this warp's private
 // double buffer with cp.async; one broadcast LDS.128 fetches four slot offsets.
 __device__ __forceinline__ void eval_chunks(uint32_t tile_lane, const uint32_t *__restrict__ Erow,
                                             const uint32_t *__restrict__ start_mask, int first, int stride, int last,
-                                            uint4 *stage, int lane, uint32_t &X, uint32_t &Y) {
+                                            uint4 *stage, int lane, uint32_t &X, uint32_t &Z) {
     if (first >= last) return;
     const uint4 *src = reinterpret_cast<const uint4 *>(Erow) + lane;  // 32 lanes x 16 B = one chunk
     cp_async16(stage + lane, src + (size_t)first * 32);
@@ -282,52 +283,77 @@ __device__ __forceinline__ void eval_chunks(uint32_t tile_lane, const uint32_t *
         }
         __syncwarp();
         const uint4 *sb = stage + buf * 32;
+        __half2 z0 = __float2half2_rn(0.f), z1 = z0;  // <= 64 each per chunk: exact
 #pragma unroll 8
         for (int q = 0; q < 32; ++q) {
             const uint4 v = sb[q];  // broadcast: four slots
             const uint32_t e0 = lds32(tile_lane + v.x), e1 = lds32(tile_lane + v.y);
             const uint32_t e2 = lds32(tile_lane + v.z), e3 = lds32(tile_lane + v.w);
             if ((sm >> q) & 1u) h = e0;  // warp-uniform: this vector opens a star
+            const __half2 hh = as_h2(h);
             X -= ge_mask(h, e0);
-            Y -= ge_mask(e0, h);
             X -= ge_mask(h, e1);
-            Y -= ge_mask(e1, h);
             X -= ge_mask(h, e2);
-            Y -= ge_mask(e2, h);
             X -= ge_mask(h, e3);
-            Y -= ge_mask(e3, h);
+            z0 = __hadd2(z0, __hsub2_sat(hh, as_h2(e0)));
+            z1 = __hadd2(z1, __hsub2_sat(hh, as_h2(e1)));
+            z0 = __hadd2(z0, __hsub2_sat(hh, as_h2(e2)));
+            z1 = __hadd2(z1, __hsub2_sat(hh, as_h2(e3)));
         }
+        const __half2 z = __hadd2(z0, z1);
+        Z += (uint32_t)__half2int_rz(__low2half(z)) + ((uint32_t)__half2int_rz(__high2half(z)) << 16);
         __syncwarp();  // every lane is done with `buf` before it is refilled
         buf ^= 1;
     }
 }
 
-// One table row: section A counts (ge, le) directly, section B (hub = second gene) with the roles swapped.
-__device__ __forceinline__ void eval_row(uint32_t tile_lane, const uint32_t *__restrict__ Erow, const ClassDesc &cd,
-                                         int first, int stride, uint4 *stage, int lane, uint32_t &ge, uint32_t &le) {
-    ge = 0;
-    le = 0;
-    eval_chunks(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, ge, le);
+struct RowAcc {
+    uint32_t xa, za, xb, zb;  // section A / B: packed -(mask) sums (X) and packed plain counts (Z)
+};
+
+// One table row.  Section A: the hub is the pair's first gene; section B: its second gene.
+__device__ __forceinline__ RowAcc eval_row(uint32_t tile_lane, const uint32_t *__restrict__ Erow, const ClassDesc &cd,
+                                           int first, int stride, uint4 *stage, int lane) {
+    RowAcc r = {0u, 0u, 0u, 0u};
+    eval_chunks(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, r.xa, r.za);
     int fb = first;  // first chunk of this warp's stride pattern inside section B
     if (stride > 1) {
         while (fb < cd.n_chunks_a) fb += stride;
     } else {
         fb = cd.n_chunks_a;
     }
-    eval_chunks(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, le, ge);
+    eval_chunks(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, r.xb, r.zb);
+    return r;
 }
 
-// acc = sum of -(mask): a true low half adds 1 to the low field and -1 to the high field, a true high
+// X = sum of -(mask): a true low half adds 1 to the low field and -1 to the high field, a true high
 // half adds 1 to the high field  =>  lo16 = n_lo, hi16 = n_hi - n_lo (mod 2^16); counts <= 65535.
 __device__ __forceinline__ void unpack_counts(uint32_t acc, int &n_lo, int &n_hi) {
     n_lo = (int)(acc & 0xffffu);
     n_hi = (int)(((acc >> 16) + (uint32_t)n_lo) & 0xffffu);
 }
 
+// (hits, total) of get_proportion (cyclone.py:206-215) for the two cells of a lane.  Over the slots of
+// section A (pair = (h, v)) and B (pair = (v, h)), with ties = hub / padding slots and genuine ties:
+//   hits  = #(first > second) = Z_A + (S_B - X_B)          ties are inside X_B, so they drop out
+//   total = #(first != second) = S - (X_A - Z_A) - (X_B - Z_B)
+__device__ __forceinline__ void row_counts(const RowAcc &r, int s_all, int s_b, int &h_lo, int &h_hi, int &t_lo,
+                                           int &t_hi) {
+    int xa_lo, xa_hi, xb_lo, xb_hi;
+    unpack_counts(r.xa, xa_lo, xa_hi);
+    unpack_counts(r.xb, xb_lo, xb_hi);
+    const int za_lo = (int)(r.za & 0xffffu), za_hi = (int)(r.za >> 16);
+    const int zb_lo = (int)(r.zb & 0xffffu), zb_hi = (int)(r.zb >> 16);
+    h_lo = za_lo + s_b - xb_lo;
+    h_hi = za_hi + s_b - xb_hi;
+    t_lo = s_all - xa_lo + za_lo - xb_lo + zb_lo;
+    t_hi = s_all - xa_hi + za_hi - xb_hi + zb_hi;
+}
+
 __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];
-    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_dyn);  // [n_union][32] packed fp16-pattern ranks
-    __shared__ uint32_t s_ge[32], s_le[32];                   // observed accumulators (packed)
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_dyn);  // [n_union][32] two fp16 ranks per word
+    __shared__ uint32_t s_obs[4][32];                         // observed accumulators (packed)
     __shared__ uint32_t s_below[TILE_CELLS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -340,33 +366,34 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         const uint16_t *r_lo = P.rank + (c_lo < P.n_cells ? c_lo : 0) * P.rank_ld;
         const uint16_t *r_hi = P.rank + (c_hi < P.n_cells ? c_hi : 0) * P.rank_ld;
         for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
-            const uint32_t lo = (c_lo < P.n_cells) ? r_lo[g] : 0u;
-            const uint32_t hi = (c_hi < P.n_cells) ? r_hi[g] : 0u;
-            tile[g * 32 + lane] = (lo | (hi << 16)) + RANK_BIAS;
+            const float lo = (c_lo < P.n_cells) ? (float)r_lo[g] : 0.f;
+            const float hi = (c_hi < P.n_cells) ? (float)r_hi[g] : 0.f;
+            const __half2 v = __floats2half2_rn(lo, hi);  // exact: ranks < 2048
+            tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
         }
     }
     const uint32_t tile_lane = smem_u32(tile) + lane * 4;
 
     for (int cls = 0; cls < P.n_classes; ++cls) {
         const ClassDesc cd = P.classes[cls];
-        const int np = cd.n_slots;  // slots = pairs + ties (hubs, padding); ties cancel below
-        if (tid < 32) s_ge[tid] = 0, s_le[tid] = 0;
+        const int s_all = cd.n_slots, s_b = (cd.n_chunks - cd.n_chunks_a) * CHUNK_SLOTS;
+        if (tid < 32) s_obs[0][tid] = 0, s_obs[1][tid] = 0, s_obs[2][tid] = 0, s_obs[3][tid] = 0;
         if (tid < TILE_CELLS) s_below[tid] = 0;
         __syncthreads();  // also orders the tile stores before the first gather
         // ---- observed proportion (row 0): chunks dealt to the warps, packed accumulators summed mod 2^32
         {
-            uint32_t ge, le;
-            eval_row(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane, ge, le);
-            atomicAdd(&s_ge[lane], ge);
-            atomicAdd(&s_le[lane], le);
+            const RowAcc r = eval_row(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane);
+            atomicAdd(&s_obs[0][lane], r.xa);
+            atomicAdd(&s_obs[1][lane], r.za);
+            atomicAdd(&s_obs[2][lane], r.xb);
+            atomicAdd(&s_obs[3][lane], r.zb);
         }
         __syncthreads();
-        int oge_lo, oge_hi, ole_lo, ole_hi;
-        unpack_counts(s_ge[lane], oge_lo, oge_hi);
-        unpack_counts(s_le[lane], ole_lo, ole_hi);
-        // hits = #(a > b) = S - #(b >= a); total = #(a != b) = 2S - #(a >= b) - #(b >= a)   (S = slots incl. ties)
-        const int h0_lo = np - ole_lo, h0_hi = np - ole_hi;
-        const int t0_lo = 2 * np - oge_lo - ole_lo, t0_hi = 2 * np - oge_hi - ole_hi;
+        int h0_lo, h0_hi, t0_lo, t0_hi;
+        {
+            const RowAcc r = {s_obs[0][lane], s_obs[1][lane], s_obs[2][lane], s_obs[3][lane]};
+            row_counts(r, s_all, s_b, h0_lo, h0_hi, t0_lo, t0_hi);
+        }
         const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
         const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
         if (warp == 0) {
@@ -382,13 +409,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         // ---- permutation null: iterations dealt round-robin to the warps
         uint32_t below_lo = 0, below_hi = 0;
         for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
-            uint32_t ge, le;
-            eval_row(tile_lane, cd.E + (size_t)k * np, cd, 0, 1, stage, lane, ge, le);
-            int ge_lo, ge_hi, le_lo, le_hi;
-            unpack_counts(ge, ge_lo, ge_hi);
-            unpack_counts(le, le_lo, le_hi);
-            const int h_lo = np - le_lo, h_hi = np - le_hi;
-            const int t_lo = 2 * np - ge_lo - le_lo, t_hi = 2 * np - ge_hi - le_hi;
+            const RowAcc r = eval_row(tile_lane, cd.E + (size_t)k * s_all, cd, 0, 1, stage, lane);
+            int h_lo, h_hi, t_lo, t_hi;
+            row_counts(r, s_all, s_b, h_lo, h_hi, t_lo, t_hi);
             // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
             if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) && (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
                 ++below_lo;
