@@ -236,6 +236,7 @@ struct ScoreParams {
     int n_classes;
     int iterations, min_iter, min_pairs;
     const ClassDesc *classes;
+    uint32_t *gtile;    // !FAST only: [gridDim.x][n_union][32] scratch
     double *scores;     // [n_classes][n_cells]
     int32_t *obs_hits;  // [n_classes][n_cells]
     int32_t *obs_total;
@@ -253,19 +254,36 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// Ranks live in the tile as integer-valued fp16 numbers (exact up to 2048 > the 1 680-gene tile limit), two
-// cells per 32-bit word.  Per slot two statistics are taken against the hub h, on two different pipes:
-//   X: (h >= v) as a 0xFFFF/0 mask per half   -- HSET2.GE (ALU pipe) + one 32-bit integer accumulate
-//   Z: (h >  v) as clamp(h - v, 0, 1) in fp16 -- HADD2.SAT + HADD2 (FMA pipe), flushed to integers per chunk
+// Two tile representations (template parameter FAST):
+//  FAST  (all marker genes of the call fit the shared-memory tile, <= 1 680 genes): ranks are integer-valued
+//        fp16 numbers (exact up to 2048), two cells per 32-bit word, tile in shared memory.  Per slot two
+//        statistics are taken against the hub h, on two different pipes:
+//          X: (h >= v) as a 0xFFFF/0 mask per half   -- HSET2.GE (ALU pipe) + one 32-bit integer accumulate
+//          Z: (h >  v) as clamp(h - v, 0, 1) in fp16 -- HADD2.SAT + HADD2 (FMA pipe)
+//  !FAST (up to 32 768 marker genes): ranks are 15-bit integers, two per word, tile in a per-CTA global
+//        scratch (L1/L2 cached gathers); (x >= y) per half is bit 15/31 of (x | 0x80008000) - y.
+// Both flush their per-chunk counters into 32-bit per-cell counters, so a class may have any number of pairs.
 __device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<const __half2 *>(&x); }
 __device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) { return __hge2_mask(as_h2(x), as_h2(y)); }
+__device__ __forceinline__ uint32_t ge_bits(uint32_t x, uint32_t y) {
+    return (((x | 0x80008000u) - y) >> 15) & 0x00010001u;
+}
+template <bool FAST> __device__ __forceinline__ uint32_t tile_load(uint64_t base, uint32_t off) {
+    if (FAST) return lds32((uint32_t)base + off);
+    return *reinterpret_cast<const uint32_t *>(base + off);  // written by this CTA: coherent load, not ld.nc
+}
 
-// For the two cells packed in this lane accumulate X -= mask(hub >= v) and Z += (hub > v) over the slots of
-// chunks first, first + stride, ... < last of one table row.  Chunks are staged into this warp's private
-// double buffer with cp.async; one broadcast LDS.128 fetches four slot offsets.
-__device__ __forceinline__ void eval_chunks(uint32_t tile_lane, const uint32_t *__restrict__ Erow,
+struct RowAcc {  // per-cell counters of one table row: section A / B, low / high cell of the lane
+    int xa_lo, xa_hi, za_lo, za_hi, xb_lo, xb_hi, zb_lo, zb_hi;
+};
+
+// For the two cells packed in this lane add, over the slots of chunks first, first + stride, ... < last of one
+// table row, X += (hub >= v) and Z += (hub > v).  Chunks are staged into this warp's private double buffer with
+// cp.async; one broadcast LDS.128 fetches four slot offsets.
+template <bool FAST>
+__device__ __forceinline__ void eval_chunks(uint64_t tile_lane, const uint32_t *__restrict__ Erow,
                                             const uint32_t *__restrict__ start_mask, int first, int stride, int last,
-                                            uint4 *stage, int lane, uint32_t &X, uint32_t &Z) {
+                                            uint4 *stage, int lane, int &x_lo, int &x_hi, int &z_lo, int &z_hi) {
     if (first >= last) return;
     const uint4 *src = reinterpret_cast<const uint4 *>(Erow) + lane;  // 32 lanes x 16 B = one chunk
     cp_async16(stage + lane, src + (size_t)first * 32);
@@ -283,54 +301,70 @@ __device__ __forceinline__ void eval_chunks(uint32_t tile_lane, const uint32_t *
         }
         __syncwarp();
         const uint4 *sb = stage + buf * 32;
-        __half2 z0 = __float2half2_rn(0.f), z1 = z0;  // <= 64 each per chunk: exact
+        if (FAST) {
+            uint32_t X = 0;                               // sum of -(mask), decoded below
+            __half2 z0 = __float2half2_rn(0.f), z1 = z0;  // <= 64 each per chunk: exact
 #pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-            const uint4 v = sb[q];  // broadcast: four slots
-            const uint32_t e0 = lds32(tile_lane + v.x), e1 = lds32(tile_lane + v.y);
-            const uint32_t e2 = lds32(tile_lane + v.z), e3 = lds32(tile_lane + v.w);
-            if ((sm >> q) & 1u) h = e0;  // warp-uniform: this vector opens a star
-            const __half2 hh = as_h2(h);
-            X -= ge_mask(h, e0);
-            X -= ge_mask(h, e1);
-            X -= ge_mask(h, e2);
-            X -= ge_mask(h, e3);
-            z0 = __hadd2(z0, __hsub2_sat(hh, as_h2(e0)));
-            z1 = __hadd2(z1, __hsub2_sat(hh, as_h2(e1)));
-            z0 = __hadd2(z0, __hsub2_sat(hh, as_h2(e2)));
-            z1 = __hadd2(z1, __hsub2_sat(hh, as_h2(e3)));
+            for (int q = 0; q < 32; ++q) {
+                const uint4 v = sb[q];  // broadcast: four slots
+                const uint32_t e0 = tile_load<true>(tile_lane, v.x), e1 = tile_load<true>(tile_lane, v.y);
+                const uint32_t e2 = tile_load<true>(tile_lane, v.z), e3 = tile_load<true>(tile_lane, v.w);
+                if ((sm >> q) & 1u) h = e0;  // warp-uniform: this vector opens a star
+                const __half2 hh = as_h2(h);
+                X -= ge_mask(h, e0);
+                X -= ge_mask(h, e1);
+                X -= ge_mask(h, e2);
+                X -= ge_mask(h, e3);
+                z0 = __hadd2(z0, __hsub2_sat(hh, as_h2(e0)));
+                z1 = __hadd2(z1, __hsub2_sat(hh, as_h2(e1)));
+                z0 = __hadd2(z0, __hsub2_sat(hh, as_h2(e2)));
+                z1 = __hadd2(z1, __hsub2_sat(hh, as_h2(e3)));
+            }
+            // a true low half adds 1 to the low field and -1 to the high field, a true high half adds 1 to the
+            // high field  =>  lo16 = n_lo, hi16 = n_hi - n_lo (mod 2^16)
+            const int n_lo = (int)(X & 0xffffu);
+            x_lo += n_lo;
+            x_hi += (int)(((X >> 16) + (uint32_t)n_lo) & 0xffffu);
+            const __half2 z = __hadd2(z0, z1);
+            z_lo += __half2int_rz(__low2half(z));
+            z_hi += __half2int_rz(__high2half(z));
+        } else {
+            uint32_t X = 0, W = 0;  // packed plain counts of (h >= v) and (v >= h); <= 128 per chunk
+#pragma unroll 4
+            for (int q = 0; q < 32; ++q) {
+                const uint4 v = sb[q];
+                const uint32_t e0 = tile_load<false>(tile_lane, v.x), e1 = tile_load<false>(tile_lane, v.y);
+                const uint32_t e2 = tile_load<false>(tile_lane, v.z), e3 = tile_load<false>(tile_lane, v.w);
+                if ((sm >> q) & 1u) h = e0;
+                X += ge_bits(h, e0) + ge_bits(h, e1) + ge_bits(h, e2) + ge_bits(h, e3);
+                W += ge_bits(e0, h) + ge_bits(e1, h) + ge_bits(e2, h) + ge_bits(e3, h);
+            }
+            x_lo += (int)(X & 0xffffu);
+            x_hi += (int)(X >> 16);
+            z_lo += CHUNK_SLOTS - (int)(W & 0xffffu);  // (h > v) = !(v >= h)
+            z_hi += CHUNK_SLOTS - (int)(W >> 16);
         }
-        const __half2 z = __hadd2(z0, z1);
-        Z += (uint32_t)__half2int_rz(__low2half(z)) + ((uint32_t)__half2int_rz(__high2half(z)) << 16);
         __syncwarp();  // every lane is done with `buf` before it is refilled
         buf ^= 1;
     }
 }
 
-struct RowAcc {
-    uint32_t xa, za, xb, zb;  // section A / B: packed -(mask) sums (X) and packed plain counts (Z)
-};
-
 // One table row.  Section A: the hub is the pair's first gene; section B: its second gene.
-__device__ __forceinline__ RowAcc eval_row(uint32_t tile_lane, const uint32_t *__restrict__ Erow, const ClassDesc &cd,
+template <bool FAST>
+__device__ __forceinline__ RowAcc eval_row(uint64_t tile_lane, const uint32_t *__restrict__ Erow, const ClassDesc &cd,
                                            int first, int stride, uint4 *stage, int lane) {
-    RowAcc r = {0u, 0u, 0u, 0u};
-    eval_chunks(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, r.xa, r.za);
+    RowAcc r = {0, 0, 0, 0, 0, 0, 0, 0};
+    eval_chunks<FAST>(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, r.xa_lo, r.xa_hi,
+                      r.za_lo, r.za_hi);
     int fb = first;  // first chunk of this warp's stride pattern inside section B
     if (stride > 1) {
         while (fb < cd.n_chunks_a) fb += stride;
     } else {
         fb = cd.n_chunks_a;
     }
-    eval_chunks(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, r.xb, r.zb);
+    eval_chunks<FAST>(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, r.xb_lo, r.xb_hi, r.zb_lo,
+                      r.zb_hi);
     return r;
-}
-
-// X = sum of -(mask): a true low half adds 1 to the low field and -1 to the high field, a true high
-// half adds 1 to the high field  =>  lo16 = n_lo, hi16 = n_hi - n_lo (mod 2^16); counts <= 65535.
-__device__ __forceinline__ void unpack_counts(uint32_t acc, int &n_lo, int &n_hi) {
-    n_lo = (int)(acc & 0xffffu);
-    n_hi = (int)(((acc >> 16) + (uint32_t)n_lo) & 0xffffu);
 }
 
 // (hits, total) of get_proportion (cyclone.py:206-215) for the two cells of a lane.  Over the slots of
@@ -339,95 +373,106 @@ __device__ __forceinline__ void unpack_counts(uint32_t acc, int &n_lo, int &n_hi
 //   total = #(first != second) = S - (X_A - Z_A) - (X_B - Z_B)
 __device__ __forceinline__ void row_counts(const RowAcc &r, int s_all, int s_b, int &h_lo, int &h_hi, int &t_lo,
                                            int &t_hi) {
-    int xa_lo, xa_hi, xb_lo, xb_hi;
-    unpack_counts(r.xa, xa_lo, xa_hi);
-    unpack_counts(r.xb, xb_lo, xb_hi);
-    const int za_lo = (int)(r.za & 0xffffu), za_hi = (int)(r.za >> 16);
-    const int zb_lo = (int)(r.zb & 0xffffu), zb_hi = (int)(r.zb >> 16);
-    h_lo = za_lo + s_b - xb_lo;
-    h_hi = za_hi + s_b - xb_hi;
-    t_lo = s_all - xa_lo + za_lo - xb_lo + zb_lo;
-    t_hi = s_all - xa_hi + za_hi - xb_hi + zb_hi;
+    h_lo = r.za_lo + s_b - r.xb_lo;
+    h_hi = r.za_hi + s_b - r.xb_hi;
+    t_lo = s_all - r.xa_lo + r.za_lo - r.xb_lo + r.zb_lo;
+    t_hi = s_all - r.xa_hi + r.za_hi - r.xb_hi + r.zb_hi;
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];
-    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_dyn);  // [n_union][32] two fp16 ranks per word
-    __shared__ uint32_t s_obs[4][32];                         // observed accumulators (packed)
+    __shared__ int s_obs[8][32];  // observed counters
     __shared__ uint32_t s_below[TILE_CELLS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (size_t)P.n_union * 128 + (size_t)warp * STAGE_BYTES);
-    const int64_t cell0 = (int64_t)blockIdx.x * TILE_CELLS;
-    const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
+    // FAST: [n_union][32] words in shared memory, followed by the per-warp staging buffers;
+    // !FAST: the tile is this CTA's slab of the global scratch, shared memory only holds the staging buffers
+    uint32_t *tile = FAST ? reinterpret_cast<uint32_t *>(smem_dyn) : P.gtile + (size_t)blockIdx.x * P.n_union * 32;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (FAST ? (size_t)P.n_union * 128 : 0) + (size_t)warp * STAGE_BYTES);
+    const uint64_t tile_lane = FAST ? (uint64_t)(smem_u32(tile) + lane * 4) : (uint64_t)(uintptr_t)(tile + lane);
+    const int64_t n_tiles = (P.n_cells + TILE_CELLS - 1) / TILE_CELLS;
 
-    // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
-    {
-        const uint16_t *r_lo = P.rank + (c_lo < P.n_cells ? c_lo : 0) * P.rank_ld;
-        const uint16_t *r_hi = P.rank + (c_hi < P.n_cells ? c_hi : 0) * P.rank_ld;
-        for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
-            const float lo = (c_lo < P.n_cells) ? (float)r_lo[g] : 0.f;
-            const float hi = (c_hi < P.n_cells) ? (float)r_hi[g] : 0.f;
-            const __half2 v = __floats2half2_rn(lo, hi);  // exact: ranks < 2048
-            tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
-        }
-    }
-    const uint32_t tile_lane = smem_u32(tile) + lane * 4;
-
-    for (int cls = 0; cls < P.n_classes; ++cls) {
-        const ClassDesc cd = P.classes[cls];
-        const int s_all = cd.n_slots, s_b = (cd.n_chunks - cd.n_chunks_a) * CHUNK_SLOTS;
-        if (tid < 32) s_obs[0][tid] = 0, s_obs[1][tid] = 0, s_obs[2][tid] = 0, s_obs[3][tid] = 0;
-        if (tid < TILE_CELLS) s_below[tid] = 0;
-        __syncthreads();  // also orders the tile stores before the first gather
-        // ---- observed proportion (row 0): chunks dealt to the warps, packed accumulators summed mod 2^32
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t cell0 = t * TILE_CELLS;
+        const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
+        // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
         {
-            const RowAcc r = eval_row(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane);
-            atomicAdd(&s_obs[0][lane], r.xa);
-            atomicAdd(&s_obs[1][lane], r.za);
-            atomicAdd(&s_obs[2][lane], r.xb);
-            atomicAdd(&s_obs[3][lane], r.zb);
-        }
-        __syncthreads();
-        int h0_lo, h0_hi, t0_lo, t0_hi;
-        {
-            const RowAcc r = {s_obs[0][lane], s_obs[1][lane], s_obs[2][lane], s_obs[3][lane]};
-            row_counts(r, s_all, s_b, h0_lo, h0_hi, t0_lo, t0_hi);
-        }
-        const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
-        const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
-        if (warp == 0) {
-            if (c_lo < P.n_cells) {
-                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_lo] = h0_lo;
-                if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_lo] = t0_lo;
-            }
-            if (c_hi < P.n_cells) {
-                if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_hi] = h0_hi;
-                if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_hi] = t0_hi;
+            const uint16_t *r_lo = P.rank + (c_lo < P.n_cells ? c_lo : 0) * P.rank_ld;
+            const uint16_t *r_hi = P.rank + (c_hi < P.n_cells ? c_hi : 0) * P.rank_ld;
+            for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
+                const uint32_t lo = (c_lo < P.n_cells) ? r_lo[g] : 0u;
+                const uint32_t hi = (c_hi < P.n_cells) ? r_hi[g] : 0u;
+                if (FAST) {
+                    const __half2 v = __floats2half2_rn((float)lo, (float)hi);  // exact: ranks < 2048
+                    tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
+                } else {
+                    tile[g * 32 + lane] = lo | (hi << 16);
+                }
             }
         }
-        // ---- permutation null: iterations dealt round-robin to the warps
-        uint32_t below_lo = 0, below_hi = 0;
-        for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
-            const RowAcc r = eval_row(tile_lane, cd.E + (size_t)k * s_all, cd, 0, 1, stage, lane);
-            int h_lo, h_hi, t_lo, t_hi;
-            row_counts(r, s_all, s_b, h_lo, h_hi, t_lo, t_hi);
-            // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
-            if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) && (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
-                ++below_lo;
-            if (ok_hi && !(h_hi < P.min_pairs || t_hi == 0) && (long long)h_hi * t0_hi < (long long)h0_hi * t_hi)
-                ++below_hi;
+        for (int cls = 0; cls < P.n_classes; ++cls) {
+            const ClassDesc cd = P.classes[cls];
+            const int s_all = cd.n_slots, s_b = (cd.n_chunks - cd.n_chunks_a) * CHUNK_SLOTS;
+            if (tid < 32)
+                for (int j = 0; j < 8; ++j) s_obs[j][tid] = 0;
+            if (tid < TILE_CELLS) s_below[tid] = 0;
+            if (!FAST) __threadfence_block();
+            __syncthreads();  // also orders the tile stores before the first gather
+            // ---- observed proportion (row 0): chunks dealt to the warps
+            {
+                const RowAcc r = eval_row<FAST>(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane);
+                atomicAdd(&s_obs[0][lane], r.xa_lo);
+                atomicAdd(&s_obs[1][lane], r.xa_hi);
+                atomicAdd(&s_obs[2][lane], r.za_lo);
+                atomicAdd(&s_obs[3][lane], r.za_hi);
+                atomicAdd(&s_obs[4][lane], r.xb_lo);
+                atomicAdd(&s_obs[5][lane], r.xb_hi);
+                atomicAdd(&s_obs[6][lane], r.zb_lo);
+                atomicAdd(&s_obs[7][lane], r.zb_hi);
+            }
+            __syncthreads();
+            int h0_lo, h0_hi, t0_lo, t0_hi;
+            {
+                const RowAcc r = {s_obs[0][lane], s_obs[1][lane], s_obs[2][lane], s_obs[3][lane],
+                                  s_obs[4][lane], s_obs[5][lane], s_obs[6][lane], s_obs[7][lane]};
+                row_counts(r, s_all, s_b, h0_lo, h0_hi, t0_lo, t0_hi);
+            }
+            const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
+            const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
+            if (warp == 0) {
+                if (c_lo < P.n_cells) {
+                    if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_lo] = h0_lo;
+                    if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_lo] = t0_lo;
+                }
+                if (c_hi < P.n_cells) {
+                    if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_hi] = h0_hi;
+                    if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_hi] = t0_hi;
+                }
+            }
+            // ---- permutation null: iterations dealt round-robin to the warps
+            uint32_t below_lo = 0, below_hi = 0;
+            for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
+                const RowAcc r = eval_row<FAST>(tile_lane, cd.E + (size_t)k * s_all, cd, 0, 1, stage, lane);
+                int h_lo, h_hi, t_lo, t_hi;
+                row_counts(r, s_all, s_b, h_lo, h_hi, t_lo, t_hi);
+                // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
+                if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) && (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
+                    ++below_lo;
+                if (ok_hi && !(h_hi < P.min_pairs || t_hi == 0) && (long long)h_hi * t0_hi < (long long)h0_hi * t_hi)
+                    ++below_hi;
+            }
+            atomicAdd(&s_below[lane], below_lo);
+            atomicAdd(&s_below[32 + lane], below_hi);
+            __syncthreads();
+            if (tid < TILE_CELLS && cell0 + tid < P.n_cells) {
+                // total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
+                double sc = nan("");
+                if (P.iterations >= P.min_iter && P.iterations > 0) sc = (double)s_below[tid] / (double)P.iterations;
+                P.scores[(int64_t)cls * P.out_ld + P.out_off + cell0 + tid] = sc;
+            }
+            __syncthreads();
         }
-        atomicAdd(&s_below[lane], below_lo);
-        atomicAdd(&s_below[32 + lane], below_hi);
-        __syncthreads();
-        if (tid < TILE_CELLS && cell0 + tid < P.n_cells) {
-            // total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
-            double s = nan("");
-            if (P.iterations >= P.min_iter && P.iterations > 0) s = (double)s_below[tid] / (double)P.iterations;
-            P.scores[(int64_t)cls * P.out_ld + P.out_off + cell0 + tid] = s;
-        }
-        __syncthreads();
     }
 }
 
@@ -514,7 +559,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         const int64_t u0 = used_off[c], u1 = used_off[c + 1], p0 = pair_off[c], p1 = pair_off[c + 1];
         if (u1 < u0 || p1 < p0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: offsets must be non-decreasing");
         if (p1 - p0 == 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: class %d has no marker pairs", c);
-        if (p1 - p0 > 60000) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 60000 marker pairs", c);
+        if (p1 - p0 > (1 << 28)) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d has more than 2^28 marker pairs", c);
         for (int64_t i = u0; i < u1; ++i) {
             if (used_idx[i] < 0 || used_idx[i] >= n_cols) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx out of range");
             if (i > u0 && used_idx[i] <= used_idx[i - 1]) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: used_idx must ascend within a class");
@@ -526,10 +571,11 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     std::sort(uni.begin(), uni.end());
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
     const int U = (int)uni.size();
-    const size_t dyn_smem = (size_t)U * 128 + (size_t)SCORE_WARPS * STAGE_BYTES;
-    if (U > 30000 || dyn_smem + 1024 > (size_t)std::min(ctx->smem_optin, 227 * 1024))
-        return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: %d distinct marker genes exceed the shared-memory tile (max %d)", U,
-                       (std::min(ctx->smem_optin, 227 * 1024) - 1024 - SCORE_WARPS * STAGE_BYTES) / 128);
+    if (U > 32768) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: %d distinct marker genes (max 32768)", U);
+    // FAST path: the whole tile (128 B per gene) + staging buffers fit in shared memory and ranks < 2048
+    const bool fast = U <= 2048 && (size_t)U * 128 + (size_t)SCORE_WARPS * STAGE_BYTES + 2048 <=
+                                       (size_t)std::min(ctx->smem_optin, 227 * 1024);
+    const size_t dyn_smem = (fast ? (size_t)U * 128 : 0) + (size_t)SCORE_WARPS * STAGE_BYTES;
 
     PP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -593,8 +639,6 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         PP_CUDA(cudaStreamSynchronize(st));  // map is a local
         const StarLayout L = build_star_layout(pairs + 2 * pair_off[c], np, nu);
         const int n_slots = (int)L.slot_src.size();
-        if (n_slots > 65535)
-            return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: class %d needs %d comparison slots (max 65535)", c, n_slots);
         PP_CUDA(d_src[c].alloc(sizeof(int32_t) * n_slots, st));
         PP_CUDA(cudaMemcpyAsync(d_src[c].p, L.slot_src.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
         PP_CUDA(d_mask[c].alloc(sizeof(uint32_t) * L.n_chunks, st));
@@ -632,7 +676,18 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     P.scores = d_scores.as<double>();
     P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
     P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
-    PP_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    DevBuf d_gtile;
+    const int slow_grid = ctx->n_sm * 2;  // persistent CTAs, one global tile slab each
+    if (!fast) PP_CUDA(d_gtile.alloc((size_t)slow_grid * U * 128, st));
+    P.gtile = d_gtile.as<uint32_t>();
+    auto launch_score = [&](int64_t nc) {
+        const int64_t n_tiles = (nc + TILE_CELLS - 1) / TILE_CELLS;
+        if (fast)
+            score_kernel<true><<<(unsigned)n_tiles, SCORE_THREADS, dyn_smem, st>>>(P);
+        else
+            score_kernel<false><<<(unsigned)std::min<int64_t>(n_tiles, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
+    };
     float score_ms = 0.f, copy_ms = 0.f;
     if (!pipelined) {
         const void *dx = x0;
@@ -650,7 +705,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         P.rank = d_rank.as<uint16_t>();
         P.n_cells = n_cells;
         P.out_off = 0;
-        score_kernel<<<(unsigned)((n_cells + TILE_CELLS - 1) / TILE_CELLS), SCORE_THREADS, dyn_smem, st>>>(P);
+        launch_score(n_cells);
         PP_CHECK_LAUNCH();
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
     } else {
@@ -689,7 +744,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             P.n_cells = nc;
             P.out_off = c0;
             PP_CUDA(cudaEventRecord(e0, st));
-            score_kernel<<<(unsigned)((nc + TILE_CELLS - 1) / TILE_CELLS), SCORE_THREADS, dyn_smem, st>>>(P);
+            launch_score(nc);
             PP_CHECK_LAUNCH();
             PP_CUDA(cudaEventRecord(e1, st));
         }

@@ -187,3 +187,67 @@ def test_host_input_is_streamed_in_chunks():
     rows = np.sort(rng.choice(n, 40, replace=False))
     for i, k in enumerate(ks):
         assert np.array_equal(s_host[i, rows], orc.phase_scores(x[rows], 40, 10, 5, pairs[k], used[k]))
+
+
+def _random_marker_case(rng, n_genes, n_pairs_per_class, n_classes, n_cells):
+    names = ["g{}".format(i) for i in range(n_genes)]
+    markers = {}
+    for c in range(n_classes):
+        a = rng.integers(0, n_genes, n_pairs_per_class)
+        b = rng.integers(0, n_genes, n_pairs_per_class)
+        markers["class{}".format(c)] = [(names[i], names[j]) for i, j in zip(a, b)]
+    x = rng.poisson(3.0, (n_cells, n_genes)).astype(np.float64)
+    return names, markers, x
+
+
+def test_large_marker_sets_take_the_general_path():
+    """More marker genes than the shared-memory tile holds (global-memory tile, integer compares) and more
+    pairs per class than a 16-bit counter holds: still bit-exact against the oracle."""
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(47)
+    for n_genes, n_pairs, n_cells, iters in [(2600, 9000, 70, 30), (300, 70000, 40, 12), (5000, 3000, 130, 25)]:
+        names, markers, x = _random_marker_case(rng, n_genes, n_pairs, 2, n_cells)
+        pairs, used = filter_marker_pairs(markers, names)
+        ks = list(pairs.keys())
+        sc, tm, oh, ot = _ffi().cyclone(x, [np.where(used[k])[0] for k in ks], [pairs[k] for k in ks], iters, 5, 3,
+                                        want_observed=True)
+        for i, k in enumerate(ks):
+            ref, eh, et = orc.phase_scores(x, iters, 5, 3, pairs[k], used[k], return_observed=True)
+            assert np.array_equal(oh[i], eh) and np.array_equal(ot[i], et), (n_genes, n_pairs, k)
+            assert np.array_equal(sc[i], ref, equal_nan=True), (n_genes, n_pairs, k)
+
+
+def test_sandbag_then_cyclone_flow():
+    """configs[0] shape (leng15-like: 247 sorted cells 76/80/91, 19 084 genes; the real matrix is not in the
+    checkout): markers from pairs.sandbag feed pairs.cyclone; both checked against the oracle."""
+    from pypairs_b200 import pairs
+    rng = np.random.default_rng(48)
+    g, sizes = 19084, {"G2M": 76, "S": 80, "G1": 91}
+    lab = np.concatenate([np.full(n, i) for i, n in enumerate(sizes.values())])
+    base = rng.normal(0.0, 1.5, g)
+    de = rng.random(g) < 0.03
+    de_class = rng.integers(0, 3, g)
+    lam = 3.0 * np.exp(base)[None, :] * np.where((lab[:, None] == de_class[None, :]) & de[None, :], 6.0, 1.0)
+    x = rng.poisson(lam).astype(np.float32)
+    gn = ["gene{}".format(i) for i in range(g)]
+    sn = ["cell{}".format(i) for i in range(len(lab))]
+    ann = {k: np.where(lab == i)[0].tolist() for i, k in enumerate(sizes.keys())}
+    markers = pairs.sandbag(x, ann, gn, sn, fraction=0.6)
+    assert set(markers.keys()) == set(sizes.keys()) and sum(len(v) for v in markers.values()) > 1000
+    # oracle on a gene subset that contains marker genes
+    top = sorted({a for v in markers.values() for a, _ in v[:40]} | {b for v in markers.values() for _, b in v[:40]})
+    cols = np.array(sorted(int(n[4:]) for n in top))[:160]
+    keep = cols[(x[:, cols] != 0).any(axis=0)]
+    rr, cc, kk = orc.sandbag_arrays(x[:, keep].astype(np.float64), lab, 3, 0.6)
+    names = list(sizes.keys())
+    exp = {(gn[keep[r]], gn[keep[c]], names[k]) for r, c, k in zip(rr, cc, kk)}
+    kept_names = {gn[i] for i in keep}
+    got = {(a, b, k) for k, v in markers.items() for a, b in v if a in kept_names and b in kept_names}
+    assert got == exp
+    # score an "unsorted" batch with the markers just found (thousands of pairs per class)
+    y = rng.poisson(3.0 * np.exp(base)[None, :] * np.ones((60, 1))).astype(np.float32)
+    sub = {k: v[:3000] for k, v in markers.items()}
+    df = pairs.cyclone(y, sub, gn, ["u{}".format(i) for i in range(60)], iterations=100, min_iter=10, min_pairs=5)
+    pr, us = orc.filter_marker_pairs(sub, gn)
+    for k in sub:
+        assert np.array_equal(df[k].values, orc.phase_scores(y, 100, 10, 5, pr[k], us[k]), equal_nan=True)
