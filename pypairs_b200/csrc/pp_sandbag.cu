@@ -89,7 +89,7 @@ struct Chunk {  // a run of cell words of one class
     int32_t w_begin;
     int32_t n_words;
     int32_t class_end;  // class index if this chunk closes the class, else -1
-    int32_t pad;
+    int32_t flush;      // WIDE kernels: fold the 16-bit counters into the 32-bit ones after this chunk
 };
 
 struct PairParams {
@@ -97,21 +97,23 @@ struct PairParams {
     const Chunk *chunks;
     const int2 *tiles;       // (ta, tb) per CTA
     const int32_t *thr;      // per class, clipped to int32
-    unsigned long long *out; // compacted (key << 8 | class)
+    unsigned long long *out; // compacted (key << 16 | class)
     unsigned long long *out_count;
     unsigned long long out_cap;
     int n_genes, n_words, n_planes, n_chunks, n_classes, wc_max;
 };
 
 // TI x TJ = per-thread register tile of gene pairs (TI in {4, 8}, TJ = 4), thread grid (128/TI) x (64/TJ).
-template <int TI, int TJ>
+// WIDE = classes with more than 65 535 cells and / or more than 254 classes: the packed 16+16-bit counters
+// are folded into 32-bit counters kept in shared memory every <= 2047 cell words, and the per-pair decision
+// state uses 16-bit fields in two registers.
+template <int TI, int TJ, bool WIDE>
 __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(const PairParams P) {
     constexpr int NTJ = TILE_B / TJ;
     constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;
     static_assert(TJ == 4 && (TI == 4 || TI == 8), "shared loads below are written for these tiles");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ int32_t thr_s[256];
 
     const int tid = threadIdx.x;
     const int ti = tid / NTJ, tj = tid % NTJ;
@@ -121,7 +123,10 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
     const uint32_t stage_words = 3u * blk_words;
     uint32_t *smem = reinterpret_cast<uint32_t *>(smem_raw);
 
-    for (int i = tid; i < P.n_classes; i += PAIR_THREADS) thr_s[i] = P.thr[i];
+    // WIDE: [TI*TJ][2][threads] 32-bit counters behind the stage ring
+    int32_t *wide = reinterpret_cast<int32_t *>(smem + (size_t)STAGES * stage_words) + tid;
+    if (WIDE)
+        for (int q = 0; q < TI * TJ * 2; ++q) wide[q * PAIR_THREADS] = 0;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
@@ -147,11 +152,14 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
     if (tid == 0)
         for (int c = 0; c < STAGES - 1 && c < P.n_chunks; ++c) issue(c);
 
-    uint32_t acc[TI][TJ], st[TI][TJ];
+    uint32_t acc[TI][TJ], st[TI][TJ], st2[WIDE ? TI : 1][WIDE ? TJ : 1];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) acc[i][j] = 0, st[i][j] = 0;
+        for (int j = 0; j < TJ; ++j) {
+            acc[i][j] = 0, st[i][j] = 0;
+            if (WIDE) st2[i][j] = 0;
+        }
 
     const int la = ti * TI;  // first local a-gene (0..127), never straddles a 64-gene block
     const uint32_t a_off = (uint32_t)(la >> 6) * blk_words + (la & 63);
@@ -201,19 +209,38 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
             sa += B * 64;
             sb += B * 64;
         }
-        if (ch.class_end >= 0) {  // CTA-uniform: thresholds of sandbag.py:184-190 for this class
-            const uint32_t k = (uint32_t)ch.class_end;
-            const int32_t thr = thr_s[k];
+        if (WIDE && (ch.flush || ch.class_end >= 0)) {
 #pragma unroll
             for (int i = 0; i < TI; ++i)
 #pragma unroll
                 for (int j = 0; j < TJ; ++j) {
-                    const int32_t pos = (int32_t)(acc[i][j] & 0xffffu), neg = (int32_t)(acc[i][j] >> 16);
-                    uint32_t s2 = st[i][j];
-                    if (pos >= thr) s2 = ((s2 & 0xff00ffffu) | (k << 16)) + 1u;
-                    if (neg >= thr) s2 = ((s2 & 0x00ffffffu) | (k << 24)) + 0x100u;
-                    st[i][j] = s2;
+                    wide[((i * TJ + j) * 2 + 0) * PAIR_THREADS] += (int32_t)(acc[i][j] & 0xffffu);
+                    wide[((i * TJ + j) * 2 + 1) * PAIR_THREADS] += (int32_t)(acc[i][j] >> 16);
                     acc[i][j] = 0;
+                }
+        }
+        if (ch.class_end >= 0) {  // CTA-uniform: thresholds of sandbag.py:184-190 for this class
+            const uint32_t k = (uint32_t)ch.class_end;
+            const int32_t thr = __ldg(P.thr + k);
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) {
+                    if (WIDE) {  // st = nup | ndn << 16, st2 = up_idx | dn_idx << 16
+                        const int32_t pos = wide[((i * TJ + j) * 2 + 0) * PAIR_THREADS];
+                        const int32_t neg = wide[((i * TJ + j) * 2 + 1) * PAIR_THREADS];
+                        wide[((i * TJ + j) * 2 + 0) * PAIR_THREADS] = 0;
+                        wide[((i * TJ + j) * 2 + 1) * PAIR_THREADS] = 0;
+                        if (pos >= thr) { st[i][j] += 1u; st2[i][j] = (st2[i][j] & 0xffff0000u) | k; }
+                        if (neg >= thr) { st[i][j] += 0x10000u; st2[i][j] = (st2[i][j] & 0x0000ffffu) | (k << 16); }
+                    } else {     // st = nup | ndn << 8 | up_idx << 16 | dn_idx << 24
+                        const int32_t pos = (int32_t)(acc[i][j] & 0xffffu), neg = (int32_t)(acc[i][j] >> 16);
+                        uint32_t s2 = st[i][j];
+                        if (pos >= thr) s2 = ((s2 & 0xff00ffffu) | (k << 16)) + 1u;
+                        if (neg >= thr) s2 = ((s2 & 0x00ffffffu) | (k << 24)) + 0x100u;
+                        st[i][j] = s2;
+                        acc[i][j] = 0;
+                    }
                 }
         }
     }
@@ -228,19 +255,21 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
         for (int j = 0; j < TJ; ++j) {
             const int ga = ga0 + i, gb = gb0 + j;
             const uint32_t s2 = st[i][j];
-            const uint32_t nup = s2 & 0xffu, ndn = (s2 >> 8) & 0xffu;
+            const uint32_t nup = WIDE ? (s2 & 0xffffu) : (s2 & 0xffu), ndn = WIDE ? (s2 >> 16) : ((s2 >> 8) & 0xffu);
+            const uint32_t up_idx = WIDE ? (st2[i][j] & 0xffffu) : ((s2 >> 16) & 0xffu);
+            const uint32_t dn_idx = WIDE ? (st2[i][j] >> 16) : ((s2 >> 24) & 0xffu);
             unsigned long long key = 0;
             bool emit = false;
             if (ga < gb && gb < P.n_genes) {
                 if (nup == 1u) {
                     if (ndn == C - 1u) {
                         emit = true;
-                        key = (((unsigned long long)ga * P.n_genes + gb) << 8) | ((s2 >> 16) & 0xffu);
+                        key = (((unsigned long long)ga * P.n_genes + gb) << 16) | up_idx;
                     }
                 } else if (ndn == 1u) {
                     if (nup == C - 1u) {
                         emit = true;
-                        key = (((unsigned long long)gb * P.n_genes + ga) << 8) | ((s2 >> 24) & 0xffu);
+                        key = (((unsigned long long)gb * P.n_genes + ga) << 16) | dn_idx;
                     }
                 }
             }
@@ -436,7 +465,7 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: x_dtype must be PP_F32/PP_F64");
     if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad matrix shape");
     if (n_classes < 1) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: n_classes < 1");
-    if (n_classes > 254) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 254 classes (%d)", n_classes);
+    if (n_classes > 65534) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65534 classes (%d)", n_classes);
     if (n_shards < 1 || shard < 0 || shard >= n_shards) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad shard %d/%d", shard, n_shards);
     if (n_genes < 0 || n_cells < 0) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: negative size");
     *out_keys = nullptr;
@@ -445,9 +474,10 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     ctx->tm = pp_timings();
     ctx->launches = 0;
     int64_t total = 0;
+    bool wide = n_classes > 254;
     for (int k = 0; k < n_classes; ++k) {
         if (class_sizes[k] <= 0) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: class %d is empty", k);
-        if (class_sizes[k] > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: class %d has more than 65535 cells", k);
+        if (class_sizes[k] > 65535) wide = true;
         total += class_sizes[k];
     }
     if (total != n_cells) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: class_sizes do not sum to n_cells");
@@ -549,18 +579,27 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
 
     // ---- chunks (runs of <= wc_max words inside one class)
-    const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 2048;
+    const int wide_bytes = wide ? 16 * 2 * 512 * 4 : 0;  // 32-bit counters of the WIDE kernel
+    const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 2048 - wide_bytes;
     int wc_max = smem_budget / (STAGES * 3 * B * 64 * 4);
     wc_max = std::max(1, std::min(wc_max, 16));
-    const size_t dyn_smem = (size_t)STAGES * 3 * wc_max * B * 64 * 4;
+    const size_t dyn_smem = (size_t)STAGES * 3 * wc_max * B * 64 * 4 + wide_bytes;
     std::vector<Chunk> chunks;
+    int since_flush = 0;
     for (int k = 0; k < n_classes; ++k)
         for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc_max) {
             Chunk c;
             c.w_begin = w;
             c.n_words = std::min(wc_max, class_w0[k + 1] - w);
             c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
-            c.pad = 0;
+            c.flush = 0;
+            since_flush += c.n_words;
+            if (c.class_end >= 0) {
+                since_flush = 0;
+            } else if (since_flush + wc_max > 2047) {  // the next chunk could overflow a 16-bit counter
+                c.flush = 1;
+                since_flush = 0;
+            }
             chunks.push_back(c);
         }
     // ---- tiles of this shard: (ta, tb) with tb >= 2*ta (only those contain pairs g1 < g2)
@@ -592,7 +631,8 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
                                                                      std::max<int64_t>(1 << 22, n_pairs_shard / 16));
     unsigned long long count = 0;
     // 4x4 register tiles, 512 threads (16 warps/SM): measured 75.0 ms on cfg3 vs 87.8 ms for 8x4 / 256 threads
-    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     for (int attempt = 0; attempt < 2; ++attempt) {
         PP_CUDA(d_out.alloc(sizeof(unsigned long long) * cap, st));
         PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
@@ -611,7 +651,10 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             P.n_chunks = (int)chunks.size();
             P.n_classes = n_classes;
             P.wc_max = wc_max;
-            pair_kernel<4, 4><<<(unsigned)tiles.size(), 512, dyn_smem, st>>>(P);
+            if (wide)
+                pair_kernel<4, 4, true><<<(unsigned)tiles.size(), 512, dyn_smem, st>>>(P);
+            else
+                pair_kernel<4, 4, false><<<(unsigned)tiles.size(), 512, dyn_smem, st>>>(P);
             PP_CHECK_LAUNCH();
         }
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -649,8 +692,8 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     if (count > 0) {
         PP_CUDA(d_out2.alloc(sizeof(unsigned long long) * count, st));
         unsigned long long *sorted = nullptr;
-        const int hi_bit = 8 + bit_length64((uint64_t)n_genes * (uint64_t)n_genes);
-        rc = radix_sort_u64(ctx, d_out.as<unsigned long long>(), d_out2.as<unsigned long long>(), (int64_t)count, 8,
+        const int hi_bit = 16 + bit_length64((uint64_t)n_genes * (uint64_t)n_genes);
+        rc = radix_sort_u64(ctx, d_out.as<unsigned long long>(), d_out2.as<unsigned long long>(), (int64_t)count, 16,
                             hi_bit, &sorted);
         if (rc) return rc;
         hk = (uint64_t *)malloc(sizeof(uint64_t) * count);
@@ -668,8 +711,8 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             return pp_fail(ctx, PP_ECUDA, "pp_sandbag: result copy failed: %s", cudaGetErrorString(e));
         }
         for (unsigned long long i = 0; i < count; ++i) {
-            hc[i] = (int32_t)(hk[i] & 0xffu);
-            hk[i] >>= 8;
+            hc[i] = (int32_t)(hk[i] & 0xffffu);
+            hk[i] >>= 16;
         }
     }
     PP_CUDA(cudaEventRecord(ctx->ev[4], st));

@@ -235,3 +235,64 @@ def test_full_size_properties():
     assert got == sorted(zip(rr.tolist(), cc.tolist(), kk.tolist()))
     print("cfg3 full size: {} markers, {} planes, kernel {:.1f} ms, prep {:.1f} ms".format(
         len(keys), tm["n_planes"], tm["main_ms"], tm["prep_ms"]))
+
+
+def test_wide_counters_and_many_classes():
+    """Classes above 65 535 cells (16-bit counters folded into 32-bit ones) and more than 254 classes."""
+    rng = np.random.default_rng(21)
+    # (a) one class of 70 001 cells next to a small one
+    n, g = 70001 + 4000, 130
+    lab = np.concatenate([np.zeros(70001, dtype=np.int64), np.ones(4000, dtype=np.int64)])
+    lam = 2.0 * np.exp(rng.normal(0, 1.0, g))[None, :] * np.where((lab[:, None] == 1) & (np.arange(g) % 5 == 0)[None, :], 5.0, 1.0)
+    x = rng.poisson(lam).astype(np.float32)
+    perm = rng.permutation(n)
+    x, lab = x[perm], lab[perm]
+    thr = orc.calc_thresholds(np.bincount(lab, minlength=2), 0.65)
+    probes = np.array([[0, 5], [3, 100], [7, 129], [10, 11]])
+    keys, cls, tm, ppos, pneg = run_kernel(x, lab, 2, thr, probe_pairs=probes)
+    rr, cc, kk = orc.sandbag_arrays(x, lab, 2, 0.65)
+    assert np.array_equal(keys, (rr * g + cc).astype(np.uint64)) and np.array_equal(cls, kk.astype(np.int32))
+    assert len(keys) > 0
+    epos, eneg = orc.pair_counts(x, lab, 2, probes)
+    assert np.array_equal(ppos, epos) and np.array_equal(pneg, eneg) and epos.max() > 65535
+    # (b) 300 classes
+    n, g, c = 3000, 90, 300
+    lab = np.arange(n) % c
+    x = rng.poisson(3.0, (n, g)).astype(np.float64) + (lab[:, None] == (np.arange(g) * 7 % c)[None, :]) * 20.0
+    for frac in (0.65, 0.3):
+        thr = orc.calc_thresholds(np.bincount(lab, minlength=c), frac)
+        keys, cls, tm = run_kernel(x, lab, c, thr)
+        rr, cc, kk = orc.sandbag_arrays(x, lab, c, frac)
+        assert np.array_equal(keys, (rr * g + cc).astype(np.uint64)) and np.array_equal(cls, kk.astype(np.int32))
+
+
+def test_atlas_shape_properties():
+    """configs[3] shape (30k genes x 50k cells, 10 classes): invariants at full size + oracle on a gene subset."""
+    import torch
+    g, n, c = 30000, 50000, 10
+    gen = torch.Generator(device="cuda").manual_seed(20264)
+    lab = torch.randint(0, c, (n,), generator=gen, device="cuda")
+    base = torch.randn(g, generator=gen, device="cuda") * 1.5
+    de = torch.rand(g, generator=gen, device="cuda") < 0.02
+    de_class = torch.randint(0, c, (g,), generator=gen, device="cuda")
+    sign = torch.where(torch.rand(g, generator=gen, device="cuda") < 0.5, -1.0, 1.0)
+    eff = torch.where(de, torch.pow(2.0, 2.0 * sign), torch.ones_like(sign))
+    x = torch.empty((n, g), dtype=torch.float32, device="cuda")
+    for i in range(0, n, 5000):
+        lam = 3.0 * torch.exp(base)[None, :] * torch.where(lab[i:i + 5000, None] == de_class[None, :], eff[None, :], 1.0)
+        x[i:i + 5000] = torch.poisson(lam, generator=gen)
+    x[:, 0] += 1.0
+    lab_h = lab.cpu().numpy().astype(np.int64)
+    thr = orc.calc_thresholds(np.bincount(lab_h, minlength=c), 0.65)
+    keys, cls, tm = run_kernel(x, lab_h, c, thr)
+    assert np.all(keys[1:] > keys[:-1]) and tm["n_units"] == g * (g - 1) // 2
+    rows, cols = (keys // np.uint64(g)).astype(np.int64), (keys % np.uint64(g)).astype(np.int64)
+    sub = np.sort(np.random.default_rng(1).choice(g, 120, replace=False))
+    xs = x[:, torch.from_numpy(sub).cuda()].cpu().numpy().astype(np.float64)
+    rr, cc, kk = orc.sandbag_arrays(xs, lab_h, c, 0.65)
+    pos = {int(v): i for i, v in enumerate(sub)}
+    m = np.isin(rows, sub) & np.isin(cols, sub)
+    got = sorted((pos[int(r)], pos[int(q)], int(k)) for r, q, k in zip(rows[m], cols[m], cls[m]))
+    assert got == sorted(zip(rr.tolist(), cc.tolist(), kk.tolist()))
+    print("cfg4 full size: {} markers, {} planes, kernel {:.1f} ms, prep {:.1f} ms -> {:.3g} pair*cell/s".format(
+        len(keys), tm["n_planes"], tm["main_ms"], tm["prep_ms"], g * (g - 1) / 2 * n / (tm["main_ms"] * 1e-3)))
