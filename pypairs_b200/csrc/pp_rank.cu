@@ -14,6 +14,9 @@
 //      cell (count data stored as doubles varies in 2-3 bytes; float32 input in <= 4)
 //   3. head flags + scan -> dense rank, scattered back to gene order as u16
 // Keys live in a per-CTA global scratch (L2 resident: 32768 genes * 10 B * 2 buffers).
+// Count fast path: when every kept value of the cell is an integer in [0, 65535] (raw UMI / read counts, the
+// usual sandbag / cyclone input) no sort is needed: a 65 536-bit presence bitmap in shared memory, a prefix
+// popcount over its 2048 words, and rank(v) = #present values below v.  Three coalesced passes over the row.
 #include <stdarg.h>
 
 #include "pp_common.cuh"
@@ -40,7 +43,14 @@ template <typename T> struct KeyOf;
 template <> struct KeyOf<float> { typedef uint32_t type; };
 template <> struct KeyOf<double> { typedef uint64_t type; };
 
+constexpr int BM_WORDS = 2048;  // 65 536-bit presence bitmap of the count fast path
+
+__device__ __forceinline__ bool is_small_count(float v) { return v >= 0.0f && v < 65536.0f && v == truncf(v); }
+__device__ __forceinline__ bool is_small_count(double v) { return v >= 0.0 && v < 65536.0 && v == trunc(v); }
+
 struct RankSmem {
+    uint32_t bitmap[BM_WORDS];
+    uint32_t bm_prefix[BM_WORDS];
     uint32_t whist[RANK_WARPS][256];  // per-warp digit histogram -> running scatter offsets
     uint32_t dig_total[256];
     uint32_t wtot[RANK_WARPS];
@@ -75,6 +85,44 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
             continue;
         }
         const T *xr = x + (int64_t)row * ld;
+        // ---- 0. count fast path
+        {
+            bool small = true;
+            for (int g = tid; g < n; g += RANK_THREADS) small = small && is_small_count(xr[gene_cols[g]]);
+            for (int i = tid; i < BM_WORDS; i += RANK_THREADS) sm.bitmap[i] = 0;
+            if (__syncthreads_and(small)) {  // CTA-uniform (NaN fails the test and takes the sort path)
+                for (int g = tid; g < n; g += RANK_THREADS) {
+                    const uint32_t u = (uint32_t)xr[gene_cols[g]];
+                    atomicOr(&sm.bitmap[u >> 5], 1u << (u & 31));
+                }
+                __syncthreads();
+                // exclusive prefix popcount over the 2048 words: 4 words per thread, warp scan, warp totals
+                uint32_t c[4], t4 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { c[j] = __popc(sm.bitmap[tid * 4 + j]); t4 += c[j]; }
+                uint32_t incl = t4;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) sm.wtot[warp] = incl;
+                __syncthreads();
+                uint32_t base = 0;
+                for (int w = 0; w < warp; ++w) base += sm.wtot[w];
+                uint32_t run = base + incl - t4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { sm.bm_prefix[tid * 4 + j] = run; run += c[j]; }
+                if (tid == RANK_THREADS - 1) atomicMax(&flags[0], (int)run - 1);  // distinct values - 1
+                __syncthreads();
+                for (int g = tid; g < n; g += RANK_THREADS) {
+                    const uint32_t u = (uint32_t)xr[gene_cols[g]];
+                    out[g] = (uint16_t)(sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & ((1u << (u & 31)) - 1u)));
+                }
+                __syncthreads();  // bitmap / prefix reused by the next cell
+                continue;
+            }
+        }
         // ---- 1. gather + key transform, find the key bits that vary
         bool nan = false;
         K first = key_of(xr[gene_cols[0]], nan);
