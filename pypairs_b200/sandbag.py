@@ -55,13 +55,18 @@ def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
     of first appearance, tuples are (gene_names[row], gene_names[col]) as numpy strings."""
     if len(keys) == 0:
         return {}
-    rows = (keys // np.uint64(n_genes)).astype(np.int64)
-    cols = (keys % np.uint64(n_genes)).astype(np.int64)
+    k64 = np.ascontiguousarray(keys).view(np.int64)  # keys < 2^32: the signed view is exact and divides faster
+    rows, cols = k64 // n_genes, k64 % n_genes
     names = np.empty(len(gene_names), dtype=object)  # the np.str_ scalars `gene_names[g]` yields, made once
-    names[:] = [gene_names[i] for i in range(len(gene_names))]
-    _, first = np.unique(cls, return_index=True)
+    names[:] = list(gene_names)
+    # classes in order of first appearance in the scan: with repeated indices the last write wins, so writing
+    # the positions in reverse leaves the smallest position of every class
+    first = np.full(len(class_names), len(cls), dtype=np.int64)
+    first[cls[::-1]] = np.arange(len(cls) - 1, -1, -1)
     out = {}
-    for k in cls[np.sort(first)]:
+    for k in np.argsort(first, kind="stable"):
+        if first[k] == len(cls):
+            break
         m = cls == k
         out[class_names[k]] = list(zip(names[rows[m]].tolist(), names[cols[m]].tolist()))
     return out
