@@ -173,6 +173,7 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
         df = e2e_call()
     sync_all(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, world)
+    e2e_tm = pairs.cyclone.last_timings
     assert np.array_equal(df[keys[0]].values[rank * CYC_CELLS:(rank + 1) * CYC_CELLS], sc[0])  # same answer both ways
 
     total_cells = CYC_CELLS * world
@@ -183,8 +184,11 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
         "kernel_ms": {"score": main_step, "prep_and_tables": prep_step},
         "gpu_launches": launches, "clocks": clocks,
         "e2e": {"value": total_cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": CYC_CELLS * CYC_GENES * 4, "d2h_bytes_per_step": len(keys) * CYC_CELLS * 8,
-                "api": "pypairs_b200.pairs.cyclone(ndarray pinned) -> DataFrame"},
+                "h2d_bytes_per_step": int(e2e_tm["h2d_bytes"]), "d2h_bytes_per_step": len(keys) * CYC_CELLS * 8,
+                "host_matrix_bytes": CYC_CELLS * CYC_GENES * 4,
+                "api": "pypairs_b200.pairs.cyclone(ndarray pinned) -> DataFrame; chunks alternate between a host-side "
+                       "gather of the {} marker-gene columns (all cores, pinned staging) and full-row copies, "
+                       "both overlapped with rank + score of earlier chunks".format(n_union)},
         "roofline": {"bound": "int_alu", "kernel": "score_kernel",
                      "achieved": alg_ops / (main_step * 1e-3) / 1e9, "peak": peaks["lop3_lane_ops_per_s"] / 1e9,
                      "unit": "Gop/s", "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],
@@ -264,6 +268,7 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
         d = e2e_call()
     sync_all(world)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, world)
+    e2e_tm = pairs.sandbag.last_timings
     n_markers = sum(len(v) for v in d.values())
     my_pairs = tm["n_units"]
     alg_ops = 2.0 * my_pairs * n  # one `>` and one `<` per gene pair x cell (sandbag.py:179-182), this rank's launch
@@ -274,7 +279,7 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
         "value": units / (ms_step * 1e-3), "ms_per_step": ms_step, "device_ms_per_step": max_over_ranks(dev_ms / args.steps, world),
         "kernel_ms": {"pair": main_step, "rank_and_bitslice": prep_step}, "gpu_launches": launches, "clocks": clocks,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "pair*cell/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": n * g * 4, "d2h_bytes_per_step": int(n_markers * 12 / max(world, 1)),
+                "h2d_bytes_per_step": int(e2e_tm["h2d_bytes"]), "d2h_bytes_per_step": int(n_markers * 12 / max(world, 1)),
                 "api": "pypairs_b200.pairs.sandbag(ndarray pinned) -> dict"},
         "roofline": {"bound": "int_alu", "kernel": "pair_kernel", "achieved": alg_ops / (main_step * 1e-3) / 1e9,
                      "peak": peaks["lop3_lane_ops_per_s"] / 1e9, "unit": "Gop/s",

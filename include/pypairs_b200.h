@@ -65,6 +65,7 @@ typedef struct pp_timings {
     int32_t n_planes; /* sandbag: bit planes used for the rank encoding */
     int32_t n_launches; /* kernels launched by this call */
     int64_t n_units;  /* sandbag: gene pairs evaluated by this shard; cyclone: cells scored by this shard */
+    int64_t h2d_bytes; /* bytes of the expression matrix actually copied host -> device by this call */
 } pp_timings;
 
 int pp_version(void);

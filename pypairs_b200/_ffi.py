@@ -22,7 +22,7 @@ SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "
 class Timings(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("prep_ms", ctypes.c_float), ("main_ms", ctypes.c_float),
                 ("post_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("n_planes", ctypes.c_int32),
-                ("n_launches", ctypes.c_int32), ("n_units", ctypes.c_int64)]
+                ("n_launches", ctypes.c_int32), ("n_units", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

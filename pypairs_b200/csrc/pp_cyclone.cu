@@ -24,6 +24,7 @@
 // sides; score = below / iterations as one IEEE double division (:246).
 #include <algorithm>
 #include <map>
+#include <thread>
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -505,6 +506,33 @@ const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
     return v;
 }
 
+// Host-side gene filtering (the north-star keeps it on the host): copy the marker-gene columns of rows
+// [r0, r0 + nr) of a host matrix into a dense [nr, n_cols_kept] pinned buffer, rows split over threads.
+template <typename T>
+void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *cols, int n_kept, T *dst, int n_threads) {
+    auto work = [=](int64_t a, int64_t b) {
+        for (int64_t r = a; r < b; ++r) {
+            const T *src = x + (r0 + r) * ld;
+            T *d = dst + r * n_kept;
+            for (int j = 0; j < n_kept; ++j) d[j] = src[cols[j]];
+        }
+    };
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, nr / 64));
+    if (n_threads == 1) {
+        work(0, nr);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, nr * t / n_threads, nr * (t + 1) / n_threads);
+    for (auto &th : pool) th.join();
+}
+
+int host_threads() {
+    if (const char *e = getenv("PP_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hc ? hc : 8u, 32u));
+}
+
 }  // namespace
 
 PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t class_index, int32_t n,
@@ -584,9 +612,13 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     DevBuf d_x, d_rows, d_uni, d_rank, d_flags, d_scores, d_oh, d_ot, d_cd;
     const uint8_t *x0 = (const uint8_t *)x + (size_t)row_begin * ld * esz;
     // Host input is streamed in chunks of one full wave of 64-cell tiles: H2D of chunk i+1 (copy stream)
-    // overlaps rank + score of chunk i (compute stream).  Device input is processed in one launch.
+    // overlaps rank + score of chunk i (compute stream).  When the marker genes are at most a quarter of the
+    // columns the host first gathers just those columns into a pinned staging buffer (gene filtering on the
+    // host, multi-threaded), so PCIe carries U instead of n_cols values per cell.  Device input is processed
+    // in one launch.
     const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
-    const bool pipelined = !x_is_device && n_cells > wave_cells;
+    const bool host_gather = !x_is_device && (int64_t)U * 4 <= n_cols;
+    const bool pipelined = !x_is_device && (n_cells > wave_cells || host_gather);
     const int64_t chunk_cells = pipelined ? wave_cells : n_cells;
     {
         std::vector<int32_t> rows(chunk_cells);
@@ -695,6 +727,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             PP_CUDA(d_x.alloc((size_t)n_cells * ld * esz, st));
             PP_CUDA(cudaEventRecord(ctx->ev[6], st));
             PP_CUDA(cudaMemcpyAsync(d_x.p, x0, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
+            ctx->tm.h2d_bytes += (int64_t)((size_t)n_cells * ld * esz);
             PP_CUDA(cudaEventRecord(ctx->ev[7], st));
             dx = d_x.p;
         }
@@ -709,48 +742,133 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         PP_CHECK_LAUNCH();
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
     } else {
-        DevBuf d_buf[2];
-        cudaEvent_t ev_copied[2], ev_free[2], ev_c0, ev_c1;
+        // Two ways for a chunk of cells to reach the device (one double-buffered lane is used per call):
+        //   G (gather): host threads copy the marker columns into pinned staging, H2D of [nc, U]
+        //   D (direct): H2D of the full rows [nc, ld], columns picked by the rank kernel
+        // Measured on the B200 box (16 host cores, cfg2: 100k x 20k f32, 1 479 marker genes): D 195 ms, G 161 ms,
+        // alternating both at once 184 ms -- all three move ~40 GB/s through host DRAM, which is the bound, so the
+        // path that touches the fewest host bytes (G, when the markers are <= 1/4 of the columns) is used alone.
+        struct Lane {
+            DevBuf buf[2];
+            cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+            int used = 0;
+            cudaStream_t cs = nullptr;
+            int64_t ldv = 0;
+            const int32_t *cols = nullptr;
+        } G, D;
+        DevBuf d_ident;
+        cudaEvent_t ev_c0, ev_c1;
         std::vector<cudaEvent_t> ev_s;
-        for (int b = 0; b < 2; ++b) {
-            PP_CUDA(d_buf[b].alloc((size_t)chunk_cells * ld * esz, st));
-            PP_CUDA(cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming));
-            PP_CUDA(cudaEventCreateWithFlags(&ev_free[b], cudaEventDisableTiming));
+        const int n_thr = host_threads();
+        const int64_t n_chunks = (n_cells + chunk_cells - 1) / chunk_cells;
+        const bool hybrid = false;
+        const bool use_d = !host_gather;
+        if (host_gather) {
+            const size_t need = (size_t)chunk_cells * U * esz;
+            if (ctx->pin_bytes < need) {
+                for (int b = 0; b < 2; ++b) {
+                    if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
+                    ctx->pin[b] = nullptr;
+                }
+                ctx->pin_bytes = 0;
+                for (int b = 0; b < 2; ++b) PP_CUDA(cudaHostAlloc(&ctx->pin[b], need, cudaHostAllocDefault));
+                ctx->pin_bytes = need;
+            }
+            std::vector<int32_t> ident(U);
+            for (int j = 0; j < U; ++j) ident[j] = j;
+            PP_CUDA(d_ident.alloc(sizeof(int32_t) * U, st));
+            PP_CUDA(cudaMemcpyAsync(d_ident.p, ident.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, st));
+            PP_CUDA(cudaStreamSynchronize(st));  // ident is a local
+            G.cs = ctx->copy_stream;
+            G.ldv = U;
+            G.cols = d_ident.as<int32_t>();
+        }
+        if (use_d) {
+            D.cs = host_gather ? ctx->copy_stream2 : ctx->copy_stream;
+            D.ldv = ld;
+            D.cols = d_uni.as<int32_t>();
+        }
+        for (Lane *L : {&G, &D}) {
+            if (!L->cs) continue;
+            for (int b = 0; b < 2; ++b) {
+                PP_CUDA(L->buf[b].alloc((size_t)chunk_cells * L->ldv * esz, st));
+                PP_CUDA(cudaEventCreateWithFlags(&L->copied[b], cudaEventDisableTiming));
+                PP_CUDA(cudaEventCreateWithFlags(&L->freed[b], cudaEventDisableTiming));
+            }
         }
         PP_CUDA(cudaEventCreate(&ev_c0));
         PP_CUDA(cudaEventCreate(&ev_c1));
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
-        PP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[3], 0));  // buffers exist before the first copy
-        PP_CUDA(cudaEventRecord(ev_c0, ctx->copy_stream));
-        int i = 0;
-        for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, ++i) {
-            const int b = i & 1;
-            const int64_t nc = std::min(chunk_cells, n_cells - c0);
-            if (i >= 2) PP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev_free[b], 0));
-            PP_CUDA(cudaMemcpyAsync(d_buf[b].p, x0 + (size_t)c0 * ld * esz, (size_t)nc * ld * esz, cudaMemcpyHostToDevice,
-                                    ctx->copy_stream));
-            PP_CUDA(cudaEventRecord(ev_copied[b], ctx->copy_stream));
-            PP_CUDA(cudaStreamWaitEvent(st, ev_copied[b], 0));
-            rc = pp_rank_launch(ctx, d_buf[b].p, x_dtype, ld, d_rows.as<int32_t>(), nc, d_uni.as<int32_t>(), U,
-                                d_rank.as<uint16_t>() + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
-            if (rc) return rc;
-            PP_CUDA(cudaEventRecord(ev_free[b], st));
+        for (Lane *L : {&G, &D})
+            if (L->cs) PP_CUDA(cudaStreamWaitEvent(L->cs, ctx->ev[3], 0));  // buffers exist before the first copy
+        PP_CUDA(cudaEventRecord(ev_c0, host_gather ? G.cs : D.cs));
+
+        struct Pending { Lane *L; int slot; int64_t c0, nc; };
+        auto start_copy = [&](Lane &L, int64_t c0, int64_t nc, Pending &out) -> int {
+            const int b = L.used & 1;
+            const void *src = x0 + (size_t)c0 * ld * esz;
+            if (&L == &G) {
+                if (L.used >= 2) PP_CUDA(cudaEventSynchronize(L.copied[b]));  // H2D two chunks ago has drained pin[b]
+                if (x_dtype == PP_F64)
+                    gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], n_thr);
+                else
+                    gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], n_thr);
+                src = ctx->pin[b];
+            }
+            if (L.used >= 2) PP_CUDA(cudaStreamWaitEvent(L.cs, L.freed[b], 0));  // rank kernel two chunks ago is done
+            PP_CUDA(cudaMemcpyAsync(L.buf[b].p, src, (size_t)nc * L.ldv * esz, cudaMemcpyHostToDevice, L.cs));
+            ctx->tm.h2d_bytes += (int64_t)((size_t)nc * L.ldv * esz);
+            PP_CUDA(cudaEventRecord(L.copied[b], L.cs));
+            L.used++;
+            out = Pending{&L, b, c0, nc};
+            return PP_OK;
+        };
+        auto compute = [&](const Pending &p) -> int {
+            Lane &L = *p.L;
+            PP_CUDA(cudaStreamWaitEvent(st, L.copied[p.slot], 0));
+            int r = pp_rank_launch(ctx, L.buf[p.slot].p, x_dtype, L.ldv, d_rows.as<int32_t>(), p.nc, L.cols, U,
+                                   d_rank.as<uint16_t>() + p.c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            if (r) return r;
+            PP_CUDA(cudaEventRecord(L.freed[p.slot], st));
             cudaEvent_t e0, e1;
             PP_CUDA(cudaEventCreate(&e0));
             PP_CUDA(cudaEventCreate(&e1));
             ev_s.push_back(e0);
             ev_s.push_back(e1);
-            P.rank = d_rank.as<uint16_t>() + c0 * rank_ld;
-            P.n_cells = nc;
-            P.out_off = c0;
+            P.rank = d_rank.as<uint16_t>() + p.c0 * rank_ld;
+            P.n_cells = p.nc;
+            P.out_off = p.c0;
             PP_CUDA(cudaEventRecord(e0, st));
-            launch_score(nc);
+            launch_score(p.nc);
             PP_CHECK_LAUNCH();
             PP_CUDA(cudaEventRecord(e1, st));
+            return PP_OK;
+        };
+        for (int64_t i = 0; i < n_chunks;) {
+            const int64_t a0 = i * chunk_cells, an = std::min(chunk_cells, n_cells - a0);
+            Pending pa, pb;
+            bool have_b = false;
+            if (hybrid && i + 1 < n_chunks) {  // the copy engine streams chunk i+1 while the CPU gathers chunk i
+                const int64_t b0 = (i + 1) * chunk_cells;
+                rc = start_copy(D, b0, std::min(chunk_cells, n_cells - b0), pb);
+                if (rc) return rc;
+                have_b = true;
+            }
+            rc = start_copy(host_gather ? G : D, a0, an, pa);
+            if (rc) return rc;
+            rc = compute(pa);
+            if (rc) return rc;
+            if (have_b) {
+                rc = compute(pb);
+                if (rc) return rc;
+            }
+            i += have_b ? 2 : 1;
         }
-        PP_CUDA(cudaEventRecord(ev_c1, ctx->copy_stream));
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
-        PP_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        for (Lane *L : {&G, &D})
+            if (L->cs) PP_CUDA(cudaStreamSynchronize(L->cs));
+        PP_CUDA(cudaEventRecord(ev_c1, host_gather ? G.cs : D.cs));
+        PP_CUDA(cudaStreamSynchronize(host_gather ? G.cs : D.cs));
         PP_CUDA(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
         for (size_t j = 0; j + 1 < ev_s.size(); j += 2) {
@@ -759,10 +877,11 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             score_ms += ms;
         }
         for (cudaEvent_t e : ev_s) cudaEventDestroy(e);
-        for (int b = 0; b < 2; ++b) {
-            cudaEventDestroy(ev_copied[b]);
-            cudaEventDestroy(ev_free[b]);
-        }
+        for (Lane *L : {&G, &D})
+            for (int b = 0; b < 2; ++b) {
+                if (L->copied[b]) cudaEventDestroy(L->copied[b]);
+                if (L->freed[b]) cudaEventDestroy(L->freed[b]);
+            }
         cudaEventDestroy(ev_c0);
         cudaEventDestroy(ev_c1);
     }

@@ -499,6 +499,7 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     if (!x_is_device) {
         PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
         PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
+        ctx->tm.h2d_bytes = (int64_t)((size_t)n_rows * ld * esz);
         dx = d_x.p;
     }
     PP_CUDA(cudaEventRecord(ctx->ev[1], st));

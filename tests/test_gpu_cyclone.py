@@ -251,3 +251,29 @@ def test_sandbag_then_cyclone_flow():
     pr, us = orc.filter_marker_pairs(sub, gn)
     for k in sub:
         assert np.array_equal(df[k].values, orc.phase_scores(y, 100, 10, 5, pr[k], us[k]), equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_gather_path(dtype):
+    """Wide host matrices (marker genes <= 1/4 of the columns): marker columns are gathered on the host into
+    pinned staging buffers before the copy.  Same scores as the device-resident path and as the oracle."""
+    import torch
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(49)
+    markers, names, _ = default_setup(rng, 1, 8000)
+    n = 148 * 64 + 500  # two chunks
+    x = rng.poisson(2.0, (n, 8000)).astype(dtype)
+    x[5] = rng.normal(size=8000)  # one non-count row (sort path of the rank kernel)
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    s_host, tm_h = _ffi().cyclone(x, u, p, 30, 10, 5)
+    s_dev, tm_d = _ffi().cyclone(torch.from_numpy(x).cuda(), u, p, 30, 10, 5)
+    assert np.array_equal(s_host, s_dev, equal_nan=True)
+    s_part, _ = _ffi().cyclone(x, u, p, 30, 10, 5, row_begin=1000, n_cells=777)  # single short chunk
+    assert np.array_equal(s_part, s_dev[:, 1000:1777], equal_nan=True)
+    rows = np.sort(rng.choice(n, 24, replace=False))
+    rows[0] = 5
+    for i, k in enumerate(ks):
+        assert np.array_equal(s_host[i, rows], orc.phase_scores(x[rows], 30, 10, 5, pairs[k], used[k]))
