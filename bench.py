@@ -186,9 +186,9 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
         "e2e": {"value": total_cells / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(e2e_tm["h2d_bytes"]), "d2h_bytes_per_step": len(keys) * CYC_CELLS * 8,
                 "host_matrix_bytes": CYC_CELLS * CYC_GENES * 4,
-                "api": "pypairs_b200.pairs.cyclone(ndarray pinned) -> DataFrame; chunks alternate between a host-side "
-                       "gather of the {} marker-gene columns (all cores, pinned staging) and full-row copies, "
-                       "both overlapped with rank + score of earlier chunks".format(n_union)},
+                "api": "pypairs_b200.pairs.cyclone(ndarray pinned) -> DataFrame; per chunk of cells the library gathers "
+                       "the {} marker-gene columns on the host (threads, pinned staging), copies them and runs rank + "
+                       "score, all overlapped; bound by host DRAM bandwidth".format(n_union)},
         "roofline": {"bound": "int_alu", "kernel": "score_kernel",
                      "achieved": alg_ops / (main_step * 1e-3) / 1e9, "peak": peaks["lop3_lane_ops_per_s"] / 1e9,
                      "unit": "Gop/s", "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],

@@ -529,8 +529,11 @@ void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *
 
 int host_threads() {
     if (const char *e = getenv("PP_HOST_THREADS")) return std::max(1, atoi(e));
-    const unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(hc ? hc : 8u, 32u));
+    unsigned hc = std::thread::hardware_concurrency();
+    hc = std::min(hc ? hc : 8u, 32u);
+    if (const char *e = getenv("LOCAL_WORLD_SIZE"))  // one process per GPU: share the host cores
+        hc = std::max(1u, hc / (unsigned)std::max(1, atoi(e)));
+    return (int)std::max(1u, hc);
 }
 
 }  // namespace
