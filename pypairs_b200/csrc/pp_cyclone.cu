@@ -620,7 +620,10 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     // host, multi-threaded), so PCIe carries U instead of n_cols values per cell.  Device input is processed
     // in one launch.
     const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
-    const bool host_gather = !x_is_device && (int64_t)U * 4 <= n_cols;
+    // (measured: with 16 host threads the gather beats full-row copies 161 vs 195 ms on cfg2; with 8 threads per
+    // rank, 4 ranks sharing the host, it loses 402 vs 349 ms -- so it needs >= 12 threads for this process)
+    const bool host_gather = !x_is_device && (int64_t)U * 4 <= n_cols && host_threads() >= 12 &&
+                             !getenv("PP_NO_HOST_GATHER");
     const bool pipelined = !x_is_device && (n_cells > wave_cells || host_gather);
     const int64_t chunk_cells = pipelined ? wave_cells : n_cells;
     {
