@@ -72,6 +72,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if absent)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes"]
+    except Exception:
+        return None
+
+
 def env_world():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -194,7 +202,7 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
                      "unit": "Gop/s", "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],
                      "peak_source": "pp_alu_peak micro-benchmark (independent LOP3 stream), measured in this run",
                      "algorithmic_ops_per_unit": 2.0 * (CYC_ITERS + 1) * n_pairs, "units_per_launch": CYC_CELLS,
-                     "traffic": None},
+                     "traffic": ncu_traffic("score_kernel")},
         "roofline_prep": {"bound": "hbm", "kernel": "rank_kernel+tables",
                           "achieved": (CYC_CELLS * CYC_GENES * 4 + CYC_CELLS * n_union * 2) / (prep_step * 1e-3) / 1e9,
                           "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -286,7 +294,8 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
                      "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],
                      "peak_source": "pp_alu_peak micro-benchmark (independent LOP3 stream), measured in this run",
                      "algorithmic_ops_per_unit": 2, "units_per_launch": my_pairs * n,
-                     "machine_lop3_per_unit": 2.0 * tm["n_planes"] / 32.0, "traffic": None},
+                     "machine_lop3_per_unit": 2.0 * tm["n_planes"] / 32.0,
+                     "traffic": ncu_traffic("pair_kernel") if world == 1 else None},
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         gs = 600

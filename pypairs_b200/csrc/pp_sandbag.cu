@@ -607,14 +607,20 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB;
     std::vector<int2> tiles;
     int64_t t_index = 0, n_pairs_shard = 0;
-    for (int ta = 0; ta < TA; ++ta)
-        for (int tb = 2 * ta; tb < TB; ++tb, ++t_index) {
-            if (t_index % n_shards != shard) continue;
-            tiles.push_back(make_int2(ta, tb));
-            const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
-            const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
-            for (int64_t a = a0; a < a1; ++a) n_pairs_shard += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
-        }
+    // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
+    // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
+    // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
+    constexpr int SUP_A = 8, SUP_B = 18;
+    for (int sa = 0; sa < TA; sa += SUP_A)
+        for (int sb = 2 * sa; sb < TB; sb += SUP_B)
+            for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
+                for (int tb = std::max(sb, 2 * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
+                    if (t_index % n_shards != shard) continue;
+                    tiles.push_back(make_int2(ta, tb));
+                    const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
+                    const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
+                    for (int64_t a = a0; a < a1; ++a) n_pairs_shard += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                }
     ctx->tm.n_units = n_pairs_shard;
     std::vector<int32_t> thr32(n_classes);
     for (int k = 0; k < n_classes; ++k)
