@@ -107,13 +107,18 @@ struct PairParams {
 // WIDE = classes with more than 65 535 cells and / or more than 254 classes: the packed 16+16-bit counters
 // are folded into 32-bit counters kept in shared memory every <= 2047 cell words, and the per-pair decision
 // state uses 16-bit fields in two registers.
+// Warps 0 .. PAIR_THREADS/32-1 consume; one extra warp (the last) is the TMA producer.  full[s] (1 arrival +
+// transaction bytes) hands a stage to the consumers, empty[s] (one arrival per consumer warp) hands it back,
+// so the consumer warps never meet at a CTA-wide barrier and drift up to STAGES-1 chunks apart.
 template <int TI, int TJ, bool WIDE>
-__global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(const PairParams P) {
+__global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_kernel(const PairParams P) {
     constexpr int NTJ = TILE_B / TJ;
-    constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;
+    constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;  // consumer threads
+    constexpr int CONSUMER_WARPS = PAIR_THREADS / 32;
     static_assert(TJ == 4 && (TI == 4 || TI == 8), "shared loads below are written for these tiles");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
 
     const int tid = threadIdx.x;
     const int ti = tid / NTJ, tj = tid % NTJ;
@@ -125,10 +130,13 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
 
     // WIDE: [TI*TJ][2][threads] 32-bit counters behind the stage ring
     int32_t *wide = reinterpret_cast<int32_t *>(smem + (size_t)STAGES * stage_words) + tid;
-    if (WIDE)
+    if (WIDE && tid < PAIR_THREADS)
         for (int q = 0; q < TI * TJ * 2; ++q) wide[q * PAIR_THREADS] = 0;
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CONSUMER_WARPS);
+        }
         fence_mbar_init();
     }
     __syncthreads();
@@ -138,19 +146,23 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
     const uint32_t *gA1 = gA0 + blk_stride;
     const uint32_t *gB = P.planes + (int64_t)tile.y * blk_stride;
 
-    auto issue = [&](int c) {  // thread 0 only
-        const Chunk ch = P.chunks[c];
-        const int s = c % STAGES;
-        uint32_t *dst = smem + (size_t)s * stage_words;
-        const uint32_t bytes = (uint32_t)ch.n_words * B * 64 * 4;
-        const int64_t off = (int64_t)ch.w_begin * B * 64;
-        mbar_arrive_expect_tx(&full_bar[s], 3 * bytes);
-        bulk_g2s(dst, gA0 + off, bytes, &full_bar[s]);
-        bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
-        bulk_g2s(dst + 2 * blk_words, gB + off, bytes, &full_bar[s]);
-    };
-    if (tid == 0)
-        for (int c = 0; c < STAGES - 1 && c < P.n_chunks; ++c) issue(c);
+    if (tid >= PAIR_THREADS) {  // ---- producer warp: one elected lane streams every chunk of this tile
+        if (tid == PAIR_THREADS) {
+            for (int c = 0; c < P.n_chunks; ++c) {
+                const int s = c % STAGES;
+                if (c >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(c / STAGES - 1) & 1u);  // consumers released it
+                const Chunk ch = P.chunks[c];
+                uint32_t *dst = smem + (size_t)s * stage_words;
+                const uint32_t bytes = (uint32_t)ch.n_words * B * 64 * 4;
+                const int64_t off = (int64_t)ch.w_begin * B * 64;
+                mbar_arrive_expect_tx(&full_bar[s], 3 * bytes);
+                bulk_g2s(dst, gA0 + off, bytes, &full_bar[s]);
+                bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
+                bulk_g2s(dst + 2 * blk_words, gB + off, bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
 
     uint32_t acc[TI][TJ], st[TI][TJ], st2[WIDE ? TI : 1][WIDE ? TJ : 1];
 #pragma unroll
@@ -166,8 +178,6 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
     const uint32_t b_off = 2u * blk_words + tj * TJ;
 
     for (int c = 0; c < P.n_chunks; ++c) {
-        __syncthreads();  // every thread is done with chunk c-1 -> its stage may be refilled
-        if (tid == 0 && c + STAGES - 1 < P.n_chunks) issue(c + STAGES - 1);
         const int s = c % STAGES;
         mbar_wait(&full_bar[s], (uint32_t)(c / STAGES) & 1u);
         const Chunk ch = P.chunks[c];
@@ -209,6 +219,8 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ), 1) pair_kernel(
             sa += B * 64;
             sb += B * 64;
         }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
         if (WIDE && (ch.flush || ch.class_end >= 0)) {
 #pragma unroll
             for (int i = 0; i < TI; ++i)
@@ -659,9 +671,9 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             P.n_classes = n_classes;
             P.wc_max = wc_max;
             if (wide)
-                pair_kernel<4, 4, true><<<(unsigned)tiles.size(), 512, dyn_smem, st>>>(P);
+                pair_kernel<4, 4, true><<<(unsigned)tiles.size(), 512 + 32, dyn_smem, st>>>(P);
             else
-                pair_kernel<4, 4, false><<<(unsigned)tiles.size(), 512, dyn_smem, st>>>(P);
+                pair_kernel<4, 4, false><<<(unsigned)tiles.size(), 512 + 32, dyn_smem, st>>>(P);
             PP_CHECK_LAUNCH();
         }
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
