@@ -55,6 +55,23 @@ extern "C" {
 
 typedef struct pp_ctx pp_ctx;
 
+/*
+ * CSR form of the expression matrix (rows = samples / cells, columns = genes), e.g. the arrays of a
+ * scipy.sparse.csr_matrix / AnnData.X.  The reference densifies such input on the host
+ * (pypairs/utils.py:278-281, 290-292, 299-301); here it is densified chunk by chunk on the device, so
+ * only the non-zeros cross PCIe.  Duplicate (row, column) entries are not allowed (scipy: sum_duplicates()),
+ * explicit zeros are; column indices need not be sorted.  All three arrays live on the host, or all three on
+ * the ctx's device (is_device != 0).
+ */
+typedef struct pp_csr {
+    const void *indptr;     /* [n_rows + 1] int32 or int64 */
+    int32_t indptr_is_64;
+    const int32_t *indices; /* [nnz] column indices */
+    const void *data;       /* [nnz] PP_F32 or PP_F64 */
+    int32_t data_dtype;
+    int32_t is_device;
+} pp_csr;
+
 /* Device-side timing of the last call, milliseconds (CUDA events on the ctx stream). */
 typedef struct pp_timings {
     float h2d_ms;     /* host -> device copy of the expression matrix (0 if x_is_device) */
@@ -115,6 +132,14 @@ int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t
                const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
                int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept);
 
+/* pp_sandbag with the matrix given in CSR form; every other argument as in pp_sandbag. */
+int pp_sandbag_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const int32_t *cell_rows,
+                   int64_t n_cells, const int64_t *class_sizes, int32_t n_classes, const int32_t *gene_cols,
+                   int64_t n_genes, const int64_t *thresholds, int32_t shard, int32_t n_shards,
+                   uint64_t **out_keys, int32_t **out_class, int64_t *out_n, const int64_t *probe_pairs,
+                   int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed,
+                   int32_t **out_kept_genes, int64_t *out_n_kept);
+
 /*
  * pp_cyclone -- replaces the per-class loop over get_phase_scores
  * (pypairs/tools/cyclone.py:151-158, 223-257) for all classes in one call.
@@ -142,6 +167,13 @@ int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t
                int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
                const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits,
                int32_t *out_obs_total);
+
+/* pp_cyclone with the matrix given in CSR form; every other argument as in pp_cyclone. */
+int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, int64_t row_begin, int64_t n_cells,
+                   int32_t n_classes, const int32_t *used_idx, const int64_t *used_off, const int32_t *pairs,
+                   const int64_t *pair_off, int32_t iterations, int32_t min_iter, int32_t min_pairs,
+                   int32_t rng_mode, uint64_t seed, const int32_t *perm_tables, double *out_scores,
+                   int32_t *out_obs_hits, int32_t *out_obs_total);
 
 /*
  * pp_phase_scores -- single-class form with the reference kernel's exact

@@ -16,7 +16,14 @@ PP_RNG_MT19937, PP_RNG_PHILOX, PP_RNG_TABLE = 0, 1, 2
 PP_ENAN = 4
 
 SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "pp_last_error", "pp_free",
-           "pp_get_timings", "pp_sandbag", "pp_cyclone", "pp_phase_scores", "pp_perm_table", "pp_dense_rank", "pp_alu_peak"]
+           "pp_get_timings", "pp_sandbag", "pp_sandbag_csr", "pp_cyclone", "pp_cyclone_csr", "pp_phase_scores",
+           "pp_perm_table", "pp_dense_rank", "pp_alu_peak"]
+
+
+class Csr(ctypes.Structure):
+    """struct pp_csr of include/pypairs_b200.h"""
+    _fields_ = [("indptr", ctypes.c_void_p), ("indptr_is_64", ctypes.c_int32), ("indices", ctypes.c_void_p),
+                ("data", ctypes.c_void_p), ("data_dtype", ctypes.c_int32), ("is_device", ctypes.c_int32)]
 
 
 class Timings(ctypes.Structure):
@@ -65,6 +72,11 @@ def load():
                                c.POINTER(i64)]
     lib.pp_cyclone.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32,
                                i32, u64, vp, vp, vp, vp]
+    lib.pp_sandbag_csr.argtypes = [vp, c.POINTER(Csr), i64, i64, vp, i64, vp, i32, vp, i64, vp, i32, i32,
+                                   c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp, i32, c.POINTER(vp),
+                                   c.POINTER(i64)]
+    lib.pp_cyclone_csr.argtypes = [vp, c.POINTER(Csr), i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32, u64,
+                                   vp, vp, vp, vp]
     lib.pp_phase_scores.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp]
     lib.pp_perm_table.argtypes = [vp, i32, u64, i32, i32, i32, vp]
     lib.pp_dense_rank.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i64, vp, c.POINTER(i32)]
@@ -145,6 +157,55 @@ def matrix_arg(x):
     return x, ctypes.c_void_p(x.ctypes.data), code, 0, x.shape[0], x.shape[1], max(ld, x.shape[1])
 
 
+def is_sparse(x):
+    """scipy.sparse matrix / array, or a torch sparse-CSR tensor."""
+    if type(x).__module__.startswith("torch"):
+        import torch
+        return x.layout == torch.sparse_csr
+    try:
+        from scipy.sparse import issparse
+    except ImportError:  # pragma: no cover
+        return False
+    return issparse(x)
+
+
+def csr_arg(x):
+    """(keepalive, Csr struct, n_rows, n_cols) for a scipy sparse matrix or a torch sparse-CSR tensor.
+
+    float32 values stay float32, anything else becomes float64 (as `data.astype(float)` in the reference);
+    duplicate entries are summed first (what `.toarray()` would do), explicit zeros are kept.
+    """
+    if type(x).__module__.startswith("torch"):
+        import torch
+        vals, crow, col = x.values(), x.crow_indices(), x.col_indices().to(torch.int32)
+        if vals.dtype not in (torch.float32, torch.float64):
+            vals = vals.to(torch.float64)
+        vals, crow, col = vals.contiguous(), crow.contiguous(), col.contiguous()
+        on_dev = vals.is_cuda
+        if not on_dev:
+            vals, crow, col = vals.numpy(), crow.numpy(), col.numpy()
+            ptr = lambda a: a.ctypes.data  # noqa: E731
+            is64, f32 = crow.dtype == np.int64, vals.dtype == np.float32
+        else:
+            ptr = lambda a: a.data_ptr()  # noqa: E731
+            is64, f32 = crow.dtype == torch.int64, vals.dtype == torch.float32
+        st = Csr(ptr(crow), 1 if is64 else 0, ptr(col), ptr(vals), PP_F32 if f32 else PP_F64, 1 if on_dev else 0)
+        return (vals, crow, col), st, x.shape[0], x.shape[1]
+    m = x.tocsr()
+    if not m.has_canonical_format:
+        m = m.copy()
+        m.sum_duplicates()
+    data = m.data if m.data.dtype in (np.float32, np.float64) else m.data.astype(np.float64)
+    data = np.ascontiguousarray(data)
+    indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+    indptr = np.ascontiguousarray(m.indptr)
+    if indptr.dtype not in (np.int32, np.int64):
+        indptr = indptr.astype(np.int64)
+    st = Csr(indptr.ctypes.data, 1 if indptr.dtype == np.int64 else 0, indices.ctypes.data, data.ctypes.data,
+             PP_F32 if data.dtype == np.float32 else PP_F64, 0)
+    return (data, indices, indptr), st, m.shape[0], m.shape[1]
+
+
 def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, device=None,
             drop_unexpressed=False):
     """-> (keys uint64[n], cls int32[n], timings dict[, probe_pos, probe_neg][, kept_gene_cols])
@@ -152,7 +213,11 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
     drop_unexpressed=True: `gene_cols` are candidates, genes that are zero in every row of x are dropped on
     the device and the kept columns are returned as the last element (keys index the kept list)."""
     lib, h = load(), ctx(device)
-    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+    sparse = is_sparse(x)
+    if sparse:
+        keep, csr, n_rows, n_cols = csr_arg(x)
+    else:
+        keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
     cell_rows = np.ascontiguousarray(cell_rows, dtype=np.int32)
     class_sizes = np.ascontiguousarray(class_sizes, dtype=np.int64)
     gene_cols = np.ascontiguousarray(gene_cols, dtype=np.int32)
@@ -168,10 +233,13 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
         ppos = np.zeros((n_probe, len(class_sizes)), dtype=np.int32)
         pneg = np.zeros_like(ppos)
     kg, kn = ctypes.c_void_p(), ctypes.c_int64()
-    rc = lib.pp_sandbag(h, px, code, is_dev, n_rows, n_cols, ld, _ptr(cell_rows), len(cell_rows), _ptr(class_sizes),
-                        len(class_sizes), _ptr(gene_cols), len(gene_cols), _ptr(thresholds), shard, n_shards,
-                        ctypes.byref(ok), ctypes.byref(oc), ctypes.byref(on), _ptr(pp), n_probe, _ptr(ppos),
-                        _ptr(pneg), 1 if drop_unexpressed else 0, ctypes.byref(kg), ctypes.byref(kn))
+    tail = (_ptr(cell_rows), len(cell_rows), _ptr(class_sizes), len(class_sizes), _ptr(gene_cols), len(gene_cols),
+            _ptr(thresholds), shard, n_shards, ctypes.byref(ok), ctypes.byref(oc), ctypes.byref(on), _ptr(pp), n_probe,
+            _ptr(ppos), _ptr(pneg), 1 if drop_unexpressed else 0, ctypes.byref(kg), ctypes.byref(kn))
+    if sparse:
+        rc = lib.pp_sandbag_csr(h, ctypes.byref(csr), n_rows, n_cols, *tail)
+    else:
+        rc = lib.pp_sandbag(h, px, code, is_dev, n_rows, n_cols, ld, *tail)
     kept = None
     if kg.value:
         kept = np.ctypeslib.as_array(ctypes.cast(kg, ctypes.POINTER(ctypes.c_int32)), shape=(max(kn.value, 1),))[
@@ -202,7 +270,11 @@ def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="
             perm_tables=None, row_begin=0, n_cells=None, want_observed=False, device=None):
     """-> (scores float64[C, n_cells], timings[, obs_hits, obs_total])"""
     lib, h = load(), ctx(device)
-    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+    sparse = is_sparse(x)
+    if sparse:
+        keep, csr, n_rows, n_cols = csr_arg(x)
+    else:
+        keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
     if n_cells is None:
         n_cells = n_rows - row_begin
     nc = len(used_idx_list)
@@ -224,9 +296,12 @@ def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="
     scores = np.empty((nc, n_cells), dtype=np.float64)
     oh = np.empty((nc, n_cells), dtype=np.int32) if want_observed else None
     ot = np.empty((nc, n_cells), dtype=np.int32) if want_observed else None
-    rc = lib.pp_cyclone(h, px, code, is_dev, n_rows, n_cols, ld, row_begin, n_cells, nc, _ptr(used), _ptr(used_off),
-                        _ptr(pairs), _ptr(pair_off), iterations, min_iter, min_pairs, _RNG[rng], seed, _ptr(tabs),
-                        _ptr(scores), _ptr(oh), _ptr(ot))
+    tail = (row_begin, n_cells, nc, _ptr(used), _ptr(used_off), _ptr(pairs), _ptr(pair_off), iterations, min_iter,
+            min_pairs, _RNG[rng], seed, _ptr(tabs), _ptr(scores), _ptr(oh), _ptr(ot))
+    if sparse:
+        rc = lib.pp_cyclone_csr(h, ctypes.byref(csr), n_rows, n_cols, *tail)
+    else:
+        rc = lib.pp_cyclone(h, px, code, is_dev, n_rows, n_cols, ld, *tail)
     check(rc, h)
     del keep
     if want_observed:

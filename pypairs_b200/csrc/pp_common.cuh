@@ -130,6 +130,23 @@ __device__ __forceinline__ uint32_t lop3_lt(uint32_t a, uint32_t b, uint32_t l) 
 }
 #endif
 
+// Device-resident CSR rows [r0, r0 + nr) of a pp_csr: indptr rebased to 0 as int64, indices / data of the slice.
+struct DevCsr {
+    DevBuf b_indptr, b_indices, b_data;
+    const int64_t *indptr = nullptr;
+    const int32_t *indices = nullptr;
+    const void *data = nullptr;
+    int64_t n_rows = 0, nnz = 0;
+    int dtype = PP_F32;
+};
+int pp_csr_validate(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const char *who);
+int pp_csr_to_device(pp_ctx *ctx, const pp_csr *x, int64_t r0, int64_t nr, DevCsr *out);
+int pp_csr_col_nonzero(pp_ctx *ctx, const DevCsr &m, uint8_t *d_nz);
+// out[i, colmap[c]] = value for every stored entry (rows[i], c) with colmap[c] >= 0; out must be zero-filled;
+// rows[i] < 0 leaves row i zero.
+int pp_csr_densify(pp_ctx *ctx, const DevCsr &m, const int32_t *d_rows, int64_t n_out, const int32_t *d_colmap,
+                   void *d_out, int64_t out_ld);
+
 // ---- internal entry points (one per .cu) --------------------------------------------------------
 // Rank transform: for each slot s < n_slots (cell_rows[s] < 0 marks a padding slot: all ranks 0),
 // rank[s * rank_ld + g] = dense rank of x[cell_rows[s], gene_cols[g]] among that cell's kept genes.

@@ -563,17 +563,21 @@ PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t c
     return PP_OK;
 }
 
-PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
-                      int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes, const int32_t *used_idx,
-                      const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off, int32_t iterations,
-                      int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
-                      const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits,
-                      int32_t *out_obs_total) {
+// Shared body of pp_cyclone (dense x, csr == NULL) and pp_cyclone_csr (csr != NULL, x / ld unused).
+static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, const pp_csr *csr, int64_t n_rows,
+                        int64_t n_cols, int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes,
+                        const int32_t *used_idx, const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off,
+                        int32_t iterations, int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
+                        const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
-    if (!x || !used_idx || !used_off || !pairs || !pair_off || !out_scores)
+    if ((!x && !csr) || !used_idx || !used_off || !pairs || !pair_off || !out_scores)
         return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: x_dtype must be PP_F32/PP_F64");
-    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad matrix shape");
+    if (n_rows <= 0 || n_cols <= 0 || (!csr && ld < n_cols)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad matrix shape");
+    if (csr) {
+        const int vrc = pp_csr_validate(ctx, csr, n_rows, n_cols, "pp_cyclone_csr");
+        if (vrc) return vrc;
+    }
     if (row_begin < 0 || n_cells < 0 || row_begin + n_cells > n_rows) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad row range");
     if (n_classes < 1) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: n_classes < 1");
     if (iterations < 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: iterations < 0");
@@ -613,7 +617,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
     const size_t esz = x_dtype == PP_F64 ? 8 : 4;
     DevBuf d_x, d_rows, d_uni, d_rank, d_flags, d_scores, d_oh, d_ot, d_cd;
-    const uint8_t *x0 = (const uint8_t *)x + (size_t)row_begin * ld * esz;
+    const uint8_t *x0 = csr ? nullptr : (const uint8_t *)x + (size_t)row_begin * ld * esz;
     // Host input is streamed in chunks of one full wave of 64-cell tiles: H2D of chunk i+1 (copy stream)
     // overlaps rank + score of chunk i (compute stream).  When the marker genes are at most a quarter of the
     // columns the host first gathers just those columns into a pinned staging buffer (gene filtering on the
@@ -622,10 +626,10 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
     // (measured: with 16 host threads the gather beats full-row copies 161 vs 195 ms on cfg2; with 8 threads per
     // rank, 4 ranks sharing the host, it loses 402 vs 349 ms -- so it needs >= 12 threads for this process)
-    const bool host_gather = !x_is_device && (int64_t)U * 4 <= n_cols && host_threads() >= 12 &&
+    const bool host_gather = !csr && !x_is_device && (int64_t)U * 4 <= n_cols && host_threads() >= 12 &&
                              !getenv("PP_NO_HOST_GATHER");
-    const bool pipelined = !x_is_device && (n_cells > wave_cells || host_gather);
-    const int64_t chunk_cells = pipelined ? wave_cells : n_cells;
+    const bool pipelined = !csr && !x_is_device && (n_cells > wave_cells || host_gather);
+    const int64_t chunk_cells = (pipelined || csr) ? std::min(wave_cells, n_cells) : n_cells;
     {
         std::vector<int32_t> rows(chunk_cells);
         for (int64_t i = 0; i < chunk_cells; ++i) rows[i] = (int32_t)i;
@@ -727,7 +731,47 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
             score_kernel<false><<<(unsigned)std::min<int64_t>(n_tiles, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
     };
     float score_ms = 0.f, copy_ms = 0.f;
-    if (!pipelined) {
+    if (csr) {
+        // CSR input: only the non-zeros of the cell shard are uploaded; every chunk of cells is densified on the
+        // device straight into the compact [cells, U] marker-gene layout, then ranked and scored.
+        DevCsr dcsr;
+        PP_CUDA(cudaEventRecord(ctx->ev[6], st));
+        rc = pp_csr_to_device(ctx, csr, row_begin, n_cells, &dcsr);
+        if (rc) return rc;
+        PP_CUDA(cudaEventRecord(ctx->ev[7], st));
+        std::vector<int32_t> colmap((size_t)n_cols, -1), ident((size_t)U), allrows((size_t)n_cells);
+        for (int j = 0; j < U; ++j) {
+            colmap[uni[j]] = j;
+            ident[j] = j;
+        }
+        for (int64_t i = 0; i < n_cells; ++i) allrows[i] = (int32_t)i;
+        DevBuf d_colmap, d_ident, d_allrows, d_dense;
+        PP_CUDA(d_colmap.alloc(sizeof(int32_t) * n_cols, st));
+        PP_CUDA(cudaMemcpyAsync(d_colmap.p, colmap.data(), sizeof(int32_t) * n_cols, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_ident.alloc(sizeof(int32_t) * U, st));
+        PP_CUDA(cudaMemcpyAsync(d_ident.p, ident.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_allrows.alloc(sizeof(int32_t) * n_cells, st));
+        PP_CUDA(cudaMemcpyAsync(d_allrows.p, allrows.data(), sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_dense.alloc((size_t)chunk_cells * U * esz, st));
+        PP_CUDA(cudaStreamSynchronize(st));  // colmap / ident / allrows are locals
+        PP_CUDA(cudaEventRecord(ctx->ev[3], st));
+        for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells) {
+            const int64_t nc = std::min(chunk_cells, n_cells - c0);
+            PP_CUDA(cudaMemsetAsync(d_dense.p, 0, (size_t)nc * U * esz, st));
+            rc = pp_csr_densify(ctx, dcsr, d_allrows.as<int32_t>() + c0, nc, d_colmap.as<int32_t>(), d_dense.p, U);
+            if (rc) return rc;
+            rc = pp_rank_launch(ctx, d_dense.p, x_dtype, U, d_rows.as<int32_t>(), nc, d_ident.as<int32_t>(), U,
+                                d_rank.as<uint16_t>() + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            if (rc) return rc;
+            P.rank = d_rank.as<uint16_t>() + c0 * rank_ld;
+            P.n_cells = nc;
+            P.out_off = c0;
+            launch_score(nc);
+            PP_CHECK_LAUNCH();
+        }
+        PP_CUDA(cudaEventRecord(ctx->ev[4], st));
+        PP_CUDA(cudaStreamSynchronize(st));  // d_dense and dcsr go out of scope
+    } else if (!pipelined) {
         const void *dx = x0;
         if (!x_is_device) {
             PP_CUDA(d_x.alloc((size_t)n_cells * ld * esz, st));
@@ -905,7 +949,7 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         cudaEventElapsedTime(&ctx->tm.prep_ms, ctx->ev[0], ctx->ev[1]);
     } else {
         float t_tab = 0.f, t_rank = 0.f;
-        if (!x_is_device) cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[6], ctx->ev[7]);
+        if (!x_is_device || csr) cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[6], ctx->ev[7]);
         cudaEventElapsedTime(&t_tab, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&t_rank, ctx->ev[1], ctx->ev[3]);
         ctx->tm.prep_ms = t_tab + t_rank - ctx->tm.h2d_ms;
@@ -915,6 +959,29 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[5]);
     ctx->tm.n_launches = ctx->launches;
     return PP_OK;
+}
+
+PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                      int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes, const int32_t *used_idx,
+                      const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off, int32_t iterations,
+                      int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
+                      const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits,
+                      int32_t *out_obs_total) {
+    if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
+    return cyclone_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, row_begin, n_cells, n_classes, used_idx,
+                        used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode, seed, perm_tables, out_scores,
+                        out_obs_hits, out_obs_total);
+}
+
+PP_API int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, int64_t row_begin,
+                          int64_t n_cells, int32_t n_classes, const int32_t *used_idx, const int64_t *used_off,
+                          const int32_t *pairs, const int64_t *pair_off, int32_t iterations, int32_t min_iter,
+                          int32_t min_pairs, int32_t rng_mode, uint64_t seed, const int32_t *perm_tables,
+                          double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
+    if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_csr: NULL argument");
+    return cyclone_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols, row_begin,
+                        n_cells, n_classes, used_idx, used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode,
+                        seed, perm_tables, out_scores, out_obs_hits, out_obs_total);
 }
 
 PP_API int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows,

@@ -19,6 +19,8 @@
 // popcount over its 2048 words, and rank(v) = #present values below v.  Three coalesced passes over the row.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "pp_common.cuh"
 
 namespace {
@@ -266,6 +268,141 @@ int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const 
         rank_kernel<float><<<grid, RANK_THREADS, 0, ctx->stream>>>(
             (const float *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
             scratch.as<uint8_t>(), per_cta, d_flags);
+    PP_CHECK_LAUNCH();
+    return PP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CSR input (scipy.sparse.csr_matrix / AnnData.X): the reference calls .toarray() on the host
+// (pypairs/utils.py:278-281); here the rows a chunk needs are densified on the device.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+__global__ void csr_col_nonzero_kernel(const int32_t *__restrict__ indices, const T *__restrict__ data, int64_t nnz,
+                                       uint8_t *__restrict__ nz) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+        if (data[k] != (T)0) nz[indices[k]] = 1;
+}
+
+// one warp per output row
+template <typename T>
+__global__ void csr_densify_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                                   const T *__restrict__ data, const int32_t *__restrict__ rows, int64_t n_out,
+                                   const int32_t *__restrict__ colmap, T *__restrict__ out, int64_t out_ld) {
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_out) return;
+    const int r = rows[i];
+    if (r < 0) return;
+    T *o = out + i * out_ld;
+    for (int64_t k = indptr[r] + (threadIdx.x & 31); k < indptr[r + 1]; k += 32) {
+        const int c = colmap[indices[k]];
+        if (c >= 0) o[c] = data[k];
+    }
+}
+
+__global__ void rebase_indptr_kernel(const void *__restrict__ src, int is64, int64_t r0, int64_t n, int64_t base,
+                                     int64_t *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t v = is64 ? ((const int64_t *)src)[r0 + i] : (int64_t)((const int32_t *)src)[r0 + i];
+    dst[i] = v - base;
+}
+
+}  // namespace
+
+int pp_csr_validate(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const char *who) {
+    if (!x || !x->indptr) return pp_fail(ctx, PP_EINVAL, "%s: NULL CSR argument", who);
+    if (x->data_dtype != PP_F32 && x->data_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "%s: CSR data_dtype must be PP_F32/PP_F64", who);
+    if (n_rows <= 0 || n_cols <= 0) return pp_fail(ctx, PP_EINVAL, "%s: bad matrix shape", who);
+    if (!x->is_device) {
+        auto ip = [&](int64_t i) { return x->indptr_is_64 ? ((const int64_t *)x->indptr)[i] : (int64_t)((const int32_t *)x->indptr)[i]; };
+        for (int64_t r = 0; r < n_rows; ++r)
+            if (ip(r + 1) < ip(r)) return pp_fail(ctx, PP_EINVAL, "%s: CSR indptr decreases at row %lld", who, (long long)r);
+        const int64_t nnz = ip(n_rows) - ip(0);
+        if (nnz > 0 && (!x->indices || !x->data)) return pp_fail(ctx, PP_EINVAL, "%s: NULL CSR indices / data", who);
+        const int32_t *idx = x->indices + ip(0);
+        for (int64_t k = 0; k < nnz; ++k)
+            if (idx[k] < 0 || idx[k] >= n_cols) return pp_fail(ctx, PP_EINVAL, "%s: CSR column index out of range", who);
+    }
+    return PP_OK;
+}
+
+int pp_csr_to_device(pp_ctx *ctx, const pp_csr *x, int64_t r0, int64_t nr, DevCsr *out) {
+    cudaStream_t st = ctx->stream;
+    const size_t esz = x->data_dtype == PP_F64 ? 8 : 4;
+    out->dtype = x->data_dtype;
+    out->n_rows = nr;
+    PP_CUDA(out->b_indptr.alloc(sizeof(int64_t) * (nr + 1), st));
+    int64_t p0 = 0, p1 = 0;
+    if (!x->is_device) {
+        std::vector<int64_t> ip(nr + 1);
+        for (int64_t i = 0; i <= nr; ++i)
+            ip[i] = x->indptr_is_64 ? ((const int64_t *)x->indptr)[r0 + i] : (int64_t)((const int32_t *)x->indptr)[r0 + i];
+        p0 = ip[0];
+        p1 = ip[nr];
+        for (int64_t i = 0; i <= nr; ++i) ip[i] -= p0;
+        PP_CUDA(cudaMemcpyAsync(out->b_indptr.p, ip.data(), sizeof(int64_t) * (nr + 1), cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaStreamSynchronize(st));  // ip is a local
+        out->nnz = p1 - p0;
+        PP_CUDA(out->b_indices.alloc(sizeof(int32_t) * out->nnz, st));
+        PP_CUDA(out->b_data.alloc(esz * out->nnz, st));
+        if (out->nnz) {
+            PP_CUDA(cudaMemcpyAsync(out->b_indices.p, x->indices + p0, sizeof(int32_t) * out->nnz, cudaMemcpyHostToDevice, st));
+            PP_CUDA(cudaMemcpyAsync(out->b_data.p, (const uint8_t *)x->data + esz * p0, esz * out->nnz, cudaMemcpyHostToDevice, st));
+        }
+        ctx->tm.h2d_bytes += (int64_t)((sizeof(int32_t) + esz) * out->nnz + sizeof(int64_t) * (nr + 1));
+        out->indices = out->b_indices.as<int32_t>();
+        out->data = out->b_data.p;
+    } else {
+        const size_t isz = x->indptr_is_64 ? 8 : 4;
+        int64_t ends[2] = {0, 0};
+        int32_t e32[2] = {0, 0};
+        for (int j = 0; j < 2; ++j) {
+            const int64_t row = j == 0 ? r0 : r0 + nr;
+            if (x->indptr_is_64) {
+                PP_CUDA(cudaMemcpyAsync(&ends[j], (const uint8_t *)x->indptr + isz * row, isz, cudaMemcpyDeviceToHost, st));
+            } else {
+                PP_CUDA(cudaMemcpyAsync(&e32[j], (const uint8_t *)x->indptr + isz * row, isz, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        PP_CUDA(cudaStreamSynchronize(st));
+        if (!x->indptr_is_64) { ends[0] = e32[0]; ends[1] = e32[1]; }
+        p0 = ends[0];
+        p1 = ends[1];
+        if (p1 < p0) return pp_fail(ctx, PP_EINVAL, "CSR indptr decreases");
+        out->nnz = p1 - p0;
+        rebase_indptr_kernel<<<(unsigned)((nr + 1 + 255) / 256), 256, 0, st>>>(x->indptr, x->indptr_is_64, r0, nr + 1, p0,
+                                                                          out->b_indptr.as<int64_t>());
+        PP_CHECK_LAUNCH();
+        out->indices = x->indices + p0;
+        out->data = (const uint8_t *)x->data + esz * p0;
+    }
+    out->indptr = out->b_indptr.as<int64_t>();
+    return PP_OK;
+}
+
+int pp_csr_col_nonzero(pp_ctx *ctx, const DevCsr &m, uint8_t *d_nz) {
+    if (m.nnz == 0) return PP_OK;
+    const unsigned grid = (unsigned)std::min<int64_t>((m.nnz + 255) / 256, (int64_t)ctx->n_sm * 16);
+    if (m.dtype == PP_F64)
+        csr_col_nonzero_kernel<double><<<grid, 256, 0, ctx->stream>>>(m.indices, (const double *)m.data, m.nnz, d_nz);
+    else
+        csr_col_nonzero_kernel<float><<<grid, 256, 0, ctx->stream>>>(m.indices, (const float *)m.data, m.nnz, d_nz);
+    PP_CHECK_LAUNCH();
+    return PP_OK;
+}
+
+int pp_csr_densify(pp_ctx *ctx, const DevCsr &m, const int32_t *d_rows, int64_t n_out, const int32_t *d_colmap,
+                   void *d_out, int64_t out_ld) {
+    if (n_out == 0) return PP_OK;
+    const unsigned grid = (unsigned)((n_out + 7) / 8);
+    if (m.dtype == PP_F64)
+        csr_densify_kernel<double><<<grid, 256, 0, ctx->stream>>>(m.indptr, m.indices, (const double *)m.data, d_rows,
+                                                                   n_out, d_colmap, (double *)d_out, out_ld);
+    else
+        csr_densify_kernel<float><<<grid, 256, 0, ctx->stream>>>(m.indptr, m.indices, (const float *)m.data, d_rows, n_out,
+                                                                  d_colmap, (float *)d_out, out_ld);
     PP_CHECK_LAUNCH();
     return PP_OK;
 }

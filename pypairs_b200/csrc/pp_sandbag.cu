@@ -465,17 +465,22 @@ int bit_length64(uint64_t v) {
 
 }  // namespace
 
-PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
-                      int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
-                      int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
-                      int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
-                      const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
-                      int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
+// Shared body of pp_sandbag (dense x, csr == NULL) and pp_sandbag_csr (csr != NULL, x / ld unused).
+static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, const pp_csr *csr, int64_t n_rows,
+                        int64_t n_cols, int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
+                        int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
+                        int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
+                        const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
+                        int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
-    if (!x || !cell_rows || !class_sizes || !gene_cols || !thresholds || !out_keys || !out_class || !out_n)
+    if ((!x && !csr) || !cell_rows || !class_sizes || !gene_cols || !thresholds || !out_keys || !out_class || !out_n)
         return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: x_dtype must be PP_F32/PP_F64");
-    if (n_rows <= 0 || n_cols <= 0 || ld < n_cols) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad matrix shape");
+    if (n_rows <= 0 || n_cols <= 0 || (!csr && ld < n_cols)) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad matrix shape");
+    if (csr) {
+        const int vrc = pp_csr_validate(ctx, csr, n_rows, n_cols, "pp_sandbag_csr");
+        if (vrc) return vrc;
+    }
     if (n_classes < 1) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: n_classes < 1");
     if (n_classes > 65534) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65534 classes (%d)", n_classes);
     if (n_shards < 1 || shard < 0 || shard >= n_shards) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad shard %d/%d", shard, n_shards);
@@ -508,7 +513,12 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     DevBuf d_x, d_slots, d_gene, d_rank, d_flags, d_planes, d_chunks, d_tiles, d_thr, d_out, d_out2, d_cnt;
     const size_t esz = x_dtype == PP_F64 ? 8 : 4;
     const void *dx = x;
-    if (!x_is_device) {
+    DevCsr dcsr;
+    int rc = PP_OK;
+    if (csr) {
+        rc = pp_csr_to_device(ctx, csr, 0, n_rows, &dcsr);
+        if (rc) return rc;
+    } else if (!x_is_device) {
         PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
         PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
         ctx->tm.h2d_bytes = (int64_t)((size_t)n_rows * ld * esz);
@@ -523,11 +533,16 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
         PP_CUDA(d_nz.alloc((size_t)n_cols, st));
         PP_CUDA(cudaMemsetAsync(d_nz.p, 0, (size_t)n_cols, st));
         dim3 grid((unsigned)((n_cols + 255) / 256), (unsigned)std::min<int64_t>((n_rows + 63) / 64, 65535));
-        if (x_dtype == PP_F64)
+        if (csr) {
+            rc = pp_csr_col_nonzero(ctx, dcsr, d_nz.as<uint8_t>());
+            if (rc) return rc;
+        } else if (x_dtype == PP_F64) {
             col_nonzero_kernel<double><<<grid, 256, 0, st>>>((const double *)dx, ld, n_rows, n_cols, d_nz.as<uint8_t>());
-        else
+            PP_CHECK_LAUNCH();
+        } else {
             col_nonzero_kernel<float><<<grid, 256, 0, st>>>((const float *)dx, ld, n_rows, n_cols, d_nz.as<uint8_t>());
-        PP_CHECK_LAUNCH();
+            PP_CHECK_LAUNCH();
+        }
         std::vector<uint8_t> nz((size_t)n_cols);
         PP_CUDA(cudaMemcpyAsync(nz.data(), d_nz.p, (size_t)n_cols, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
@@ -569,9 +584,40 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
     PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
 
-    int rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
+    if (csr) {
+        // densify the kept genes of a run of slots, rank them, next run (<= 256 MB of dense values at a time)
+        std::vector<int32_t> colmap((size_t)n_cols, -1), ident((size_t)n_genes);
+        for (int64_t g = 0; g < n_genes; ++g) {
+            colmap[gene_cols[g]] = (int32_t)g;
+            ident[g] = (int32_t)g;
+        }
+        int64_t chunk = std::max<int64_t>(32, (((int64_t)256 << 20) / (n_genes * (int64_t)esz)) / 32 * 32);
+        chunk = std::min(chunk, n_slots);
+        std::vector<int32_t> loc((size_t)n_slots);
+        for (int64_t sl = 0; sl < n_slots; ++sl) loc[sl] = slots[sl] < 0 ? -1 : (int32_t)(sl % chunk);
+        DevBuf d_colmap, d_ident, d_loc, d_dense;
+        PP_CUDA(d_colmap.alloc(sizeof(int32_t) * n_cols, st));
+        PP_CUDA(cudaMemcpyAsync(d_colmap.p, colmap.data(), sizeof(int32_t) * n_cols, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_ident.alloc(sizeof(int32_t) * n_genes, st));
+        PP_CUDA(cudaMemcpyAsync(d_ident.p, ident.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_loc.alloc(sizeof(int32_t) * n_slots, st));
+        PP_CUDA(cudaMemcpyAsync(d_loc.p, loc.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_dense.alloc((size_t)chunk * n_genes * esz, st));
+        for (int64_t s0 = 0; s0 < n_slots; s0 += chunk) {
+            const int64_t nl = std::min(chunk, n_slots - s0);
+            PP_CUDA(cudaMemsetAsync(d_dense.p, 0, (size_t)nl * n_genes * esz, st));
+            rc = pp_csr_densify(ctx, dcsr, d_slots.as<int32_t>() + s0, nl, d_colmap.as<int32_t>(), d_dense.p, n_genes);
+            if (rc) return rc;
+            rc = pp_rank_launch(ctx, d_dense.p, x_dtype, n_genes, d_loc.as<int32_t>() + s0, nl, d_ident.as<int32_t>(),
+                                n_genes, d_rank.as<uint16_t>() + s0 * n_genes, n_genes, d_flags.as<int32_t>());
+            if (rc) return rc;
+        }
+        PP_CUDA(cudaStreamSynchronize(st));  // colmap / ident / loc are locals
+    } else {
+        rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
                             d_rank.as<uint16_t>(), n_genes, d_flags.as<int32_t>());
-    if (rc) return rc;
+        if (rc) return rc;
+    }
     int32_t flags[4];
     PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaStreamSynchronize(st));
@@ -746,4 +792,29 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     *out_class = hc;
     *out_n = (int64_t)count;
     return PP_OK;
+}
+
+PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                      int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
+                      int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
+                      int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
+                      const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
+                      int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
+    if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
+    return sandbag_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, cell_rows, n_cells, class_sizes,
+                        n_classes, gene_cols, n_genes, thresholds, shard, n_shards, out_keys, out_class, out_n,
+                        probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed, out_kept_genes, out_n_kept);
+}
+
+PP_API int pp_sandbag_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const int32_t *cell_rows,
+                          int64_t n_cells, const int64_t *class_sizes, int32_t n_classes, const int32_t *gene_cols,
+                          int64_t n_genes, const int64_t *thresholds, int32_t shard, int32_t n_shards,
+                          uint64_t **out_keys, int32_t **out_class, int64_t *out_n, const int64_t *probe_pairs,
+                          int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed,
+                          int32_t **out_kept_genes, int64_t *out_n_kept) {
+    if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag_csr: NULL argument");
+    return sandbag_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
+                        cell_rows, n_cells, class_sizes, n_classes, gene_cols, n_genes, thresholds, shard, n_shards,
+                        out_keys, out_class, out_n, probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed,
+                        out_kept_genes, out_n_kept);
 }

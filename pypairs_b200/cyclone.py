@@ -101,7 +101,8 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
     logg.hint("received {} marker pairs".format(total))
     if quantile_transform:
         from sklearn.preprocessing import QuantileTransformer
-        raw = QuantileTransformer().fit_transform(np.asarray(raw, dtype=np.float64))
+        dense = raw.toarray() if utils.issparse(raw) else raw
+        raw = QuantileTransformer().fit_transform(np.asarray(dense, dtype=np.float64))
 
     keys = list(pairs.keys())
     rank, ws = _dist.world()

@@ -25,8 +25,10 @@ def is_cuda_tensor(data):
     return type(data).__module__.startswith("torch") and getattr(data, "is_cuda", False)
 
 
-def _dense(x):
-    return x.toarray() if issparse(x) else x
+def _matrix(x):
+    """Sparse input stays sparse: the reference calls .toarray() here (pypairs/utils.py:278-281, 290-292,
+    299-301); the CUDA library takes CSR and densifies chunk by chunk on the device instead."""
+    return x.tocsr() if issparse(x) else x
 
 
 def parse_data(data, gene_names=None, sample_names=None):
@@ -40,17 +42,17 @@ def parse_data(data, gene_names=None, sample_names=None):
             sample_names = list(data.obs_names)
         if gene_names is None:
             gene_names = list(data.var_names)
-        raw = _dense(data.X)
+        raw = _matrix(data.X)
     elif isinstance(data, DataFrame):
         if gene_names is None:
             gene_names = list(data.columns)
         if sample_names is None:
             sample_names = list(data.index)
-        raw = _dense(data.values)
+        raw = _matrix(data.values)
     elif isinstance(data, np.ndarray) or issparse(data) or is_cuda_tensor(data):
         if gene_names is None or sample_names is None:
             raise ValueError("Provide gene names and sample names in ``gene_names`` and ``sample_names``")
-        raw = _dense(data)
+        raw = _matrix(data)
     else:
         raise ValueError("data can only be of type AnnData, DataFrame or ndarray")
     if len(raw.shape) != 2:
@@ -116,6 +118,11 @@ def expressed_gene_mask(raw):
     """~all(data == 0, axis=0) over ALL samples, before sample filtering (pypairs/utils.py:368)."""
     if is_cuda_tensor(raw):
         return (raw != 0).any(dim=0).cpu().numpy()
+    if issparse(raw):
+        m = raw.tocsr()
+        out = np.zeros(m.shape[1], dtype=bool)
+        out[m.indices[m.data != 0]] = True
+        return out
     raw = np.asarray(raw)
     out = np.zeros(raw.shape[1], dtype=bool)
     step = max(1, (1 << 24) // max(1, raw.shape[1]))  # bounded temporaries on large matrices

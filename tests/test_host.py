@@ -47,6 +47,9 @@ def _emulated_sandbag(monkeypatch):
     from pypairs_b200 import _ffi
 
     def fake(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, **kw):
+        if _ffi.is_sparse(x):
+            assert x.format == "csr"  # the host keeps sparse input sparse and hands CSR to the library
+            x = x.toarray()
         x = np.asarray(x, dtype=np.float64)
         gene_cols = np.asarray(gene_cols)
         if kw.get("drop_unexpressed"):
@@ -89,6 +92,28 @@ def test_sandbag_host_logic_vs_reference(monkeypatch, sandbag_api, sandbag_minre
     for frac_s, ref in m["results"].items():
         got = pairs.sandbag(xm, m["annotation"], m["gene_names"], m["sample_names"], fraction=float(frac_s))
         assert [[str(k), [[str(p), str(q)] for p, q in v]] for k, v in got.items()] == ref
+
+
+def test_sparse_input_stays_sparse(monkeypatch, sandbag_api):
+    """scipy-sparse input (any format) reaches the library as CSR and gives the dense answer."""
+    import scipy.sparse as sp
+    from pypairs_b200 import _ffi, pairs, utils
+    _emulated_sandbag(monkeypatch)
+    a = sandbag_api
+    x = np.array(a["x"])
+    sn, gn, lab = a["sample_names"], a["gene_names"], np.array(a["labels"])
+    ann = {k: np.where(lab == i)[0].tolist() for i, k in enumerate(["G1", "S", "G2M"])}
+    exp = pairs.sandbag(x, ann, gn, sn, fraction=0.65)
+    for m in (sp.csr_matrix(x), sp.csc_matrix(x), sp.coo_matrix(x)):
+        raw, _, _ = utils.parse_data(m, gn, sn)
+        assert sp.issparse(raw) and raw.format == "csr"
+        assert list(pairs.sandbag(m, ann, gn, sn, fraction=0.65).items()) == list(exp.items())
+    keep, st, n_rows, n_cols = _ffi.csr_arg(sp.csc_matrix(x.astype(np.int32)))
+    assert (n_rows, n_cols) == x.shape and st.data_dtype == _ffi.PP_F64 and st.is_device == 0
+    dup = sp.csr_matrix((np.array([1.0, 2.0, 5.0]), np.array([3, 3, 1]), np.array([0, 3] + [3] * (x.shape[0] - 1))),
+                        shape=x.shape)
+    keep, st, _, _ = _ffi.csr_arg(dup)  # duplicates are summed, as .toarray() would
+    assert keep[0].tolist() == [5.0, 3.0] and keep[1].tolist() == [1, 3]
 
 
 def test_sandbag_input_errors(monkeypatch):
