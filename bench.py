@@ -278,6 +278,15 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, world)
     e2e_tm = pairs.sandbag.last_timings
     n_markers = sum(len(v) for v in d.values())
+    # same call returning the columnar MarkerTable (no Python tuples): supplementary, not the headline e2e
+    pairs.sandbag(xh, ann, gn, sn, fraction=SB_FRACTION, as_table=True)
+    sync_all(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tab = pairs.sandbag(xh, ann, gn, sn, fraction=SB_FRACTION, as_table=True)
+    sync_all(world)
+    e2e_tab_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, world)
+    assert len(tab) == n_markers
     my_pairs = tm["n_units"]
     alg_ops = 2.0 * my_pairs * n  # one `>` and one `<` per gene pair x cell (sandbag.py:179-182), this rank's launch
     out = {
@@ -288,7 +297,9 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
         "kernel_ms": {"pair": main_step, "rank_and_bitslice": prep_step}, "gpu_launches": launches, "clocks": clocks,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "pair*cell/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(e2e_tm["h2d_bytes"]), "d2h_bytes_per_step": int(n_markers * 12 / max(world, 1)),
-                "api": "pypairs_b200.pairs.sandbag(ndarray pinned) -> dict"},
+                "api": "pypairs_b200.pairs.sandbag(ndarray pinned) -> dict",
+                "as_table": {"value": units / (e2e_tab_ms * 1e-3), "ms_per_step": e2e_tab_ms,
+                             "api": "pairs.sandbag(..., as_table=True) -> utils.MarkerTable (index arrays, no tuples)"}},
         "roofline": {"bound": "int_alu", "kernel": "pair_kernel", "achieved": alg_ops / (main_step * 1e-3) / 1e9,
                      "peak": peaks["lop3_lane_ops_per_s"] / 1e9, "unit": "Gop/s",
                      "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],

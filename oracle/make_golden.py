@@ -16,6 +16,7 @@ Outputs
     cyclone_cases.npz/.json   synthetic matrices + marker dicts + reference scores / observed counters
     mt19937.json              generator known answers + permutation-table digests
     default_cc_marker.json    compact columnar form of the bundled leng15 marker set (data fixture)
+    evaluate_prediction.json  utils.evaluate_prediction tables (sklearn) on four label vectors
 """
 import hashlib
 import json
@@ -231,6 +232,16 @@ def main():
                                 "first_row_head": t[0][:8].tolist(), "last_row_head": t[-1][:8].tolist()}
     mt["tables"]["7_seed99"] = {"rows": nb_tables(99, 7, 6).tolist()}
     json.dump(mt, open(os.path.join(OUT, "mt19937.json"), "w"), indent=0)
+    # ---------------------------------------------------------------- utils.evaluate_prediction (pypairs/utils.py:23-94)
+    ev_cases = [(list("AABBCCDD"), list("AABBCCDD")), (list("AABBCCDD"), list("DDBBCCAA")),
+                (["G1", "S", "S", "G2M", "N/A", "G1", "G1"], ["G1", "S", "G2M", "G2M", "S", "G1", "S"]),
+                (list("aabbccab"), list("abcabcab"))]
+    ev = []
+    for pred, ref in ev_cases:
+        r = utils.evaluate_prediction(prediction=pred, reference=ref)
+        ev.append({"prediction": pred, "reference": ref, "index": [str(i) for i in r.index],
+                   "columns": [str(c) for c in r.columns], "values": r.values.astype(float).tolist()})
+    json.dump(ev, open(os.path.join(OUT, "evaluate_prediction.json"), "w"))
     print("reference version", pypairs.__version__, "numba", numba.__version__)
 
 

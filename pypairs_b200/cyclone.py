@@ -21,9 +21,18 @@ def filter_marker_pairs(marker_pairs, gene_names):
     n = len(gene_names)
     out_pairs, out_used = {}, {}
     removed = 0
-    for cat, pairs in marker_pairs.items():
-        ia = np.fromiter((name_to_idx.get(p[0], -1) for p in pairs), dtype=np.int64, count=len(pairs))
-        ib = np.fromiter((name_to_idx.get(p[1], -1) for p in pairs), dtype=np.int64, count=len(pairs))
+    if isinstance(marker_pairs, utils.MarkerTable):  # columnar markers: map each distinct gene once
+        t = marker_pairs
+        g2i = np.fromiter((name_to_idx.get(g, -1) for g in t.gene_names.tolist()), dtype=np.int64,
+                          count=len(t.gene_names))
+        per_class = [(t.class_names[k], g2i[t.rows[t.cls == k]], g2i[t.cols[t.cls == k]]) for k in t.class_order()]
+    else:
+        per_class = []
+        for cat, pairs in marker_pairs.items():
+            per_class.append((cat,
+                              np.fromiter((name_to_idx.get(p[0], -1) for p in pairs), dtype=np.int64, count=len(pairs)),
+                              np.fromiter((name_to_idx.get(p[1], -1) for p in pairs), dtype=np.int64, count=len(pairs))))
+    for cat, ia, ib in per_class:
         ok = (ia >= 0) & (ib >= 0)
         removed += int((~ok).sum())
         ia, ib = ia[ok], ib[ok]

@@ -73,7 +73,7 @@ def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
 
 
 def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=0.65, filter_genes=None,
-            filter_samples=None):
+            filter_samples=None, *, as_table=False):
     """Calculate the pairs of genes serving as marker pairs for each category.
 
     Same signature, defaults and return value as pypairs.pairs.sandbag
@@ -81,6 +81,9 @@ def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=
     (gene_high, gene_low) tuples in the reference's order.  `data` may be an AnnData (classes from
     ``obs['category']`` unless `annotation` is given), a DataFrame, an ndarray / scipy-sparse matrix
     with `gene_names` and `sample_names`, or a CUDA torch tensor.
+
+    `as_table=True` (keyword-only extension) returns a `utils.MarkerTable` -- the same markers as index arrays,
+    without building Python tuples (`.to_dict()` gives the dict); pairs.cyclone accepts it directly.
 
     Under torch.distributed (one process per GPU) the gene-pair tiles are sharded over the ranks
     and every rank returns the complete dict.
@@ -95,11 +98,18 @@ def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=
         keys, cls = _dist.allgather_varlen((keys, cls))
         order = np.argsort(keys, kind="stable")
         keys, cls = keys[order], cls[order]
+    sandbag.last_timings = tm
+    if as_table:
+        k64 = np.ascontiguousarray(keys).view(np.int64)
+        n = max(len(kept), 1)
+        out = utils.MarkerTable(k64 // n, k64 % n, cls, p["gene_names"][kept], p["class_names"])
+        logg.info("finished", time_=True)
+        logg.hint("found {} marker pairs ({})".format(len(out), out.counts()))
+        return out
     out = markers_to_dict(keys, cls, len(kept), p["gene_names"][kept], p["class_names"])
     logg.info("finished", time_=True)
     logg.hint("found {} marker pairs ({})".format(len(keys), ", ".join(
         "{}: {}".format(k, len(v)) for k, v in out.items())))
-    sandbag.last_timings = tm
     return out
 
 

@@ -10,6 +10,9 @@ import os
 verbosity = 1
 """0 silent ... 4 chatty (only messages, never results)."""
 
+writedir = "./write/"
+"""Root of utils.export_marker / utils.load_marker when `defaultpath=True` (pypairs/settings.py:19)."""
+
 n_jobs = os.cpu_count()
 """Kept for source compatibility; the GPU path ignores it."""
 

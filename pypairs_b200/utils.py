@@ -4,6 +4,7 @@ Everything here is cheap index / mask logic; the expression matrix itself is nev
 or filtered on the host -- the kernels gather the kept rows / columns on the device.
 """
 import json
+import os
 
 import numpy as np
 from pandas import DataFrame
@@ -149,14 +150,99 @@ def same_marker(a, b):
     return True
 
 
-def export_marker(marker, fname):
-    """Marker dict -> JSON file (pypairs/utils.py:97-130 semantics: lists of 2-lists per class)."""
-    with open(fname, "w") as f:
-        json.dump({str(k): [[str(a), str(b)] for a, b in v] for k, v in marker.items()}, f)
+def export_marker(marker, fname, defaultpath=True):
+    """Marker pairs -> JSON file under `settings.writedir` (or at `fname` itself with defaultpath=False).
+    I/O errors are logged, not raised (pypairs/utils.py:97-130)."""
+    from . import log as logg, settings
+    fpath = settings.writedir + fname if defaultpath else fname
+    try:
+        if defaultpath and settings.writedir and not os.path.isdir(settings.writedir):
+            os.makedirs(settings.writedir, exist_ok=True)
+        with open(fpath, "w") as f:
+            json.dump({str(k): [[str(a), str(b)] for a, b in v] for k, v in dict(marker).items()}, f)
+        logg.hint("marker pairs written to: " + str(fpath))
+    except IOError as e:
+        logg.error("could not write to {}. Please verify that the path exists and is writable. "
+                   "Or change `writedir` via `pypairs_b200.settings.writedir`".format(fpath))
+        logg.error(str(e))
 
 
-def load_marker(fname):
-    """JSON file -> marker dict of tuples (pypairs/utils.py:133-166)."""
-    with open(fname) as f:
-        d = json.load(f)
-    return {k: [tuple(p) for p in v] for k, v in d.items()}
+def load_marker(fname, defaultpath=True):
+    """JSON file -> marker dict; None (and a logged error) if it cannot be read (pypairs/utils.py:133-166)."""
+    from . import log as logg, settings
+    fpath = settings.writedir + fname if defaultpath else fname
+    try:
+        with open(fpath) as f:
+            marker = json.load(f)
+    except IOError:
+        logg.error("could not read from {}.\n Please verify that the path exists and is writable.".format(fpath))
+        return None
+    logg.hint("loaded {} marker pairs".format(sum(len(p) for p in marker.values())))
+    return marker
+
+
+def evaluate_prediction(prediction, reference):
+    """F1 score, recall and precision of a cyclone prediction (pypairs/utils.py:23-94).
+
+    Returns a DataFrame indexed by the sorted union of labels plus "average", with columns "f1", "recall",
+    "precision", "average" (the row-wise mean of the three).  Same numbers as the reference's sklearn calls
+    (per-label scores with `labels=np.unique(ref + pred)`, macro average, 0 where a denominator is 0).
+    """
+    ref = np.array(reference)
+    pred = np.array(prediction)
+    labels = np.unique(list(ref) + list(pred))
+    tp = np.array([np.sum((ref == k) & (pred == k)) for k in labels], dtype=np.float64)
+    n_ref = np.array([np.sum(ref == k) for k in labels], dtype=np.float64)
+    n_pred = np.array([np.sum(pred == k) for k in labels], dtype=np.float64)
+
+    def ratio(a, b):
+        return np.divide(a, b, out=np.zeros_like(a), where=b != 0)
+
+    recall = ratio(tp, n_ref)
+    precision = ratio(tp, n_pred)
+    f1 = ratio(2.0 * tp, n_ref + n_pred)
+    rows = {"f1": np.append(f1, f1.mean()), "recall": np.append(recall, recall.mean()),
+            "precision": np.append(precision, precision.mean())}
+    df = DataFrame(rows, index=np.append(labels, "average"), columns=["f1", "recall", "precision"])
+    df["average"] = df[["f1", "recall", "precision"]].mean(axis=1)
+    return df
+
+
+class MarkerTable(object):
+    """Columnar form of a sandbag result: index arrays instead of hundreds of thousands of Python tuples.
+
+    `rows[i]`, `cols[i]` index `gene_names`, `cls[i]` indexes `class_names`; entries are in the reference's
+    scan order (row-major over the kept-gene matrix).  `to_dict()` gives exactly what pairs.sandbag returns;
+    pairs.cyclone accepts a MarkerTable directly and maps the genes by name without building tuples.
+    """
+
+    def __init__(self, rows, cols, cls, gene_names, class_names):
+        self.rows = np.asarray(rows, dtype=np.int64)
+        self.cols = np.asarray(cols, dtype=np.int64)
+        self.cls = np.asarray(cls, dtype=np.int64)
+        self.gene_names = np.asarray(gene_names)
+        self.class_names = np.asarray(class_names)
+
+    def __len__(self):
+        return len(self.rows)
+
+    def class_order(self):
+        """Class indices in order of first appearance (the reference's dict key order)."""
+        first = np.full(len(self.class_names), len(self.cls), dtype=np.int64)
+        first[self.cls[::-1]] = np.arange(len(self.cls) - 1, -1, -1)
+        return [int(k) for k in np.argsort(first, kind="stable") if first[k] < len(self.cls)]
+
+    def keys(self):
+        return [self.class_names[k] for k in self.class_order()]
+
+    def counts(self):
+        return {self.class_names[k]: int(np.sum(self.cls == k)) for k in self.class_order()}
+
+    def to_dict(self):
+        names = np.empty(len(self.gene_names), dtype=object)
+        names[:] = list(self.gene_names)
+        out = {}
+        for k in self.class_order():
+            m = self.cls == k
+            out[self.class_names[k]] = list(zip(names[self.rows[m]].tolist(), names[self.cols[m]].tolist()))
+        return out

@@ -296,3 +296,21 @@ def test_atlas_shape_properties():
     assert got == sorted(zip(rr.tolist(), cc.tolist(), kk.tolist()))
     print("cfg4 full size: {} markers, {} planes, kernel {:.1f} ms, prep {:.1f} ms -> {:.3g} pair*cell/s".format(
         len(keys), tm["n_planes"], tm["main_ms"], tm["prep_ms"], g * (g - 1) / 2 * n / (tm["main_ms"] * 1e-3)))
+
+
+def test_marker_table_roundtrip_and_cyclone():
+    """as_table=True gives the same markers without tuples; pairs.cyclone takes the table directly."""
+    from pypairs_b200 import pairs, utils
+    rng = np.random.default_rng(51)
+    x, lab = synth(rng, 300, 400, 3, frac_de=0.3, dtype=np.float32)
+    gn = ["g{}".format(i) for i in range(400)]
+    sn = ["c{}".format(i) for i in range(300)]
+    ann = {k: np.where(lab == i)[0].tolist() for i, k in enumerate(["G1", "S", "G2M"])}
+    d = pairs.sandbag(x, ann, gn, sn, fraction=0.6)
+    t = pairs.sandbag(x, ann, gn, sn, fraction=0.6, as_table=True)
+    assert isinstance(t, utils.MarkerTable) and list(t.to_dict().items()) == list(d.items())
+    y = rng.poisson(3.0, (50, 400)).astype(np.float32)
+    yn = ["u{}".format(i) for i in range(50)]
+    a = pairs.cyclone(y, d, gn, yn, iterations=60, min_iter=10, min_pairs=3)
+    b = pairs.cyclone(y, t, gn, yn, iterations=60, min_iter=10, min_pairs=3)
+    assert a.equals(b) and list(a.columns)[:len(d)] == list(d.keys())

@@ -207,3 +207,88 @@ def test_two_rank_gloo_merge():
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert all("GLOO_OK" in o for o in outs), "\n".join(outs)
+
+
+def test_evaluate_prediction_vs_reference(golden_dir):
+    """pypairs/tests/test_utils.py:7-30 known answers + tables produced by the reference (sklearn)."""
+    from pypairs_b200 import utils
+    pred = list("AABBCCDD")
+    e = utils.evaluate_prediction(prediction=pred, reference=list("AABBCCDD"))
+    assert np.array_equal(np.array(e.values, dtype=float), np.ones((5, 4)))
+    e = utils.evaluate_prediction(prediction=pred, reference=list("DDBBCCAA"))
+    assert np.array_equal(e.values, np.array([[0] * 4, [1] * 4, [1] * 4, [0] * 4, [0.5] * 4], dtype=float))
+    for case in json.load(open(os.path.join(golden_dir, "evaluate_prediction.json"))):
+        e = utils.evaluate_prediction(case["prediction"], case["reference"])
+        assert [str(i) for i in e.index] == case["index"] and [str(c) for c in e.columns] == case["columns"]
+        assert np.allclose(e.values.astype(float), np.array(case["values"]), rtol=0, atol=1e-15)
+
+
+def test_marker_export_load_roundtrip(tmp_path, monkeypatch):
+    """pypairs/tests/test_utils.py:33-58: default path under settings.writedir, failures are logged not raised."""
+    from pypairs_b200 import datasets, settings, utils
+    m = datasets.default_cc_marker()
+    monkeypatch.setattr(settings, "writedir", str(tmp_path) + "/w/")
+    monkeypatch.setattr(settings, "verbosity", 0)
+    bad = "/not/existing/path/marker_exp.json"
+    utils.export_marker(m, bad, defaultpath=False)
+    assert not os.path.isfile(bad)
+    utils.export_marker(m, "marker_exp.json")
+    assert os.path.isfile(settings.writedir + "marker_exp.json")
+    assert utils.load_marker(bad, defaultpath=False) is None
+    assert utils.same_marker(m, utils.load_marker("marker_exp.json"))
+
+
+def test_marker_table_and_cli(monkeypatch, tmp_path, sandbag_api):
+    """Columnar MarkerTable == dict result; it feeds filter_marker_pairs like the dict; CLIs run end to end
+    (kernels emulated by the oracle)."""
+    from click.testing import CliRunner
+    from pandas import DataFrame
+    from pypairs_b200 import _ffi, pairs, utils
+    from pypairs_b200.cli.cyclone.__main__ import main as cyclone_cli
+    from pypairs_b200.cli.sandbag.__main__ import main as sandbag_cli
+    from pypairs_b200.cyclone import filter_marker_pairs
+    _emulated_sandbag(monkeypatch)
+    a = sandbag_api
+    x = np.array(a["x"])
+    sn, gn, lab = a["sample_names"], a["gene_names"], np.array(a["labels"])
+    ann = {k: np.where(lab == i)[0].tolist() for i, k in enumerate(["G1", "S", "G2M"])}
+    d = pairs.sandbag(x, ann, gn, sn, fraction=0.65)
+    t = pairs.sandbag(x, ann, gn, sn, fraction=0.65, as_table=True)
+    assert isinstance(t, utils.MarkerTable) and list(t.to_dict().items()) == list(d.items())
+    assert t.keys() == list(d.keys()) and t.counts() == {k: len(v) for k, v in d.items()} and len(t) == sum(t.counts().values())
+    names = gn[5:] + ["other"]
+    p_d, u_d = filter_marker_pairs(d, names)
+    p_t, u_t = filter_marker_pairs(t, names)
+    assert list(p_d.keys()) == list(p_t.keys())
+    assert all(np.array_equal(p_d[k], p_t[k]) and np.array_equal(u_d[k], u_t[k]) for k in p_d)
+
+    # CLI: sandbag
+    data_csv, ann_csv, out_json = tmp_path / "d.csv", tmp_path / "a.csv", tmp_path / "m.json"
+    DataFrame(x, index=sn, columns=gn).to_csv(data_csv)
+    with open(ann_csv, "w") as f:
+        f.write("name,class\n" + "".join("{},{}\n".format(sn[i], ["G1", "S", "G2M"][lab[i]]) for i in range(len(sn)) if lab[i] >= 0))
+    r = CliRunner().invoke(sandbag_cli, ["-d", str(data_csv), "-a", str(ann_csv), "-f", "0.65", "-o", str(out_json), "-v", "0"])
+    assert r.exit_code == 0, r.output
+    got = json.load(open(out_json))
+    assert utils.same_marker(got, d)
+
+    # CLI: cyclone (kernel emulated)
+    def fake_cyclone(xm, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,
+                     row_begin=0, n_cells=None, **kw):
+        xm = np.asarray(xm, dtype=np.float64)
+        out = []
+        for u, p in zip(used_idx_list, pairs_list):
+            used = np.zeros(xm.shape[1], dtype=bool)
+            used[u] = True
+            out.append(orc.phase_scores(xm, iterations, min_iter, min_pairs, p, used, seed=seed))
+        return np.stack(out), {}
+
+    monkeypatch.setattr(_ffi, "cyclone", fake_cyclone)
+    out_csv = tmp_path / "s.csv"
+    r = CliRunner().invoke(cyclone_cli, ["-d", str(data_csv), "-m", str(out_json), "-i", "40", "-x", "10", "-y", "2",
+                                         "-o", str(out_csv), "-v", "0"])
+    assert r.exit_code == 0, r.output
+    import pandas as pd
+    sc = pd.read_csv(out_csv, index_col=0)
+    exp = pairs.cyclone(DataFrame(x, index=sn, columns=gn), got, iterations=40, min_iter=10, min_pairs=2)
+    assert list(sc.columns) == list(exp.columns) and np.allclose(sc[list(got.keys())].values, exp[list(got.keys())].values)
