@@ -8,7 +8,7 @@ from math import ceil
 
 import numpy as np
 
-from . import _dist, _ffi, log as logg, utils
+from . import _dist, _ffi, log as logg, settings, utils
 
 
 def calc_thresholds(class_sizes, fraction):
@@ -104,7 +104,8 @@ def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=
         n = max(len(kept), 1)
         out = utils.MarkerTable(k64 // n, k64 % n, cls, p["gene_names"][kept], p["class_names"])
         logg.info("finished", time_=True)
-        logg.hint("found {} marker pairs ({})".format(len(out), out.counts()))
+        if settings.verbosity >= 4:
+            logg.hint("found {} marker pairs ({})".format(len(out), out.counts()))
         return out
     out = markers_to_dict(keys, cls, len(kept), p["gene_names"][kept], p["class_names"])
     logg.info("finished", time_=True)
