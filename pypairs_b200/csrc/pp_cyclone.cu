@@ -24,6 +24,7 @@
 // sides; score = below / iterations as one IEEE double division (:246).
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -494,12 +495,14 @@ struct PermKey {
 // MT19937 tables depend on (seed, n, iters) only and cost ~10 ms of serial host time each:
 // keep the few a process ever needs.
 std::map<PermKey, std::vector<uint16_t>> g_perm_cache;
+std::mutex g_perm_mutex;  // contexts are single-threaded, but two contexts may run in two threads
 
 const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
+    std::lock_guard<std::mutex> lock(g_perm_mutex);
     PermKey key{PP_RNG_MT19937, seed, 0, n, iters};
     auto it = g_perm_cache.find(key);
     if (it != g_perm_cache.end()) return it->second;
-    if (g_perm_cache.size() > 64) g_perm_cache.clear();
+    // entries are never evicted while in use: a std::map node is stable and the table is tiny (n * iters * 2 B)
     std::vector<uint16_t> &v = g_perm_cache[key];
     v.resize((size_t)n * iters);
     mt_perm_table(seed, n, iters, v.data());

@@ -16,7 +16,8 @@
 // Keys live in a per-CTA global scratch (L2 resident: 32768 genes * 10 B * 2 buffers).
 // Count fast path: when every kept value of the cell is an integer in [0, 65535] (raw UMI / read counts, the
 // usual sandbag / cyclone input) no sort is needed: a 65 536-bit presence bitmap in shared memory, a prefix
-// popcount over its 2048 words, and rank(v) = #present values below v.  Three coalesced passes over the row.
+// popcount over its 2048 words, and rank(v) = #present values below v.  One pass over the row from global
+// memory; the counts are staged as u16 in shared memory for the look-up pass.
 #include <stdarg.h>
 
 #include <algorithm>
@@ -67,6 +68,7 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
             uint8_t *__restrict__ scratch, size_t scratch_per_cta, int32_t *__restrict__ flags) {
     typedef typename KeyOf<T>::type K;
     __shared__ RankSmem sm;
+    extern __shared__ __align__(16) uint16_t vals[];  // [n] staged counts of the fast path
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // warp-contiguous element ranges (multiples of 32 so every step is a full, aligned warp step)
     const int per_warp = ((n + RANK_WARPS * 32 - 1) / (RANK_WARPS * 32)) * 32;
@@ -87,17 +89,34 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
             continue;
         }
         const T *xr = x + (int64_t)row * ld;
-        // ---- 0. count fast path
+        // ---- 0. count fast path: one pass over the row from global memory (8 independent loads in flight per
+        //         thread), values staged as u16 in shared memory for the rank look-up pass
         {
-            bool small = true;
-            for (int g = tid; g < n; g += RANK_THREADS) small = small && is_small_count(xr[gene_cols[g]]);
             for (int i = tid; i < BM_WORDS; i += RANK_THREADS) sm.bitmap[i] = 0;
-            if (__syncthreads_and(small)) {  // CTA-uniform (NaN fails the test and takes the sort path)
-                for (int g = tid; g < n; g += RANK_THREADS) {
-                    const uint32_t u = (uint32_t)xr[gene_cols[g]];
-                    atomicOr(&sm.bitmap[u >> 5], 1u << (u & 31));
+            __syncthreads();
+            bool small = true;
+            for (int g0 = tid; g0 < n; g0 += RANK_THREADS * 8) {
+                T v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = g0 + j * RANK_THREADS;
+                    v[j] = g < n ? xr[gene_cols[g]] : (T)0;
                 }
-                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int g = g0 + j * RANK_THREADS;
+                    if (g < n) {
+                        const bool ok = is_small_count(v[j]);
+                        small = small && ok;
+                        const uint32_t u = ok ? (uint32_t)v[j] : 0u;
+                        vals[g] = (uint16_t)u;
+                        const uint32_t bit = 1u << (u & 31);
+                        // most cells hold a handful of distinct counts: test first, the atomic is then rare
+                        if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
+                    }
+                }
+            }
+            if (__syncthreads_and(small)) {  // CTA-uniform (NaN fails the test and takes the sort path)
                 // exclusive prefix popcount over the 2048 words: 4 words per thread, warp scan, warp totals
                 uint32_t c[4], t4 = 0;
 #pragma unroll
@@ -118,10 +137,10 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                 if (tid == RANK_THREADS - 1) atomicMax(&flags[0], (int)run - 1);  // distinct values - 1
                 __syncthreads();
                 for (int g = tid; g < n; g += RANK_THREADS) {
-                    const uint32_t u = (uint32_t)xr[gene_cols[g]];
+                    const uint32_t u = vals[g];
                     out[g] = (uint16_t)(sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & ((1u << (u & 31)) - 1u)));
                 }
-                __syncthreads();  // bitmap / prefix reused by the next cell
+                __syncthreads();  // bitmap / prefix / vals reused by the next cell
                 continue;
             }
         }
@@ -260,12 +279,15 @@ int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const 
     int grid = (int)((n_slots < (int64_t)ctx->n_sm * 3) ? n_slots : (int64_t)ctx->n_sm * 3);
     DevBuf scratch;
     PP_CUDA(scratch.alloc(per_cta * (size_t)grid, ctx->stream));
+    const size_t dyn = ((size_t)n_genes * 2 + 15) & ~(size_t)15;
+    PP_CUDA(cudaFuncSetAttribute(rank_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    PP_CUDA(cudaFuncSetAttribute(rank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     if (x_dtype == PP_F64)
-        rank_kernel<double><<<grid, RANK_THREADS, 0, ctx->stream>>>(
+        rank_kernel<double><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
             (const double *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
             scratch.as<uint8_t>(), per_cta, d_flags);
     else
-        rank_kernel<float><<<grid, RANK_THREADS, 0, ctx->stream>>>(
+        rank_kernel<float><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
             (const float *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
             scratch.as<uint8_t>(), per_cta, d_flags);
     PP_CHECK_LAUNCH();
