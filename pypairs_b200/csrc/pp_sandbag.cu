@@ -89,7 +89,7 @@ struct Chunk {  // a run of cell words of one class
     int32_t w_begin;
     int32_t n_words;
     int32_t class_end;  // class index if this chunk closes the class, else -1
-    int32_t flush;      // WIDE kernels: fold the 16-bit counters into the 32-bit ones after this chunk
+    int32_t flush;      // unused
 };
 
 struct PairParams {
@@ -103,41 +103,49 @@ struct PairParams {
     int n_genes, n_words, n_planes, n_chunks, n_classes, wc_max;
 };
 
-// TI x TJ = per-thread register tile of gene pairs (TI in {4, 8}, TJ = 4), thread grid (128/TI) x (64/TJ).
-// WIDE = classes with more than 65 535 cells and / or more than 254 classes: the packed 16+16-bit counters
-// are folded into 32-bit counters kept in shared memory every <= 2047 cell words, and the per-pair decision
-// state uses 16-bit fields in two registers.
-// Warps 0 .. PAIR_THREADS/32-1 consume; one extra warp (the last) is the TMA producer.  full[s] (1 arrival +
-// transaction bytes) hands a stage to the consumers, empty[s] (one arrival per consumer warp) hands it back,
-// so the consumer warps never meet at a CTA-wide barrier and drift up to STAGES-1 chunks apart.
-template <int TI, int TJ, bool WIDE>
+// Two sweeps over the cell words of a 128 x 64 gene tile, one kernel.
+//  Sweep 1 (all pairs): only num_pos = #(x[g1] > x[g2]) is accumulated -- ONE LOP3 per plane per pair and word -- and
+//     thresholded per class (nup, up_idx).  The decision of sandbag.py:192-197 can only emit when nup == 1 or
+//     nup == C-1, whatever num_neg is; on expression data that is ~1-2 % of the pairs ("candidates").
+//  Sweep 2 (candidates only, 512 per round = one per consumer thread): the same operand stream is replayed and
+//     num_neg = #(x[g1] < x[g2]) is accumulated for the candidates, thresholded (ndn, dn_idx), and the decision emits.
+// So the second predicate of sandbag.py:179-182 is evaluated exactly where it can matter, halving the LOP3 work.
+// Per-pair counters are plain 32-bit registers (any class size), the state packs nup | up_idx << 16 (<= 65 534 classes).
+//
+// TI x TJ = per-thread register tile of gene pairs (4 x 4), consumer thread grid (128/TI) x (64/TJ) = 512 threads.
+// Warps 0 .. 15 consume; one extra warp is the TMA producer.  full[s] (1 arrival + transaction bytes) hands a stage to
+// the consumers, empty[s] (one arrival per consumer warp) hands it back, so the consumer warps never meet at a CTA-wide
+// barrier inside a sweep and drift up to STAGES-1 chunks apart.
+constexpr int CAND_PER_ROUND = 512;
+
+template <int TI, int TJ>
 __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_kernel(const PairParams P) {
     constexpr int NTJ = TILE_B / TJ;
     constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;  // consumer threads
     constexpr int CONSUMER_WARPS = PAIR_THREADS / 32;
     static_assert(TJ == 4 && (TI == 4 || TI == 8), "shared loads below are written for these tiles");
+    static_assert(PAIR_THREADS == CAND_PER_ROUND, "one candidate per consumer thread and round");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ uint2 cand[CAND_PER_ROUND];  // .x = la | lb << 8 (tile-local genes), .y = nup | up_idx << 16
+    __shared__ int s_total;
 
     const int tid = threadIdx.x;
     const int ti = tid / NTJ, tj = tid % NTJ;
     const int2 tile = P.tiles[blockIdx.x];
     const int B = P.n_planes;
-    const int blk_words = P.wc_max * B * 64;              // u32 per gene block per stage
+    const int blk_words = P.wc_max * B * 64;  // u32 per gene block per stage
     const uint32_t stage_words = 3u * blk_words;
     uint32_t *smem = reinterpret_cast<uint32_t *>(smem_raw);
 
-    // WIDE: [TI*TJ][2][threads] 32-bit counters behind the stage ring
-    int32_t *wide = reinterpret_cast<int32_t *>(smem + (size_t)STAGES * stage_words) + tid;
-    if (WIDE && tid < PAIR_THREADS)
-        for (int q = 0; q < TI * TJ * 2; ++q) wide[q * PAIR_THREADS] = 0;
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], CONSUMER_WARPS);
         }
         fence_mbar_init();
+        s_total = 0;
     }
     __syncthreads();
 
@@ -146,11 +154,12 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
     const uint32_t *gA1 = gA0 + blk_stride;
     const uint32_t *gB = P.planes + (int64_t)tile.y * blk_stride;
 
-    if (tid >= PAIR_THREADS) {  // ---- producer warp: one elected lane streams every chunk of this tile
-        if (tid == PAIR_THREADS) {
-            for (int c = 0; c < P.n_chunks; ++c) {
-                const int s = c % STAGES;
-                if (c >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(c / STAGES - 1) & 1u);  // consumers released it
+    if (tid >= PAIR_THREADS) {  // ---- producer warp: one elected lane streams the chunk sequence once per sweep
+        int q = 0;              // running chunk number over all sweeps (stage = q % STAGES)
+        auto stream_sweep = [&]() {
+            for (int c = 0; c < P.n_chunks; ++c, ++q) {
+                const int s = q % STAGES;
+                if (q >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(q / STAGES - 1) & 1u);  // consumers released it
                 const Chunk ch = P.chunks[c];
                 uint32_t *dst = smem + (size_t)s * stage_words;
                 const uint32_t bytes = (uint32_t)ch.n_words * B * 64 * 4;
@@ -160,31 +169,35 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
                 bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
                 bulk_g2s(dst + 2 * blk_words, gB + off, bytes, &full_bar[s]);
             }
-        }
+        };
+        if (tid == PAIR_THREADS) stream_sweep();
+        __syncthreads();  // (A) sweep 1 is consumed and the candidates are counted
+        const int rounds = (s_total + CAND_PER_ROUND - 1) / CAND_PER_ROUND;
+        if (tid == PAIR_THREADS)
+            for (int r = 0; r < rounds; ++r) stream_sweep();
         return;
     }
 
-    uint32_t acc[TI][TJ], st[TI][TJ], st2[WIDE ? TI : 1][WIDE ? TJ : 1];
+    // =============================== sweep 1: num_pos of every pair of the tile
+    uint32_t acc[TI][TJ], st[TI][TJ];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) {
-            acc[i][j] = 0, st[i][j] = 0;
-            if (WIDE) st2[i][j] = 0;
-        }
+        for (int j = 0; j < TJ; ++j) acc[i][j] = 0, st[i][j] = 0;
 
     const int la = ti * TI;  // first local a-gene (0..127), never straddles a 64-gene block
     const uint32_t a_off = (uint32_t)(la >> 6) * blk_words + (la & 63);
     const uint32_t b_off = 2u * blk_words + tj * TJ;
+    int q = 0;
 
-    for (int c = 0; c < P.n_chunks; ++c) {
-        const int s = c % STAGES;
-        mbar_wait(&full_bar[s], (uint32_t)(c / STAGES) & 1u);
+    for (int c = 0; c < P.n_chunks; ++c, ++q) {
+        const int s = q % STAGES;
+        mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
         const Chunk ch = P.chunks[c];
         const uint32_t *sa = smem + (size_t)s * stage_words + a_off;
         const uint32_t *sb = smem + (size_t)s * stage_words + b_off;
         for (int w = 0; w < ch.n_words; ++w) {
-            uint32_t gt[TI][TJ], lt[TI][TJ];
+            uint32_t gt[TI][TJ];
             {
                 uint32_t a[TI], b[TJ];
                 load_words<TI>(sa, a);
@@ -192,12 +205,9 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
 #pragma unroll
                 for (int i = 0; i < TI; ++i)
 #pragma unroll
-                    for (int j = 0; j < TJ; ++j) {
-                        gt[i][j] = a[i] & ~b[j];
-                        lt[i][j] = ~a[i] & b[j];
-                    }
+                    for (int j = 0; j < TJ; ++j) gt[i][j] = a[i] & ~b[j];
             }
-#pragma unroll 2
+#pragma unroll 4
             for (int p = 1; p < B; ++p) {
                 uint32_t a[TI], b[TJ];
                 load_words<TI>(sa + p * 64, a);
@@ -205,95 +215,121 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
 #pragma unroll
                 for (int i = 0; i < TI; ++i)
 #pragma unroll
-                    for (int j = 0; j < TJ; ++j) {
-                        gt[i][j] = lop3_gt(a[i], b[j], gt[i][j]);
-                        lt[i][j] = lop3_lt(a[i], b[j], lt[i][j]);
-                    }
+                    for (int j = 0; j < TJ; ++j) gt[i][j] = lop3_gt(a[i], b[j], gt[i][j]);
             }
 #pragma unroll
             for (int i = 0; i < TI; ++i)
 #pragma unroll
-                for (int j = 0; j < TJ; ++j)
-                    acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u,
-                                             fma_pipe_mad((uint32_t)__popc(lt[i][j]), 65536u, acc[i][j]));
+                for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
             sa += B * 64;
             sb += B * 64;
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
-        if (WIDE && (ch.flush || ch.class_end >= 0)) {
-#pragma unroll
-            for (int i = 0; i < TI; ++i)
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) {
-                    wide[((i * TJ + j) * 2 + 0) * PAIR_THREADS] += (int32_t)(acc[i][j] & 0xffffu);
-                    wide[((i * TJ + j) * 2 + 1) * PAIR_THREADS] += (int32_t)(acc[i][j] >> 16);
-                    acc[i][j] = 0;
-                }
-        }
-        if (ch.class_end >= 0) {  // CTA-uniform: thresholds of sandbag.py:184-190 for this class
+        if (ch.class_end >= 0) {  // CTA-uniform: `num_pos[i] >= thresholds[i]` of sandbag.py:185-187, last class wins
             const uint32_t k = (uint32_t)ch.class_end;
-            const int32_t thr = __ldg(P.thr + k);
+            const int64_t thr = (int64_t)__ldg(P.thr + k);
 #pragma unroll
             for (int i = 0; i < TI; ++i)
 #pragma unroll
                 for (int j = 0; j < TJ; ++j) {
-                    if (WIDE) {  // st = nup | ndn << 16, st2 = up_idx | dn_idx << 16
-                        const int32_t pos = wide[((i * TJ + j) * 2 + 0) * PAIR_THREADS];
-                        const int32_t neg = wide[((i * TJ + j) * 2 + 1) * PAIR_THREADS];
-                        wide[((i * TJ + j) * 2 + 0) * PAIR_THREADS] = 0;
-                        wide[((i * TJ + j) * 2 + 1) * PAIR_THREADS] = 0;
-                        if (pos >= thr) { st[i][j] += 1u; st2[i][j] = (st2[i][j] & 0xffff0000u) | k; }
-                        if (neg >= thr) { st[i][j] += 0x10000u; st2[i][j] = (st2[i][j] & 0x0000ffffu) | (k << 16); }
-                    } else {     // st = nup | ndn << 8 | up_idx << 16 | dn_idx << 24
-                        const int32_t pos = (int32_t)(acc[i][j] & 0xffffu), neg = (int32_t)(acc[i][j] >> 16);
-                        uint32_t s2 = st[i][j];
-                        if (pos >= thr) s2 = ((s2 & 0xff00ffffu) | (k << 16)) + 1u;
-                        if (neg >= thr) s2 = ((s2 & 0x00ffffffu) | (k << 24)) + 0x100u;
-                        st[i][j] = s2;
-                        acc[i][j] = 0;
-                    }
+                    if ((int64_t)acc[i][j] >= thr) st[i][j] = ((st[i][j] & 0xffffu) + 1u) | (k << 16);
+                    acc[i][j] = 0;
                 }
         }
     }
 
-    // decision of sandbag.py:192-197 + warp-aggregated compaction
+    // =============================== candidates: pairs whose decision can still emit (nup == 1 or nup == C-1)
     const int ga0 = tile.x * TILE_A + la, gb0 = tile.y * TILE_B + tj * TJ;
     const uint32_t C = (uint32_t)P.n_classes;
     const int lane = tid & 31;
+    uint32_t cmask = 0;
 #pragma unroll
     for (int i = 0; i < TI; ++i)
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
-            const int ga = ga0 + i, gb = gb0 + j;
-            const uint32_t s2 = st[i][j];
-            const uint32_t nup = WIDE ? (s2 & 0xffffu) : (s2 & 0xffu), ndn = WIDE ? (s2 >> 16) : ((s2 >> 8) & 0xffu);
-            const uint32_t up_idx = WIDE ? (st2[i][j] & 0xffffu) : ((s2 >> 16) & 0xffu);
-            const uint32_t dn_idx = WIDE ? (st2[i][j] >> 16) : ((s2 >> 24) & 0xffu);
-            unsigned long long key = 0;
-            bool emit = false;
-            if (ga < gb && gb < P.n_genes) {
-                if (nup == 1u) {
-                    if (ndn == C - 1u) {
-                        emit = true;
-                        key = (((unsigned long long)ga * P.n_genes + gb) << 16) | up_idx;
+            const uint32_t nup = st[i][j] & 0xffffu;
+            if (ga0 + i < gb0 + j && gb0 + j < P.n_genes && (nup == 1u || nup == C - 1u)) cmask |= 1u << (i * TJ + j);
+        }
+    const int my_first = cmask ? atomicAdd(&s_total, __popc(cmask)) : 0;  // tickets of this thread's candidates
+    __syncthreads();  // (A)
+    const int total = s_total;
+    const int rounds = (total + CAND_PER_ROUND - 1) / CAND_PER_ROUND;
+
+    // =============================== sweep 2: num_neg of the candidates, CAND_PER_ROUND per replay of the stream
+    for (int r = 0; r < rounds; ++r) {
+        {
+            int t = my_first;
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j)
+                    if (cmask & (1u << (i * TJ + j))) {
+                        if (t / CAND_PER_ROUND == r)
+                            cand[t % CAND_PER_ROUND] = make_uint2((uint32_t)(la + i) | ((uint32_t)(tj * TJ + j) << 8), st[i][j]);
+                        ++t;
                     }
-                } else if (ndn == 1u) {
-                    if (nup == C - 1u) {
-                        emit = true;
-                        key = (((unsigned long long)gb * P.n_genes + ga) << 16) | dn_idx;
-                    }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PAIR_THREADS) : "memory");  // consumers only: the list is complete
+        const bool have = tid < min(CAND_PER_ROUND, total - r * CAND_PER_ROUND);
+        const uint2 me = have ? cand[tid] : make_uint2(0u, 0u);
+        const uint32_t ca = me.x & 0xffu, cb = me.x >> 8;
+        const uint32_t ca_off = (ca >> 6) * blk_words + (ca & 63), cb_off = 2u * blk_words + cb;
+        uint32_t neg = 0, ndn = 0, dn_idx = 0;
+        for (int c = 0; c < P.n_chunks; ++c, ++q) {
+            const int s = q % STAGES;
+            mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
+            const Chunk ch = P.chunks[c];
+            if (have) {
+                const uint32_t *sa = smem + (size_t)s * stage_words + ca_off;
+                const uint32_t *sb = smem + (size_t)s * stage_words + cb_off;
+                for (int w = 0; w < ch.n_words; ++w) {
+                    uint32_t lt = 0;
+                    for (int p = 0; p < B; ++p) lt = lop3_lt(sa[p * 64], sb[p * 64], lt);
+                    neg += __popc(lt);
+                    sa += B * 64;
+                    sb += B * 64;
                 }
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, emit);
-            if (m) {
-                unsigned long long base = 0;
-                if (lane == __ffs(m) - 1) base = atomicAdd(P.out_count, (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-                if (emit && pos < P.out_cap) P.out[pos] = key;
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+            if (ch.class_end >= 0) {  // `num_neg[i] >= thresholds[i]` of sandbag.py:188-190
+                if ((int64_t)neg >= (int64_t)__ldg(P.thr + ch.class_end)) {
+                    ++ndn;
+                    dn_idx = (uint32_t)ch.class_end;
+                }
+                neg = 0;
             }
         }
+        // decision of sandbag.py:192-197 + warp-aggregated compaction
+        const uint32_t nup = me.y & 0xffffu, up_idx = me.y >> 16;
+        const unsigned long long ga = (unsigned long long)(tile.x * TILE_A + (int)ca);
+        const unsigned long long gb = (unsigned long long)(tile.y * TILE_B + (int)cb);
+        unsigned long long key = 0;
+        bool emit = false;
+        if (have) {
+            if (nup == 1u) {
+                if (ndn == C - 1u) {
+                    emit = true;
+                    key = ((ga * P.n_genes + gb) << 16) | up_idx;
+                }
+            } else if (ndn == 1u) {
+                if (nup == C - 1u) {
+                    emit = true;
+                    key = ((gb * P.n_genes + ga) << 16) | dn_idx;
+                }
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, emit);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(P.out_count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+            if (emit && pos < P.out_cap) P.out[pos] = key;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PAIR_THREADS) : "memory");  // cand[] is rewritten by the next round
+    }
 }
 
 // per-class counters of selected pairs straight from the planes (one warp per probe pair)
@@ -491,10 +527,8 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     ctx->tm = pp_timings();
     ctx->launches = 0;
     int64_t total = 0;
-    bool wide = n_classes > 254;
     for (int k = 0; k < n_classes; ++k) {
         if (class_sizes[k] <= 0) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: class %d is empty", k);
-        if (class_sizes[k] > 65535) wide = true;
         total += class_sizes[k];
     }
     if (total != n_cells) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: class_sizes do not sum to n_cells");
@@ -638,13 +672,11 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
 
     // ---- chunks (runs of <= wc_max words inside one class)
-    const int wide_bytes = wide ? 16 * 2 * 512 * 4 : 0;  // 32-bit counters of the WIDE kernel
-    const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 2048 - wide_bytes;
+    const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 8192;  // static: barriers + candidate list
     int wc_max = smem_budget / (STAGES * 3 * B * 64 * 4);
     wc_max = std::max(1, std::min(wc_max, 16));
-    const size_t dyn_smem = (size_t)STAGES * 3 * wc_max * B * 64 * 4 + wide_bytes;
+    const size_t dyn_smem = (size_t)STAGES * 3 * wc_max * B * 64 * 4;
     std::vector<Chunk> chunks;
-    int since_flush = 0;
     for (int k = 0; k < n_classes; ++k)
         for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc_max) {
             Chunk c;
@@ -652,13 +684,6 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             c.n_words = std::min(wc_max, class_w0[k + 1] - w);
             c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
             c.flush = 0;
-            since_flush += c.n_words;
-            if (c.class_end >= 0) {
-                since_flush = 0;
-            } else if (since_flush + wc_max > 2047) {  // the next chunk could overflow a 16-bit counter
-                c.flush = 1;
-                since_flush = 0;
-            }
             chunks.push_back(c);
         }
     // ---- tiles of this shard: (ta, tb) with tb >= 2*ta (only those contain pairs g1 < g2)
@@ -696,8 +721,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                                                                      std::max<int64_t>(1 << 22, n_pairs_shard / 16));
     unsigned long long count = 0;
     // 4x4 register tiles, 512 threads (16 warps/SM): measured 75.0 ms on cfg3 vs 87.8 ms for 8x4 / 256 threads
-    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     for (int attempt = 0; attempt < 2; ++attempt) {
         PP_CUDA(d_out.alloc(sizeof(unsigned long long) * cap, st));
         PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
@@ -716,10 +740,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             P.n_chunks = (int)chunks.size();
             P.n_classes = n_classes;
             P.wc_max = wc_max;
-            if (wide)
-                pair_kernel<4, 4, true><<<(unsigned)tiles.size(), 512 + 32, dyn_smem, st>>>(P);
-            else
-                pair_kernel<4, 4, false><<<(unsigned)tiles.size(), 512 + 32, dyn_smem, st>>>(P);
+            pair_kernel<4, 4><<<(unsigned)tiles.size(), 512 + 32, dyn_smem, st>>>(P);
             PP_CHECK_LAUNCH();
         }
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
