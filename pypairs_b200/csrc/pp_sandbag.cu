@@ -66,7 +66,12 @@ bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes,
 // ------------------------------------------------------------------------------------------
 // pair kernel
 // ------------------------------------------------------------------------------------------
-constexpr int TILE_A = 128;  // a-genes per CTA = 2 gene blocks
+#ifndef PP_TILE_A
+#define PP_TILE_A 128
+#endif
+constexpr int TILE_A = PP_TILE_A;     // a-genes per CTA = 1 or 2 gene blocks
+constexpr int A_BLOCKS = TILE_A / 64;
+constexpr int CTAS_PER_SM = TILE_A == 64 ? 2 : 1;  // 64 x 64 tiles: two CTAs share an SM, one can be in sweep 2
 constexpr int TILE_B = 64;   // b-genes per CTA = 1 gene block
 constexpr int STAGES = 3;
 
@@ -97,6 +102,7 @@ struct PairParams {
     const Chunk *chunks;
     const int2 *tiles;       // (ta, tb) per CTA
     const int32_t *thr;      // per class, clipped to int32
+    const int32_t *max_pos_dn;  // per class n_k - thr_k: num_neg >= thr_k needs num_pos <= this
     unsigned long long *out; // compacted (key << 16 | class)
     unsigned long long *out_count;
     unsigned long long out_cap;
@@ -106,7 +112,9 @@ struct PairParams {
 // Two sweeps over the cell words of a 128 x 64 gene tile, one kernel.
 //  Sweep 1 (all pairs): only num_pos = #(x[g1] > x[g2]) is accumulated -- ONE LOP3 per plane per pair and word -- and
 //     thresholded per class (nup, up_idx).  The decision of sandbag.py:192-197 can only emit when nup == 1 or
-//     nup == C-1, whatever num_neg is; on expression data that is ~1-2 % of the pairs ("candidates").
+//     nup == C-1; and since num_pos + num_neg <= n_k, a class can only count as "down" if num_pos <= n_k - thr_k
+//     (ncd = number of such classes): emitting needs ncd >= C-1 (first branch) or ncd >= 1 (second).  Pairs passing
+//     these necessary conditions are the "candidates" -- well under 1 % of the pairs on expression data.
 //  Sweep 2 (candidates only, 512 per round = one per consumer thread): the same operand stream is replayed and
 //     num_neg = #(x[g1] < x[g2]) is accumulated for the candidates, thresholded (ndn, dn_idx), and the decision emits.
 // So the second predicate of sandbag.py:179-182 is evaluated exactly where it can matter, halving the LOP3 work.
@@ -116,10 +124,11 @@ struct PairParams {
 // Warps 0 .. 15 consume; one extra warp is the TMA producer.  full[s] (1 arrival + transaction bytes) hands a stage to
 // the consumers, empty[s] (one arrival per consumer warp) hands it back, so the consumer warps never meet at a CTA-wide
 // barrier inside a sweep and drift up to STAGES-1 chunks apart.
-constexpr int CAND_PER_ROUND = 512;
+constexpr int CAND_PER_ROUND = (TILE_A / 4) * (TILE_B / 4);  // = consumer threads
 
-template <int TI, int TJ>
-__global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_kernel(const PairParams P) {
+// BP = number of bit planes when known at compile time (plane loops fully unrolled), 0 = run-time P.n_planes.
+template <int TI, int TJ, int BP>
+__global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_SM) pair_kernel(const PairParams P) {
     constexpr int NTJ = TILE_B / TJ;
     constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;  // consumer threads
     constexpr int CONSUMER_WARPS = PAIR_THREADS / 32;
@@ -130,13 +139,15 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ uint2 cand[CAND_PER_ROUND];  // .x = la | lb << 8 (tile-local genes), .y = nup | up_idx << 16
     __shared__ int s_total;
+    constexpr int CHUNK_CACHE = 192;         // chunk descriptors kept in shared memory (global beyond that)
+    __shared__ Chunk s_chunks[CHUNK_CACHE];
 
     const int tid = threadIdx.x;
     const int ti = tid / NTJ, tj = tid % NTJ;
     const int2 tile = P.tiles[blockIdx.x];
-    const int B = P.n_planes;
+    const int B = BP > 0 ? BP : P.n_planes;
     const int blk_words = P.wc_max * B * 64;  // u32 per gene block per stage
-    const uint32_t stage_words = 3u * blk_words;
+    const uint32_t stage_words = (uint32_t)(A_BLOCKS + 1) * blk_words;
     uint32_t *smem = reinterpret_cast<uint32_t *>(smem_raw);
 
     if (tid == 0) {
@@ -147,10 +158,12 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
         fence_mbar_init();
         s_total = 0;
     }
+    for (int c = tid; c < min(P.n_chunks, CHUNK_CACHE); c += blockDim.x) s_chunks[c] = P.chunks[c];
     __syncthreads();
+    auto chunk_at = [&](int c) -> Chunk { return c < CHUNK_CACHE ? s_chunks[c] : P.chunks[c]; };
 
     const int64_t blk_stride = (int64_t)P.n_words * B * 64;  // u32 per gene block in HBM
-    const uint32_t *gA0 = P.planes + (int64_t)(2 * tile.x) * blk_stride;
+    const uint32_t *gA0 = P.planes + (int64_t)(A_BLOCKS * tile.x) * blk_stride;
     const uint32_t *gA1 = gA0 + blk_stride;
     const uint32_t *gB = P.planes + (int64_t)tile.y * blk_stride;
 
@@ -160,14 +173,14 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
             for (int c = 0; c < P.n_chunks; ++c, ++q) {
                 const int s = q % STAGES;
                 if (q >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(q / STAGES - 1) & 1u);  // consumers released it
-                const Chunk ch = P.chunks[c];
+                const Chunk ch = chunk_at(c);
                 uint32_t *dst = smem + (size_t)s * stage_words;
                 const uint32_t bytes = (uint32_t)ch.n_words * B * 64 * 4;
                 const int64_t off = (int64_t)ch.w_begin * B * 64;
-                mbar_arrive_expect_tx(&full_bar[s], 3 * bytes);
+                mbar_arrive_expect_tx(&full_bar[s], (A_BLOCKS + 1) * bytes);
                 bulk_g2s(dst, gA0 + off, bytes, &full_bar[s]);
-                bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
-                bulk_g2s(dst + 2 * blk_words, gB + off, bytes, &full_bar[s]);
+                if (A_BLOCKS == 2) bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
+                bulk_g2s(dst + A_BLOCKS * blk_words, gB + off, bytes, &full_bar[s]);
             }
         };
         if (tid == PAIR_THREADS) stream_sweep();
@@ -179,21 +192,21 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
     }
 
     // =============================== sweep 1: num_pos of every pair of the tile
-    uint32_t acc[TI][TJ], st[TI][TJ];
+    uint32_t acc[TI][TJ], st[TI][TJ], ncd[TI][TJ];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) acc[i][j] = 0, st[i][j] = 0;
+        for (int j = 0; j < TJ; ++j) acc[i][j] = 0, st[i][j] = 0, ncd[i][j] = 0;
 
     const int la = ti * TI;  // first local a-gene (0..127), never straddles a 64-gene block
     const uint32_t a_off = (uint32_t)(la >> 6) * blk_words + (la & 63);
-    const uint32_t b_off = 2u * blk_words + tj * TJ;
+    const uint32_t b_off = (uint32_t)A_BLOCKS * blk_words + tj * TJ;
     int q = 0;
 
     for (int c = 0; c < P.n_chunks; ++c, ++q) {
         const int s = q % STAGES;
+        const Chunk ch = chunk_at(c);
         mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
-        const Chunk ch = P.chunks[c];
         const uint32_t *sa = smem + (size_t)s * stage_words + a_off;
         const uint32_t *sb = smem + (size_t)s * stage_words + b_off;
         for (int w = 0; w < ch.n_words; ++w) {
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
 #pragma unroll
                     for (int j = 0; j < TJ; ++j) gt[i][j] = a[i] & ~b[j];
             }
-#pragma unroll 4
+#pragma unroll(BP > 0 ? 16 : 4)
             for (int p = 1; p < B; ++p) {
                 uint32_t a[TI], b[TJ];
                 load_words<TI>(sa + p * 64, a);
@@ -228,12 +241,13 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
         if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
         if (ch.class_end >= 0) {  // CTA-uniform: `num_pos[i] >= thresholds[i]` of sandbag.py:185-187, last class wins
             const uint32_t k = (uint32_t)ch.class_end;
-            const int64_t thr = (int64_t)__ldg(P.thr + k);
+            const int64_t thr = (int64_t)__ldg(P.thr + k), mpd = (int64_t)__ldg(P.max_pos_dn + k);
 #pragma unroll
             for (int i = 0; i < TI; ++i)
 #pragma unroll
                 for (int j = 0; j < TJ; ++j) {
                     if ((int64_t)acc[i][j] >= thr) st[i][j] = ((st[i][j] & 0xffffu) + 1u) | (k << 16);
+                    if ((int64_t)acc[i][j] <= mpd) ncd[i][j] += 1u;
                     acc[i][j] = 0;
                 }
         }
@@ -249,7 +263,8 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
 #pragma unroll
         for (int j = 0; j < TJ; ++j) {
             const uint32_t nup = st[i][j] & 0xffffu;
-            if (ga0 + i < gb0 + j && gb0 + j < P.n_genes && (nup == 1u || nup == C - 1u)) cmask |= 1u << (i * TJ + j);
+            const bool can = (nup == 1u) ? (ncd[i][j] >= C - 1u) : (nup == C - 1u && ncd[i][j] >= 1u);
+            if (ga0 + i < gb0 + j && gb0 + j < P.n_genes && can) cmask |= 1u << (i * TJ + j);
         }
     const int my_first = cmask ? atomicAdd(&s_total, __popc(cmask)) : 0;  // tickets of this thread's candidates
     __syncthreads();  // (A)
@@ -274,12 +289,12 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, 1) pair_ke
         const bool have = tid < min(CAND_PER_ROUND, total - r * CAND_PER_ROUND);
         const uint2 me = have ? cand[tid] : make_uint2(0u, 0u);
         const uint32_t ca = me.x & 0xffu, cb = me.x >> 8;
-        const uint32_t ca_off = (ca >> 6) * blk_words + (ca & 63), cb_off = 2u * blk_words + cb;
+        const uint32_t ca_off = (ca >> 6) * blk_words + (ca & 63), cb_off = (uint32_t)A_BLOCKS * blk_words + cb;
         uint32_t neg = 0, ndn = 0, dn_idx = 0;
         for (int c = 0; c < P.n_chunks; ++c, ++q) {
             const int s = q % STAGES;
+            const Chunk ch = chunk_at(c);
             mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
-            const Chunk ch = P.chunks[c];
             if (have) {
                 const uint32_t *sa = smem + (size_t)s * stage_words + ca_off;
                 const uint32_t *sb = smem + (size_t)s * stage_words + cb_off;
@@ -673,9 +688,9 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
 
     // ---- chunks (runs of <= wc_max words inside one class)
     const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 8192;  // static: barriers + candidate list
-    int wc_max = smem_budget / (STAGES * 3 * B * 64 * 4);
+    int wc_max = (smem_budget / CTAS_PER_SM - (CTAS_PER_SM > 1 ? 6144 : 0)) / (STAGES * (A_BLOCKS + 1) * B * 64 * 4);
     wc_max = std::max(1, std::min(wc_max, 16));
-    const size_t dyn_smem = (size_t)STAGES * 3 * wc_max * B * 64 * 4;
+    const size_t dyn_smem = (size_t)STAGES * (A_BLOCKS + 1) * wc_max * B * 64 * 4;
     std::vector<Chunk> chunks;
     for (int k = 0; k < n_classes; ++k)
         for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc_max) {
@@ -686,18 +701,18 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             c.flush = 0;
             chunks.push_back(c);
         }
-    // ---- tiles of this shard: (ta, tb) with tb >= 2*ta (only those contain pairs g1 < g2)
+    // ---- tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain pairs g1 < g2)
     const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB;
     std::vector<int2> tiles;
     int64_t t_index = 0, n_pairs_shard = 0;
     // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
     // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
     // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
-    constexpr int SUP_A = 8, SUP_B = 18;
+    constexpr int SUP_A = 8 * (128 / TILE_A), SUP_B = 18;
     for (int sa = 0; sa < TA; sa += SUP_A)
-        for (int sb = 2 * sa; sb < TB; sb += SUP_B)
+        for (int sb = A_BLOCKS * sa; sb < TB; sb += SUP_B)
             for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
-                for (int tb = std::max(sb, 2 * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
+                for (int tb = std::max(sb, A_BLOCKS * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
                     if (t_index % n_shards != shard) continue;
                     tiles.push_back(make_int2(ta, tb));
                     const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
@@ -705,9 +720,11 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                     for (int64_t a = a0; a < a1; ++a) n_pairs_shard += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
                 }
     ctx->tm.n_units = n_pairs_shard;
-    std::vector<int32_t> thr32(n_classes);
-    for (int k = 0; k < n_classes; ++k)
+    std::vector<int32_t> thr32(n_classes), mpd32(n_classes);
+    for (int k = 0; k < n_classes; ++k) {
         thr32[k] = (int32_t)std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, thresholds[k]));
+        mpd32[k] = (int32_t)std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, class_sizes[k] - thresholds[k]));
+    }
 
     PP_CUDA(d_chunks.alloc(sizeof(Chunk) * chunks.size(), st));
     PP_CUDA(cudaMemcpyAsync(d_chunks.p, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, st));
@@ -715,13 +732,24 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st));
     PP_CUDA(d_thr.alloc(sizeof(int32_t) * n_classes, st));
     PP_CUDA(cudaMemcpyAsync(d_thr.p, thr32.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
+    DevBuf d_mpd;
+    PP_CUDA(d_mpd.alloc(sizeof(int32_t) * n_classes, st));
+    PP_CUDA(cudaMemcpyAsync(d_mpd.p, mpd32.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
     PP_CUDA(d_cnt.alloc(sizeof(unsigned long long), st));
 
     unsigned long long cap = (unsigned long long)std::min<int64_t>(std::max<int64_t>(n_pairs_shard, 1),
                                                                      std::max<int64_t>(1 << 22, n_pairs_shard / 16));
     unsigned long long count = 0;
     // 4x4 register tiles, 512 threads (16 warps/SM): measured 75.0 ms on cfg3 vs 87.8 ms for 8x4 / 256 threads
-    PP_CUDA(cudaFuncSetAttribute(pair_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    // plane count known at compile time for 1..16 (fully unrolled plane loops)
+    typedef void (*PairFn)(const PairParams);
+    static const PairFn pair_fns[17] = {
+        pair_kernel<4, 4, 0>,  pair_kernel<4, 4, 1>,  pair_kernel<4, 4, 2>,  pair_kernel<4, 4, 3>,  pair_kernel<4, 4, 4>,
+        pair_kernel<4, 4, 5>,  pair_kernel<4, 4, 6>,  pair_kernel<4, 4, 7>,  pair_kernel<4, 4, 8>,  pair_kernel<4, 4, 9>,
+        pair_kernel<4, 4, 10>, pair_kernel<4, 4, 11>, pair_kernel<4, 4, 12>, pair_kernel<4, 4, 13>, pair_kernel<4, 4, 14>,
+        pair_kernel<4, 4, 15>, pair_kernel<4, 4, 16>};
+    const PairFn pair_fn = pair_fns[B <= 16 ? B : 0];
+    PP_CUDA(cudaFuncSetAttribute(pair_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     for (int attempt = 0; attempt < 2; ++attempt) {
         PP_CUDA(d_out.alloc(sizeof(unsigned long long) * cap, st));
         PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
@@ -731,6 +759,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             P.chunks = d_chunks.as<Chunk>();
             P.tiles = d_tiles.as<int2>();
             P.thr = d_thr.as<int32_t>();
+            P.max_pos_dn = d_mpd.as<int32_t>();
             P.out = d_out.as<unsigned long long>();
             P.out_count = d_cnt.as<unsigned long long>();
             P.out_cap = cap;
@@ -740,12 +769,13 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             P.n_chunks = (int)chunks.size();
             P.n_classes = n_classes;
             P.wc_max = wc_max;
-            pair_kernel<4, 4><<<(unsigned)tiles.size(), 512 + 32, dyn_smem, st>>>(P);
+            pair_fn<<<(unsigned)tiles.size(), CAND_PER_ROUND + 32, dyn_smem, st>>>(P);
             PP_CHECK_LAUNCH();
         }
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
         PP_CUDA(cudaMemcpyAsync(&count, d_cnt.p, sizeof(count), cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
+
         if (count <= cap) break;
         if (attempt == 1) return pp_fail(ctx, PP_ECUDA, "pp_sandbag: compaction buffer overflow after resize");
         cap = count;  // exact size known now; evaluate once more
