@@ -76,6 +76,7 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int b = 0; b < 2; ++b)
         if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);

@@ -24,6 +24,8 @@ struct pp_ctx {
     cudaEvent_t ev[8] = {};
     void *pin[2] = {nullptr, nullptr};  // pinned staging buffers of the host-gather path (grown on demand)
     size_t pin_bytes = 0;
+    void *pin_out = nullptr;  // pinned staging buffer for results copied device -> host (grown on demand)
+    size_t pin_out_bytes = 0;
     std::string err;
     pp_timings tm = {};
     int launches = 0;

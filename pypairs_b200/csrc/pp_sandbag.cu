@@ -819,16 +819,27 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             free(hc);
             return pp_fail(ctx, PP_ENOMEM, "pp_sandbag: host allocation of %llu markers failed", count);
         }
-        cudaError_t e = cudaMemcpyAsync(hk, sorted, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, st);
+        // device -> pinned staging (a pageable destination would be staged by the driver at a fraction of the rate)
+        cudaError_t e = cudaSuccess;
+        if (ctx->pin_out_bytes < sizeof(uint64_t) * count) {
+            if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+            ctx->pin_out = nullptr;
+            ctx->pin_out_bytes = 0;
+            const size_t want = std::max<size_t>(sizeof(uint64_t) * count * 2, (size_t)8 << 20);
+            e = cudaHostAlloc(&ctx->pin_out, want, cudaHostAllocDefault);
+            if (e == cudaSuccess) ctx->pin_out_bytes = want;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->pin_out, sorted, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
             free(hk);
             free(hc);
             return pp_fail(ctx, PP_ECUDA, "pp_sandbag: result copy failed: %s", cudaGetErrorString(e));
         }
+        const uint64_t *packed = (const uint64_t *)ctx->pin_out;
         for (unsigned long long i = 0; i < count; ++i) {
-            hc[i] = (int32_t)(hk[i] & 0xffffu);
-            hk[i] >>= 16;
+            hc[i] = (int32_t)(packed[i] & 0xffffu);
+            hk[i] = packed[i] >> 16;
         }
     }
     PP_CUDA(cudaEventRecord(ctx->ev[4], st));
