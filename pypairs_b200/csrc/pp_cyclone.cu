@@ -239,6 +239,8 @@ struct ScoreParams {
     int iterations, min_iter, min_pairs;
     const ClassDesc *classes;
     uint32_t *gtile;    // !FAST only: [gridDim.x][n_union][32] scratch
+    const int32_t *class_order;  // classes by decreasing cost: work unit u = (class_order[u / n_tiles], tile u % n_tiles)
+    int *unit_counter;           // dynamic work-unit counter (zeroed before the launch)
     double *scores;     // [n_classes][n_cells]
     int32_t *obs_hits;  // [n_classes][n_cells]
     int32_t *obs_total;
@@ -386,6 +388,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
     extern __shared__ __align__(128) uint8_t smem_dyn[];
     __shared__ int s_obs[8][32];  // observed counters
     __shared__ uint32_t s_below[TILE_CELLS];
+    __shared__ int s_unit;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // FAST: [n_union][32] words in shared memory, followed by the per-warp staging buffers;
@@ -395,8 +398,16 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
     const uint64_t tile_lane = FAST ? (uint64_t)(smem_u32(tile) + lane * 4) : (uint64_t)(uintptr_t)(tile + lane);
     const int64_t n_tiles = (P.n_cells + TILE_CELLS - 1) / TILE_CELLS;
 
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int64_t cell0 = t * TILE_CELLS;
+    // Work units = (class, 64-cell tile), handed out dynamically, most expensive class first: equal-cost tiles would
+    // quantise the launch into whole waves (1 563 tiles on 148 SMs = 10.56 -> 11), units a third of that size don't.
+    const int64_t n_units = n_tiles * P.n_classes;
+    for (;;) {
+        if (tid == 0) s_unit = atomicAdd(P.unit_counter, 1);
+        __syncthreads();
+        const int64_t u = s_unit;
+        if (u >= n_units) break;
+        const int cls = P.class_order[u / n_tiles];
+        const int64_t cell0 = (u % n_tiles) * TILE_CELLS;
         const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
         // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
         {
@@ -413,7 +424,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
                 }
             }
         }
-        for (int cls = 0; cls < P.n_classes; ++cls) {
+        {
             const ClassDesc cd = P.classes[cls];
             const int s_all = cd.n_slots, s_b = (cd.n_chunks - cd.n_chunks_a) * CHUNK_SLOTS;
             if (tid < 32)
@@ -726,12 +737,27 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const int slow_grid = ctx->n_sm * 2;  // persistent CTAs, one global tile slab each
     if (!fast) PP_CUDA(d_gtile.alloc((size_t)slow_grid * U * 128, st));
     P.gtile = d_gtile.as<uint32_t>();
+    // classes by decreasing cost (slots) + the dynamic work-unit counter
+    DevBuf d_order, d_counter;
+    {
+        std::vector<int32_t> order(n_classes);
+        for (int c = 0; c < n_classes; ++c) order[c] = c;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cds[a].n_slots > cds[b].n_slots; });
+        PP_CUDA(d_order.alloc(sizeof(int32_t) * n_classes, st));
+        PP_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
+        PP_CUDA(d_counter.alloc(sizeof(int), st));
+        PP_CUDA(cudaStreamSynchronize(st));  // order is a local
+    }
+    P.class_order = d_order.as<int32_t>();
+    P.unit_counter = d_counter.as<int>();
     auto launch_score = [&](int64_t nc) {
-        const int64_t n_tiles = (nc + TILE_CELLS - 1) / TILE_CELLS;
+        const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes;
+        cudaMemsetAsync(d_counter.p, 0, sizeof(int), st);
+        const int64_t grid = std::min<int64_t>(n_units, fast ? ctx->n_sm : slow_grid);
         if (fast)
-            score_kernel<true><<<(unsigned)n_tiles, SCORE_THREADS, dyn_smem, st>>>(P);
+            score_kernel<true><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
         else
-            score_kernel<false><<<(unsigned)std::min<int64_t>(n_tiles, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
+            score_kernel<false><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
     };
     float score_ms = 0.f, copy_ms = 0.f;
     if (csr) {
