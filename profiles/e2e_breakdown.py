@@ -25,7 +25,8 @@ if which == "sandbag":
     gn = np.array(["g{}".format(i) for i in range(g)])
     sn = ["c{}".format(i) for i in range(n)]
     ann = {k: np.where(lab == i)[0] for i, k in enumerate(["G1", "S", "G2M"])}
-    call = lambda: pairs.sandbag(xh, ann, gn, sn, fraction=0.65)  # noqa: E731
+    as_table = len(sys.argv) > 2 and sys.argv[2] == "table"
+    call = lambda: pairs.sandbag(xh, ann, gn, sn, fraction=0.65, as_table=as_table)  # noqa: E731
 else:
     markers, names, keys, used_idx, pair_idx, _, _ = bench.cyclone_setup()
     gen = torch.Generator(device="cuda").manual_seed(1)

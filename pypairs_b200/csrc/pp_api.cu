@@ -18,6 +18,29 @@ int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+void *pp_slab(pp_ctx *ctx, int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->slab_bytes[slot] >= bytes) return ctx->slab[slot];
+    cudaStreamSynchronize(ctx->stream);  // nothing may still be using the old slab
+    if (ctx->slab[slot]) cudaFree(ctx->slab[slot]);
+    ctx->slab[slot] = nullptr;
+    ctx->slab_bytes[slot] = 0;
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ctx->slab[slot], want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&ctx->slab[slot], bytes);
+        if (e != cudaSuccess) {
+            pp_fail(ctx, PP_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            return nullptr;
+        }
+        ctx->slab_bytes[slot] = bytes;
+        return ctx->slab[slot];
+    }
+    ctx->slab_bytes[slot] = want;
+    return ctx->slab[slot];
+}
+
 PP_API int pp_version(void) { return PP_ABI_VERSION; }
 
 PP_API int pp_device_count(void) {
@@ -77,6 +100,8 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
     for (int b = 0; b < 2; ++b)
         if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    for (int i = 0; i < pp_ctx::N_SLABS; ++i)
+        if (ctx->slab[i]) cudaFree(ctx->slab[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);

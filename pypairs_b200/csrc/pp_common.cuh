@@ -26,6 +26,11 @@ struct pp_ctx {
     size_t pin_bytes = 0;
     void *pin_out = nullptr;  // pinned staging buffer for results copied device -> host (grown on demand)
     size_t pin_out_bytes = 0;
+    // grow-only device slabs for the few large buffers of a call (matrix copy, rank matrix, bit planes, ...): calls
+    // are synchronous, so the same slab is safely re-used by the next call and the allocator is out of the timed path
+    static constexpr int N_SLABS = 10;
+    void *slab[N_SLABS] = {};
+    size_t slab_bytes[N_SLABS] = {};
     std::string err;
     pp_timings tm = {};
     int launches = 0;
@@ -34,6 +39,9 @@ struct pp_ctx {
 extern thread_local std::string g_pp_err;  // errors raised without a ctx
 
 int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...);
+// pointer to at least `bytes` of device memory in slab `slot` (contents undefined); nullptr + error on failure
+void *pp_slab(pp_ctx *ctx, int slot, size_t bytes);
+enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, SLAB_CHUNK0 = 5, SLAB_CHUNK1 = 6, SLAB_MISC = 7, SLAB_SORT = 8 };
 
 #define PP_CUDA(call)                                                                              \
     do {                                                                                           \

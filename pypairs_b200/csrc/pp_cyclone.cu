@@ -630,7 +630,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     cudaStream_t st = ctx->stream;
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
     const size_t esz = x_dtype == PP_F64 ? 8 : 4;
-    DevBuf d_x, d_rows, d_uni, d_rank, d_flags, d_scores, d_oh, d_ot, d_cd;
+    DevBuf d_rows, d_uni, d_flags, d_scores, d_oh, d_ot, d_cd;
+    void *s_rank = nullptr;  // ctx slab
     const uint8_t *x0 = csr ? nullptr : (const uint8_t *)x + (size_t)row_begin * ld * esz;
     // Host input is streamed in chunks of one full wave of 64-cell tiles: H2D of chunk i+1 (copy stream)
     // overlaps rank + score of chunk i (compute stream).  When the marker genes are at most a quarter of the
@@ -654,7 +655,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(d_uni.alloc(sizeof(int32_t) * U, st));
     PP_CUDA(cudaMemcpyAsync(d_uni.p, uni.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, st));
     const int64_t rank_ld = (U + 7) & ~7;
-    PP_CUDA(d_rank.alloc(sizeof(uint16_t) * n_cells * rank_ld, st));
+    if (!(s_rank = pp_slab(ctx, SLAB_RANK, sizeof(uint16_t) * n_cells * rank_ld))) return PP_ENOMEM;
     PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
     PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
     int rc = PP_OK;
@@ -733,10 +734,9 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
     P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
     PP_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    DevBuf d_gtile;
     const int slow_grid = ctx->n_sm * 2;  // persistent CTAs, one global tile slab each
-    if (!fast) PP_CUDA(d_gtile.alloc((size_t)slow_grid * U * 128, st));
-    P.gtile = d_gtile.as<uint32_t>();
+    P.gtile = nullptr;
+    if (!fast && !(P.gtile = (uint32_t *)pp_slab(ctx, SLAB_MISC, (size_t)slow_grid * U * 128))) return PP_ENOMEM;
     // classes by decreasing cost (slots) + the dynamic work-unit counter
     DevBuf d_order, d_counter;
     {
@@ -774,47 +774,49 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             ident[j] = j;
         }
         for (int64_t i = 0; i < n_cells; ++i) allrows[i] = (int32_t)i;
-        DevBuf d_colmap, d_ident, d_allrows, d_dense;
+        DevBuf d_colmap, d_ident, d_allrows;
+        void *s_dense = pp_slab(ctx, SLAB_CHUNK0, (size_t)chunk_cells * U * esz);
+        if (!s_dense) return PP_ENOMEM;
         PP_CUDA(d_colmap.alloc(sizeof(int32_t) * n_cols, st));
         PP_CUDA(cudaMemcpyAsync(d_colmap.p, colmap.data(), sizeof(int32_t) * n_cols, cudaMemcpyHostToDevice, st));
         PP_CUDA(d_ident.alloc(sizeof(int32_t) * U, st));
         PP_CUDA(cudaMemcpyAsync(d_ident.p, ident.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, st));
         PP_CUDA(d_allrows.alloc(sizeof(int32_t) * n_cells, st));
         PP_CUDA(cudaMemcpyAsync(d_allrows.p, allrows.data(), sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, st));
-        PP_CUDA(d_dense.alloc((size_t)chunk_cells * U * esz, st));
         PP_CUDA(cudaStreamSynchronize(st));  // colmap / ident / allrows are locals
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
         for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells) {
             const int64_t nc = std::min(chunk_cells, n_cells - c0);
-            PP_CUDA(cudaMemsetAsync(d_dense.p, 0, (size_t)nc * U * esz, st));
-            rc = pp_csr_densify(ctx, dcsr, d_allrows.as<int32_t>() + c0, nc, d_colmap.as<int32_t>(), d_dense.p, U);
+            PP_CUDA(cudaMemsetAsync(s_dense, 0, (size_t)nc * U * esz, st));
+            rc = pp_csr_densify(ctx, dcsr, d_allrows.as<int32_t>() + c0, nc, d_colmap.as<int32_t>(), s_dense, U);
             if (rc) return rc;
-            rc = pp_rank_launch(ctx, d_dense.p, x_dtype, U, d_rows.as<int32_t>(), nc, d_ident.as<int32_t>(), U,
-                                d_rank.as<uint16_t>() + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            rc = pp_rank_launch(ctx, s_dense, x_dtype, U, d_rows.as<int32_t>(), nc, d_ident.as<int32_t>(), U,
+                                (uint16_t *)s_rank + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
             if (rc) return rc;
-            P.rank = d_rank.as<uint16_t>() + c0 * rank_ld;
+            P.rank = (uint16_t *)s_rank + c0 * rank_ld;
             P.n_cells = nc;
             P.out_off = c0;
             launch_score(nc);
             PP_CHECK_LAUNCH();
         }
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
-        PP_CUDA(cudaStreamSynchronize(st));  // d_dense and dcsr go out of scope
+        PP_CUDA(cudaStreamSynchronize(st));  // dcsr goes out of scope
     } else if (!pipelined) {
         const void *dx = x0;
         if (!x_is_device) {
-            PP_CUDA(d_x.alloc((size_t)n_cells * ld * esz, st));
+            void *s_x = pp_slab(ctx, SLAB_X, (size_t)n_cells * ld * esz);
+            if (!s_x) return PP_ENOMEM;
             PP_CUDA(cudaEventRecord(ctx->ev[6], st));
-            PP_CUDA(cudaMemcpyAsync(d_x.p, x0, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
+            PP_CUDA(cudaMemcpyAsync(s_x, x0, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
             ctx->tm.h2d_bytes += (int64_t)((size_t)n_cells * ld * esz);
             PP_CUDA(cudaEventRecord(ctx->ev[7], st));
-            dx = d_x.p;
+            dx = s_x;
         }
         rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_uni.as<int32_t>(), U,
-                            d_rank.as<uint16_t>(), rank_ld, d_flags.as<int32_t>());
+                            (uint16_t *)s_rank, rank_ld, d_flags.as<int32_t>());
         if (rc) return rc;
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
-        P.rank = d_rank.as<uint16_t>();
+        P.rank = (uint16_t *)s_rank;
         P.n_cells = n_cells;
         P.out_off = 0;
         launch_score(n_cells);
@@ -828,7 +830,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         // alternating both at once 184 ms -- all three move ~40 GB/s through host DRAM, which is the bound, so the
         // path that touches the fewest host bytes (G, when the markers are <= 1/4 of the columns) is used alone.
         struct Lane {
-            DevBuf buf[2];
+            void *buf[2] = {nullptr, nullptr};  // ctx slabs
             cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
             int used = 0;
             cudaStream_t cs = nullptr;
@@ -870,7 +872,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         for (Lane *L : {&G, &D}) {
             if (!L->cs) continue;
             for (int b = 0; b < 2; ++b) {
-                PP_CUDA(L->buf[b].alloc((size_t)chunk_cells * L->ldv * esz, st));
+                if (!(L->buf[b] = pp_slab(ctx, b == 0 ? SLAB_CHUNK0 : SLAB_CHUNK1, (size_t)chunk_cells * L->ldv * esz)))
+                    return PP_ENOMEM;
                 PP_CUDA(cudaEventCreateWithFlags(&L->copied[b], cudaEventDisableTiming));
                 PP_CUDA(cudaEventCreateWithFlags(&L->freed[b], cudaEventDisableTiming));
             }
@@ -895,7 +898,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 src = ctx->pin[b];
             }
             if (L.used >= 2) PP_CUDA(cudaStreamWaitEvent(L.cs, L.freed[b], 0));  // rank kernel two chunks ago is done
-            PP_CUDA(cudaMemcpyAsync(L.buf[b].p, src, (size_t)nc * L.ldv * esz, cudaMemcpyHostToDevice, L.cs));
+            PP_CUDA(cudaMemcpyAsync(L.buf[b], src, (size_t)nc * L.ldv * esz, cudaMemcpyHostToDevice, L.cs));
             ctx->tm.h2d_bytes += (int64_t)((size_t)nc * L.ldv * esz);
             PP_CUDA(cudaEventRecord(L.copied[b], L.cs));
             L.used++;
@@ -905,8 +908,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         auto compute = [&](const Pending &p) -> int {
             Lane &L = *p.L;
             PP_CUDA(cudaStreamWaitEvent(st, L.copied[p.slot], 0));
-            int r = pp_rank_launch(ctx, L.buf[p.slot].p, x_dtype, L.ldv, d_rows.as<int32_t>(), p.nc, L.cols, U,
-                                   d_rank.as<uint16_t>() + p.c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            int r = pp_rank_launch(ctx, L.buf[p.slot], x_dtype, L.ldv, d_rows.as<int32_t>(), p.nc, L.cols, U,
+                                   (uint16_t *)s_rank + p.c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
             if (r) return r;
             PP_CUDA(cudaEventRecord(L.freed[p.slot], st));
             cudaEvent_t e0, e1;
@@ -914,7 +917,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             PP_CUDA(cudaEventCreate(&e1));
             ev_s.push_back(e0);
             ev_s.push_back(e1);
-            P.rank = d_rank.as<uint16_t>() + p.c0 * rank_ld;
+            P.rank = (uint16_t *)s_rank + p.c0 * rank_ld;
             P.n_cells = p.nc;
             P.out_off = p.c0;
             PP_CUDA(cudaEventRecord(e0, st));

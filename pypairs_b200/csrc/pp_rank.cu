@@ -277,19 +277,19 @@ int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const 
     const size_t n_al = ((size_t)n_genes + 15) & ~(size_t)15;
     const size_t per_cta = 2 * n_al * ksz + 2 * n_al * 2;
     int grid = (int)((n_slots < (int64_t)ctx->n_sm * 3) ? n_slots : (int64_t)ctx->n_sm * 3);
-    DevBuf scratch;
-    PP_CUDA(scratch.alloc(per_cta * (size_t)grid, ctx->stream));
+    uint8_t *scratch = (uint8_t *)pp_slab(ctx, SLAB_SORT, per_cta * (size_t)grid);  // sort path only; stream-ordered reuse
+    if (!scratch) return PP_ENOMEM;
     const size_t dyn = ((size_t)n_genes * 2 + 15) & ~(size_t)15;
     PP_CUDA(cudaFuncSetAttribute(rank_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     PP_CUDA(cudaFuncSetAttribute(rank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     if (x_dtype == PP_F64)
         rank_kernel<double><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
             (const double *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
-            scratch.as<uint8_t>(), per_cta, d_flags);
+            scratch, per_cta, d_flags);
     else
         rank_kernel<float><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
             (const float *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
-            scratch.as<uint8_t>(), per_cta, d_flags);
+            scratch, per_cta, d_flags);
     PP_CHECK_LAUNCH();
     return PP_OK;
 }

@@ -559,7 +559,8 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
-    DevBuf d_x, d_slots, d_gene, d_rank, d_flags, d_planes, d_chunks, d_tiles, d_thr, d_out, d_out2, d_cnt;
+    DevBuf d_slots, d_gene, d_flags, d_chunks, d_tiles, d_thr, d_cnt;
+    void *s_x = nullptr, *s_rank = nullptr, *s_planes = nullptr, *s_out = nullptr, *s_out2 = nullptr;  // ctx slabs
     const size_t esz = x_dtype == PP_F64 ? 8 : 4;
     const void *dx = x;
     DevCsr dcsr;
@@ -568,10 +569,10 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         rc = pp_csr_to_device(ctx, csr, 0, n_rows, &dcsr);
         if (rc) return rc;
     } else if (!x_is_device) {
-        PP_CUDA(d_x.alloc((size_t)n_rows * ld * esz, st));
-        PP_CUDA(cudaMemcpyAsync(d_x.p, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
+        if (!(s_x = pp_slab(ctx, SLAB_X, (size_t)n_rows * ld * esz))) return PP_ENOMEM;
+        PP_CUDA(cudaMemcpyAsync(s_x, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
         ctx->tm.h2d_bytes = (int64_t)((size_t)n_rows * ld * esz);
-        dx = d_x.p;
+        dx = s_x;
     }
     PP_CUDA(cudaEventRecord(ctx->ev[1], st));
 
@@ -629,7 +630,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
     PP_CUDA(d_gene.alloc(sizeof(int32_t) * n_genes, st));
     PP_CUDA(cudaMemcpyAsync(d_gene.p, gene_cols, sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
-    PP_CUDA(d_rank.alloc(sizeof(uint16_t) * n_slots * n_genes, st));
+    if (!(s_rank = pp_slab(ctx, SLAB_RANK, sizeof(uint16_t) * n_slots * n_genes))) return PP_ENOMEM;
     PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
     PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
 
@@ -658,30 +659,29 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             rc = pp_csr_densify(ctx, dcsr, d_slots.as<int32_t>() + s0, nl, d_colmap.as<int32_t>(), d_dense.p, n_genes);
             if (rc) return rc;
             rc = pp_rank_launch(ctx, d_dense.p, x_dtype, n_genes, d_loc.as<int32_t>() + s0, nl, d_ident.as<int32_t>(),
-                                n_genes, d_rank.as<uint16_t>() + s0 * n_genes, n_genes, d_flags.as<int32_t>());
+                                n_genes, (uint16_t *)s_rank + s0 * n_genes, n_genes, d_flags.as<int32_t>());
             if (rc) return rc;
         }
         PP_CUDA(cudaStreamSynchronize(st));  // colmap / ident / loc are locals
     } else {
         rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
-                            d_rank.as<uint16_t>(), n_genes, d_flags.as<int32_t>());
+                            (uint16_t *)s_rank, n_genes, d_flags.as<int32_t>());
         if (rc) return rc;
     }
     int32_t flags[4];
     PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaStreamSynchronize(st));
-    d_x.release();
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
     const int B = std::max(1, bit_length64((uint64_t)flags[0]));
     ctx->tm.n_planes = B;
 
     // ---- bit-slice
     const size_t plane_words = (size_t)NB_alloc * W * B * 64;
-    PP_CUDA(d_planes.alloc(plane_words * 4, st));
-    PP_CUDA(cudaMemsetAsync(d_planes.p, 0, plane_words * 4, st));
+    if (!(s_planes = pp_slab(ctx, SLAB_PLANES, plane_words * 4))) return PP_ENOMEM;
+    PP_CUDA(cudaMemsetAsync(s_planes, 0, plane_words * 4, st));
     {
         dim3 grid(W, (unsigned)((n_genes + 255) / 256));
-        bitslice_kernel<<<grid, 256, 0, st>>>(d_rank.as<uint16_t>(), n_genes, (int)n_genes, W, B, d_planes.as<uint32_t>());
+        bitslice_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_genes, (int)n_genes, W, B, (uint32_t *)s_planes);
         PP_CHECK_LAUNCH();
     }
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
@@ -751,16 +751,16 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const PairFn pair_fn = pair_fns[B <= 16 ? B : 0];
     PP_CUDA(cudaFuncSetAttribute(pair_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     for (int attempt = 0; attempt < 2; ++attempt) {
-        PP_CUDA(d_out.alloc(sizeof(unsigned long long) * cap, st));
+        if (!(s_out = pp_slab(ctx, SLAB_OUT, sizeof(unsigned long long) * cap))) return PP_ENOMEM;
         PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
         if (!tiles.empty()) {
             PairParams P;
-            P.planes = d_planes.as<uint32_t>();
+            P.planes = (uint32_t *)s_planes;
             P.chunks = d_chunks.as<Chunk>();
             P.tiles = d_tiles.as<int2>();
             P.thr = d_thr.as<int32_t>();
             P.max_pos_dn = d_mpd.as<int32_t>();
-            P.out = d_out.as<unsigned long long>();
+            P.out = (unsigned long long *)s_out;
             P.out_count = d_cnt.as<unsigned long long>();
             P.out_cap = cap;
             P.n_genes = (int)n_genes;
@@ -792,7 +792,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(d_pos.alloc(cb, st));
         PP_CUDA(d_neg.alloc(cb, st));
         PP_CUDA(cudaMemcpyAsync(d_pp.p, probe_pairs, sizeof(int64_t) * 2 * n_probe, cudaMemcpyHostToDevice, st));
-        probe_kernel<<<(unsigned)((n_probe + 3) / 4), 128, 0, st>>>(d_planes.as<uint32_t>(), d_chunks.as<Chunk>(),
+        probe_kernel<<<(unsigned)((n_probe + 3) / 4), 128, 0, st>>>((uint32_t *)s_planes, d_chunks.as<Chunk>(),
                                                                    (int)chunks.size(), W, B, n_classes,
                                                                    d_pp.as<int64_t>(), n_probe, d_pos.as<int32_t>(),
                                                                    d_neg.as<int32_t>());
@@ -806,10 +806,10 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     uint64_t *hk = nullptr;
     int32_t *hc = nullptr;
     if (count > 0) {
-        PP_CUDA(d_out2.alloc(sizeof(unsigned long long) * count, st));
+        if (!(s_out2 = pp_slab(ctx, SLAB_OUT2, sizeof(unsigned long long) * count))) return PP_ENOMEM;
         unsigned long long *sorted = nullptr;
         const int hi_bit = 16 + bit_length64((uint64_t)n_genes * (uint64_t)n_genes);
-        rc = radix_sort_u64(ctx, d_out.as<unsigned long long>(), d_out2.as<unsigned long long>(), (int64_t)count, 16,
+        rc = radix_sort_u64(ctx, (unsigned long long *)s_out, (unsigned long long *)s_out2, (int64_t)count, 16,
                             hi_bit, &sorted);
         if (rc) return rc;
         hk = (uint64_t *)malloc(sizeof(uint64_t) * count);
