@@ -209,33 +209,68 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_S
         mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
         const uint32_t *sa = smem + (size_t)s * stage_words + a_off;
         const uint32_t *sb = smem + (size_t)s * stage_words + b_off;
-        for (int w = 0; w < ch.n_words; ++w) {
-            uint32_t gt[TI][TJ];
-            {
-                uint32_t a[TI], b[TJ];
-                load_words<TI>(sa, a);
-                load_words<TJ>(sb, b);
+        if (BP > 0) {
+            // compile-time plane count: software-pipelined -- the operands of plane p+1 (or of plane 0 of the next
+            // word) are requested before the 16 LOP3 of plane p issue, so the LDS latency hides behind them
+            uint32_t a[TI], b[TJ];
+            load_words<TI>(sa, a);
+            load_words<TJ>(sb, b);
+            for (int w = 0; w < ch.n_words; ++w) {
+                uint32_t gt[TI][TJ];
+#pragma unroll
+                for (int p = 0; p < (BP > 0 ? BP : 1); ++p) {
+                    uint32_t an[TI], bn[TJ];
+                    const int nxt = (p + 1 < BP) ? (p + 1) * 64 : BP * 64;  // next plane, or plane 0 of the next word
+                    if (p + 1 < BP || w + 1 < ch.n_words) {
+                        load_words<TI>(sa + nxt, an);
+                        load_words<TJ>(sb + nxt, bn);
+                    }
+#pragma unroll
+                    for (int i = 0; i < TI; ++i)
+#pragma unroll
+                        for (int j = 0; j < TJ; ++j)
+                            gt[i][j] = (p == 0) ? (a[i] & ~b[j]) : lop3_gt(a[i], b[j], gt[i][j]);
+#pragma unroll
+                    for (int i = 0; i < TI; ++i) a[i] = an[i];
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) b[j] = bn[j];
+                }
 #pragma unroll
                 for (int i = 0; i < TI; ++i)
 #pragma unroll
-                    for (int j = 0; j < TJ; ++j) gt[i][j] = a[i] & ~b[j];
+                    for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
+                sa += BP * 64;
+                sb += BP * 64;
             }
-#pragma unroll(BP > 0 ? 16 : 4)
-            for (int p = 1; p < B; ++p) {
-                uint32_t a[TI], b[TJ];
-                load_words<TI>(sa + p * 64, a);
-                load_words<TJ>(sb + p * 64, b);
+        } else {
+            for (int w = 0; w < ch.n_words; ++w) {
+                uint32_t gt[TI][TJ];
+                {
+                    uint32_t a[TI], b[TJ];
+                    load_words<TI>(sa, a);
+                    load_words<TJ>(sb, b);
+#pragma unroll
+                    for (int i = 0; i < TI; ++i)
+#pragma unroll
+                        for (int j = 0; j < TJ; ++j) gt[i][j] = a[i] & ~b[j];
+                }
+#pragma unroll 4
+                for (int p = 1; p < B; ++p) {
+                    uint32_t a[TI], b[TJ];
+                    load_words<TI>(sa + p * 64, a);
+                    load_words<TJ>(sb + p * 64, b);
+#pragma unroll
+                    for (int i = 0; i < TI; ++i)
+#pragma unroll
+                        for (int j = 0; j < TJ; ++j) gt[i][j] = lop3_gt(a[i], b[j], gt[i][j]);
+                }
 #pragma unroll
                 for (int i = 0; i < TI; ++i)
 #pragma unroll
-                    for (int j = 0; j < TJ; ++j) gt[i][j] = lop3_gt(a[i], b[j], gt[i][j]);
+                    for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
+                sa += B * 64;
+                sb += B * 64;
             }
-#pragma unroll
-            for (int i = 0; i < TI; ++i)
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
-            sa += B * 64;
-            sb += B * 64;
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
