@@ -57,18 +57,17 @@ def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
         return {}
     k64 = np.ascontiguousarray(keys).view(np.int64)  # keys < 2^32: the signed view is exact and divides faster
     rows, cols = k64 // n_genes, k64 % n_genes
-    names = np.empty(len(gene_names), dtype=object)  # the np.str_ scalars `gene_names[g]` yields, made once
-    names[:] = list(gene_names)
+    names = list(gene_names)  # the np.str_ scalars `gene_names[g]` yields, made once
     # classes in order of first appearance in the scan: with repeated indices the last write wins, so writing
     # the positions in reverse leaves the smallest position of every class
     first = np.full(len(class_names), len(cls), dtype=np.int64)
     first[cls[::-1]] = np.arange(len(cls) - 1, -1, -1)
+    per_class = utils.pair_lists(names, rows, cols, cls, len(class_names))
     out = {}
     for k in np.argsort(first, kind="stable"):
         if first[k] == len(cls):
             break
-        m = cls == k
-        out[class_names[k]] = list(zip(names[rows[m]].tolist(), names[cols[m]].tolist()))
+        out[class_names[k]] = per_class[k]
     return out
 
 

@@ -16,6 +16,33 @@ except ImportError:  # pragma: no cover
     _AnnData = None
 
 
+try:  # optional C helper built by __graft_entry__.build(); pure-Python equivalents below
+    from ._pytuples import pair_list as _c_pair_list, pair_lists as _c_pair_lists
+except ImportError:  # pragma: no cover
+    _c_pair_list = _c_pair_lists = None
+
+
+def pair_lists(names, rows, cols, cls, n_classes):
+    """Per class k the list of (names[rows[i]], names[cols[i]]) over the entries with cls[i] == k, input order kept."""
+    names = names if isinstance(names, list) else list(names)
+    if _c_pair_lists is not None:
+        return _c_pair_lists(names, np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int64),
+                             np.ascontiguousarray(cls, dtype=np.int32), int(n_classes))
+    obj = np.empty(len(names), dtype=object)
+    obj[:] = names
+    cls = np.asarray(cls)
+    return [list(zip(obj[rows[cls == k]].tolist(), obj[cols[cls == k]].tolist())) for k in range(n_classes)]
+
+
+def pair_list(names, rows, cols):
+    """[(names[rows[i]], names[cols[i]]) ...] -- `names` is an object array / list of the gene-name scalars."""
+    if _c_pair_list is not None:
+        return _c_pair_list(names if isinstance(names, list) else names.tolist(),
+                            np.ascontiguousarray(rows, dtype=np.int64), np.ascontiguousarray(cols, dtype=np.int64))
+    names = np.asarray(names, dtype=object)
+    return list(zip(names[rows].tolist(), names[cols].tolist()))
+
+
 def is_anndata(data):
     if _AnnData is not None and isinstance(data, _AnnData):
         return True
@@ -239,10 +266,5 @@ class MarkerTable(object):
         return {self.class_names[k]: int(np.sum(self.cls == k)) for k in self.class_order()}
 
     def to_dict(self):
-        names = np.empty(len(self.gene_names), dtype=object)
-        names[:] = list(self.gene_names)
-        out = {}
-        for k in self.class_order():
-            m = self.cls == k
-            out[self.class_names[k]] = list(zip(names[self.rows[m]].tolist(), names[self.cols[m]].tolist()))
-        return out
+        per_class = pair_lists(list(self.gene_names), self.rows, self.cols, self.cls, len(self.class_names))
+        return {self.class_names[k]: per_class[k] for k in self.class_order()}
