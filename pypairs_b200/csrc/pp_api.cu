@@ -73,7 +73,6 @@ PP_API int pp_ctx_create(int device, pp_ctx **out) {
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) {
         // keep freed blocks in the pool: repeated calls re-use them instead of hitting the driver
@@ -104,7 +103,6 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
         if (ctx->slab[i]) cudaFree(ctx->slab[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
     delete ctx;
 }
 

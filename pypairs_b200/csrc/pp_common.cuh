@@ -20,7 +20,6 @@ struct pp_ctx {
     int smem_optin = 0;
     cudaStream_t stream = nullptr;   // compute stream
     cudaStream_t copy_stream = nullptr;  // H2D prefetch stream
-    cudaStream_t copy_stream2 = nullptr; // second H2D stream (full-row copies of the hybrid host path)
     cudaEvent_t ev[8] = {};
     void *pin[2] = {nullptr, nullptr};  // pinned staging buffers of the host-gather path (grown on demand)
     size_t pin_bytes = 0;

@@ -641,8 +641,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
     // (measured: with 16 host threads the gather beats full-row copies 161 vs 195 ms on cfg2; with 8 threads per
     // rank, 4 ranks sharing the host, it loses 402 vs 349 ms -- so it needs >= 12 threads for this process)
-    const bool host_gather = !csr && !x_is_device && (int64_t)U * 4 <= n_cols && host_threads() >= 12 &&
-                             !getenv("PP_NO_HOST_GATHER");
+    const bool host_gather = !csr && !x_is_device && (int64_t)U * 4 <= n_cols && host_threads() >= 12;
     const bool pipelined = !csr && !x_is_device && (n_cells > wave_cells || host_gather);
     const int64_t chunk_cells = (pipelined || csr) ? std::min(wave_cells, n_cells) : n_cells;
     {
@@ -823,27 +822,31 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CHECK_LAUNCH();
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
     } else {
-        // Two ways for a chunk of cells to reach the device (one double-buffered lane is used per call):
-        //   G (gather): host threads copy the marker columns into pinned staging, H2D of [nc, U]
-        //   D (direct): H2D of the full rows [nc, ld], columns picked by the rank kernel
-        // Measured on the B200 box (16 host cores, cfg2: 100k x 20k f32, 1 479 marker genes): D 195 ms, G 161 ms,
-        // alternating both at once 184 ms -- all three move ~40 GB/s through host DRAM, which is the bound, so the
-        // path that touches the fewest host bytes (G, when the markers are <= 1/4 of the columns) is used alone.
-        struct Lane {
-            void *buf[2] = {nullptr, nullptr};  // ctx slabs
-            cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-            int used = 0;
-            cudaStream_t cs = nullptr;
-            int64_t ldv = 0;
-            const int32_t *cols = nullptr;
-        } G, D;
-        DevBuf d_ident;
-        cudaEvent_t ev_c0, ev_c1;
+        // Two ways for a chunk of cells to reach the device, through one double-buffered lane:
+        //   gather: host threads copy the marker columns into pinned staging, H2D of [nc, U]
+        //   direct: H2D of the full rows [nc, ld], columns picked by the rank kernel
+        // Measured on the B200 box (16 host cores, cfg2: 100k x 20k f32, 1 479 marker genes): direct 195 ms, gather
+        // 161 ms, alternating both at once 184 ms -- all three move ~40-50 GB/s through host DRAM, which is the bound,
+        // so the way that touches the fewest host bytes is used alone.
+        struct Events {  // destroyed on every exit path
+            std::vector<cudaEvent_t> ev;
+            cudaError_t make(cudaEvent_t *e, unsigned flags) {
+                const cudaError_t rc = cudaEventCreateWithFlags(e, flags);
+                if (rc == cudaSuccess) ev.push_back(*e);
+                return rc;
+            }
+            ~Events() {
+                for (cudaEvent_t e : ev) cudaEventDestroy(e);
+            }
+        } events;
+        void *buf[2] = {nullptr, nullptr};  // device chunk buffers (ctx slabs)
+        cudaEvent_t copied[2], freed[2], ev_c0, ev_c1;
         std::vector<cudaEvent_t> ev_s;
+        DevBuf d_ident;
         const int n_thr = host_threads();
-        const int64_t n_chunks = (n_cells + chunk_cells - 1) / chunk_cells;
-        const bool hybrid = false;
-        const bool use_d = !host_gather;
+        const int64_t dev_ld = host_gather ? U : ld;  // row length of the device chunk buffers
+        const int32_t *dev_cols = d_uni.as<int32_t>();
+        cudaStream_t cs = ctx->copy_stream;
         if (host_gather) {
             const size_t need = (size_t)chunk_cells * U * esz;
             if (ctx->pin_bytes < need) {
@@ -860,97 +863,57 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             PP_CUDA(d_ident.alloc(sizeof(int32_t) * U, st));
             PP_CUDA(cudaMemcpyAsync(d_ident.p, ident.data(), sizeof(int32_t) * U, cudaMemcpyHostToDevice, st));
             PP_CUDA(cudaStreamSynchronize(st));  // ident is a local
-            G.cs = ctx->copy_stream;
-            G.ldv = U;
-            G.cols = d_ident.as<int32_t>();
+            dev_cols = d_ident.as<int32_t>();
         }
-        if (use_d) {
-            D.cs = host_gather ? ctx->copy_stream2 : ctx->copy_stream;
-            D.ldv = ld;
-            D.cols = d_uni.as<int32_t>();
+        for (int b = 0; b < 2; ++b) {
+            if (!(buf[b] = pp_slab(ctx, b == 0 ? SLAB_CHUNK0 : SLAB_CHUNK1, (size_t)chunk_cells * dev_ld * esz)))
+                return PP_ENOMEM;
+            PP_CUDA(events.make(&copied[b], cudaEventDisableTiming));
+            PP_CUDA(events.make(&freed[b], cudaEventDisableTiming));
         }
-        for (Lane *L : {&G, &D}) {
-            if (!L->cs) continue;
-            for (int b = 0; b < 2; ++b) {
-                if (!(L->buf[b] = pp_slab(ctx, b == 0 ? SLAB_CHUNK0 : SLAB_CHUNK1, (size_t)chunk_cells * L->ldv * esz)))
-                    return PP_ENOMEM;
-                PP_CUDA(cudaEventCreateWithFlags(&L->copied[b], cudaEventDisableTiming));
-                PP_CUDA(cudaEventCreateWithFlags(&L->freed[b], cudaEventDisableTiming));
-            }
-        }
-        PP_CUDA(cudaEventCreate(&ev_c0));
-        PP_CUDA(cudaEventCreate(&ev_c1));
+        PP_CUDA(events.make(&ev_c0, cudaEventDefault));
+        PP_CUDA(events.make(&ev_c1, cudaEventDefault));
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
-        for (Lane *L : {&G, &D})
-            if (L->cs) PP_CUDA(cudaStreamWaitEvent(L->cs, ctx->ev[3], 0));  // buffers exist before the first copy
-        PP_CUDA(cudaEventRecord(ev_c0, host_gather ? G.cs : D.cs));
-
-        struct Pending { Lane *L; int slot; int64_t c0, nc; };
-        auto start_copy = [&](Lane &L, int64_t c0, int64_t nc, Pending &out) -> int {
-            const int b = L.used & 1;
+        PP_CUDA(cudaStreamWaitEvent(cs, ctx->ev[3], 0));  // buffers exist before the first copy
+        PP_CUDA(cudaEventRecord(ev_c0, cs));
+        int i = 0;
+        for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, ++i) {
+            const int b = i & 1;
+            const int64_t nc = std::min(chunk_cells, n_cells - c0);
             const void *src = x0 + (size_t)c0 * ld * esz;
-            if (&L == &G) {
-                if (L.used >= 2) PP_CUDA(cudaEventSynchronize(L.copied[b]));  // H2D two chunks ago has drained pin[b]
+            if (host_gather) {
+                if (i >= 2) PP_CUDA(cudaEventSynchronize(copied[b]));  // H2D two chunks ago has drained pin[b]
                 if (x_dtype == PP_F64)
                     gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], n_thr);
                 else
                     gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], n_thr);
                 src = ctx->pin[b];
             }
-            if (L.used >= 2) PP_CUDA(cudaStreamWaitEvent(L.cs, L.freed[b], 0));  // rank kernel two chunks ago is done
-            PP_CUDA(cudaMemcpyAsync(L.buf[b], src, (size_t)nc * L.ldv * esz, cudaMemcpyHostToDevice, L.cs));
-            ctx->tm.h2d_bytes += (int64_t)((size_t)nc * L.ldv * esz);
-            PP_CUDA(cudaEventRecord(L.copied[b], L.cs));
-            L.used++;
-            out = Pending{&L, b, c0, nc};
-            return PP_OK;
-        };
-        auto compute = [&](const Pending &p) -> int {
-            Lane &L = *p.L;
-            PP_CUDA(cudaStreamWaitEvent(st, L.copied[p.slot], 0));
-            int r = pp_rank_launch(ctx, L.buf[p.slot], x_dtype, L.ldv, d_rows.as<int32_t>(), p.nc, L.cols, U,
-                                   (uint16_t *)s_rank + p.c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
-            if (r) return r;
-            PP_CUDA(cudaEventRecord(L.freed[p.slot], st));
+            if (i >= 2) PP_CUDA(cudaStreamWaitEvent(cs, freed[b], 0));  // the rank kernel two chunks ago is done
+            PP_CUDA(cudaMemcpyAsync(buf[b], src, (size_t)nc * dev_ld * esz, cudaMemcpyHostToDevice, cs));
+            ctx->tm.h2d_bytes += (int64_t)((size_t)nc * dev_ld * esz);
+            PP_CUDA(cudaEventRecord(copied[b], cs));
+            PP_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
+            rc = pp_rank_launch(ctx, buf[b], x_dtype, dev_ld, d_rows.as<int32_t>(), nc, dev_cols, U,
+                                (uint16_t *)s_rank + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            if (rc) return rc;
+            PP_CUDA(cudaEventRecord(freed[b], st));
             cudaEvent_t e0, e1;
-            PP_CUDA(cudaEventCreate(&e0));
-            PP_CUDA(cudaEventCreate(&e1));
+            PP_CUDA(events.make(&e0, cudaEventDefault));
+            PP_CUDA(events.make(&e1, cudaEventDefault));
             ev_s.push_back(e0);
             ev_s.push_back(e1);
-            P.rank = (uint16_t *)s_rank + p.c0 * rank_ld;
-            P.n_cells = p.nc;
-            P.out_off = p.c0;
+            P.rank = (uint16_t *)s_rank + c0 * rank_ld;
+            P.n_cells = nc;
+            P.out_off = c0;
             PP_CUDA(cudaEventRecord(e0, st));
-            launch_score(p.nc);
+            launch_score(nc);
             PP_CHECK_LAUNCH();
             PP_CUDA(cudaEventRecord(e1, st));
-            return PP_OK;
-        };
-        for (int64_t i = 0; i < n_chunks;) {
-            const int64_t a0 = i * chunk_cells, an = std::min(chunk_cells, n_cells - a0);
-            Pending pa, pb;
-            bool have_b = false;
-            if (hybrid && i + 1 < n_chunks) {  // the copy engine streams chunk i+1 while the CPU gathers chunk i
-                const int64_t b0 = (i + 1) * chunk_cells;
-                rc = start_copy(D, b0, std::min(chunk_cells, n_cells - b0), pb);
-                if (rc) return rc;
-                have_b = true;
-            }
-            rc = start_copy(host_gather ? G : D, a0, an, pa);
-            if (rc) return rc;
-            rc = compute(pa);
-            if (rc) return rc;
-            if (have_b) {
-                rc = compute(pb);
-                if (rc) return rc;
-            }
-            i += have_b ? 2 : 1;
         }
+        PP_CUDA(cudaEventRecord(ev_c1, cs));
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
-        for (Lane *L : {&G, &D})
-            if (L->cs) PP_CUDA(cudaStreamSynchronize(L->cs));
-        PP_CUDA(cudaEventRecord(ev_c1, host_gather ? G.cs : D.cs));
-        PP_CUDA(cudaStreamSynchronize(host_gather ? G.cs : D.cs));
+        PP_CUDA(cudaStreamSynchronize(cs));
         PP_CUDA(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
         for (size_t j = 0; j + 1 < ev_s.size(); j += 2) {
@@ -958,14 +921,6 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             cudaEventElapsedTime(&ms, ev_s[j], ev_s[j + 1]);
             score_ms += ms;
         }
-        for (cudaEvent_t e : ev_s) cudaEventDestroy(e);
-        for (Lane *L : {&G, &D})
-            for (int b = 0; b < 2; ++b) {
-                if (L->copied[b]) cudaEventDestroy(L->copied[b]);
-                if (L->freed[b]) cudaEventDestroy(L->freed[b]);
-            }
-        cudaEventDestroy(ev_c0);
-        cudaEventDestroy(ev_c1);
     }
     PP_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, sizeof(double) * out_cnt, cudaMemcpyDeviceToHost, st));
     if (out_obs_hits) PP_CUDA(cudaMemcpyAsync(out_obs_hits, d_oh.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));

@@ -94,7 +94,7 @@ struct Chunk {  // a run of cell words of one class
     int32_t w_begin;
     int32_t n_words;
     int32_t class_end;  // class index if this chunk closes the class, else -1
-    int32_t flush;      // unused
+    int32_t pad;
 };
 
 struct PairParams {
@@ -733,7 +733,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             c.w_begin = w;
             c.n_words = std::min(wc_max, class_w0[k + 1] - w);
             c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
-            c.flush = 0;
+            c.pad = 0;
             chunks.push_back(c);
         }
     // ---- tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain pairs g1 < g2)

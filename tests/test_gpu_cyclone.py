@@ -277,3 +277,42 @@ def test_host_gather_path(dtype):
     rows[0] = 5
     for i, k in enumerate(ks):
         assert np.array_equal(s_host[i, rows], orc.phase_scores(x[rows], 30, 10, 5, pairs[k], used[k]))
+
+
+def _score_vs_oracle(x, pairs, used, iterations, min_iter, min_pairs):
+    got = _ffi().phase_scores(x, iterations, min_iter, min_pairs, pairs, used)
+    exp = orc.phase_scores(x, iterations, min_iter, min_pairs, pairs, used)
+    assert np.array_equal(got, exp, equal_nan=True)
+    return got
+
+
+def test_degenerate_cells_and_parameters():
+    """Cells where every pair ties (score 0 by cyclone.py:223-229 'cur_score == 0' rule), cells below min_pairs,
+    min_iter above what the permutations can reach, iterations = 1, and a single marker pair."""
+    rng = np.random.default_rng(41)
+    n, g = 150, 120
+    x = rng.poisson(1.0, (n, g)).astype(np.float64)
+    x[3] = 2.0                                        # all ties: no informative pair
+    x[4, :] = 0.0
+    x[4, 7] = 1.0                                     # one or two informative pairs only
+    used = (rng.random(g) < 0.6).astype(np.uint8)     # pairs index the used-compacted genes (cyclone.py:303-309)
+    used[7] = 1
+    pairs = rng.integers(0, int(used.sum()), (300, 2))
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    for iterations, min_iter, min_pairs in [(200, 50, 10), (200, 250, 10), (1, 1, 1), (64, 1, 400), (100, 100, 0)]:
+        _score_vs_oracle(x, pairs, used, iterations, min_iter, min_pairs)
+    u1 = np.zeros(g, dtype=np.uint8)
+    u1[[5, 9]] = 1
+    _score_vs_oracle(x, np.array([[0, 1]]), u1, 50, 10, 1)
+
+
+def test_repeated_and_mirrored_pairs():
+    """The reference keeps duplicate pairs and both orientations (cyclone.py:273-311 never dedups)."""
+    rng = np.random.default_rng(43)
+    n, g = 200, 60
+    x = rng.poisson(2.0, (n, g)).astype(np.float32)
+    used = (rng.random(g) < 0.7).astype(np.uint8)
+    base = rng.integers(0, int(used.sum()), (80, 2))
+    base = base[base[:, 0] != base[:, 1]]
+    pairs = np.concatenate([base, base[:30], base[:40, ::-1]])
+    _score_vs_oracle(x, pairs, used, 300, 100, 5)

@@ -314,3 +314,62 @@ def test_marker_table_roundtrip_and_cyclone():
     a = pairs.cyclone(y, d, gn, yn, iterations=60, min_iter=10, min_pairs=3)
     b = pairs.cyclone(y, t, gn, yn, iterations=60, min_iter=10, min_pairs=3)
     assert a.equals(b) and list(a.columns)[:len(d)] == list(d.keys())
+
+
+def _check_against_oracle(x, lab, thr):
+    g = x.shape[1]
+    keys, cls, tm = run_kernel(x, lab, len(thr), thr)
+    res = orc.check_pairs(x, lab, thr)
+    rr, cc = np.where(res != -1)
+    assert np.array_equal(keys, (rr * g + cc).astype(np.uint64))
+    assert np.array_equal(cls, res[rr, cc].astype(np.int32))
+    return len(keys), tm
+
+
+@pytest.mark.parametrize("thr", [[0, 0, 0], [-3, 5, 0], [1, 1, 1], [10 ** 6, 2, 2], [40, 0, 10 ** 6]])
+def test_degenerate_thresholds(thr):
+    """Thresholds the reference never clamps (fraction <= 0 gives thr <= 0, sandbag.py:212-217): zero / negative
+    thresholds make every class 'up' and 'down' at once, thresholds above the class size can never be met."""
+    rng = np.random.default_rng(23)
+    x, lab = synth(rng, 130, 310, 3, frac_de=0.3)
+    _check_against_oracle(x, lab, np.array(thr, dtype=np.int64))
+
+
+def test_second_sweep_runs_many_rounds():
+    """Strong two-class signal: most pairs of a 128 x 64 tile are candidates, so the second sweep needs several
+    rounds of its 512-entry candidate list, and the hit buffer is regrown."""
+    rng = np.random.default_rng(29)
+    n, g = 260, 700
+    lab = (np.arange(n) % 2).astype(np.int64)
+    level = rng.permutation(g).astype(np.float64)
+    x = np.where(lab[:, None] == 0, level[None, :], level[::-1][None, :]) + rng.integers(0, 2, (n, g))
+    n_hits, tm = _check_against_oracle(x, lab, orc.calc_thresholds(np.bincount(lab), 0.9))
+    assert n_hits > 100_000
+
+
+def test_values_that_stress_the_rank_transform():
+    """Negative values, signed zeros, huge magnitudes, denormals and all-equal cells."""
+    rng = np.random.default_rng(31)
+    n, g = 90, 260
+    lab = rng.integers(0, 3, n)
+    lab[:3] = np.arange(3)
+    x = rng.normal(0, 3, (n, g)).round(0)           # many ties, half of them negative
+    x[x == 0] = np.where(rng.random((x == 0).sum()) < 0.5, -0.0, 0.0)
+    x[5] = 7.0                                       # a cell where all genes tie
+    x[6] = rng.normal(0, 1, g) * 1e300
+    x[7] = rng.normal(0, 1, g) * 5e-324 * 1000       # denormals
+    x[:, 17] += np.where(lab == 1, 50.0, 0.0)
+    x[:, 40] -= np.where(lab == 2, 50.0, 0.0)
+    n_hits, _ = _check_against_oracle(x, lab, orc.calc_thresholds(np.bincount(lab, minlength=3), 0.6))
+    assert n_hits > 0
+    xc = np.full((n, g), 3.0)                        # a constant matrix: no pair differs anywhere
+    assert _check_against_oracle(xc, lab, np.array([1, 1, 1]))[0] == 0
+
+
+def test_single_cell_classes_and_tiny_inputs():
+    rng = np.random.default_rng(37)
+    x = rng.poisson(2.0, (3, 70)).astype(np.float64)  # one cell per class
+    lab = np.arange(3)
+    _check_against_oracle(x, lab, np.array([1, 1, 1]))
+    x2 = rng.poisson(2.0, (5, 2)).astype(np.float64)  # two genes: one pair
+    _check_against_oracle(x2, np.array([0, 0, 1, 1, 1]), np.array([2, 2]))
