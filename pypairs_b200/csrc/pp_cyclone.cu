@@ -23,6 +23,7 @@
 // multiplication (counts < 2^16), NaN rules of get_proportion (:217-218) applied to both
 // sides; score = below / iterations as one IEEE double division (:246).
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -151,12 +152,23 @@ StarLayout build_star_layout(const int32_t *pairs, int np, int nu) {
     std::vector<char> covered(np, 0);
     struct Star { int hub, side; std::vector<int> others; };
     std::vector<Star> stars;
-    for (;;) {
-        int best = 0, bg = -1, bs = 0;
-        for (int sd = 0; sd < 2; ++sd)
-            for (int g = 0; g < nu; ++g)
-                if (deg[sd][g] > best) { best = deg[sd][g]; bg = g; bs = sd; }
-        if (bg < 0) break;
+    // bucket queue over the degree with lazy deletion (degrees only fall): largest degree first, O(pairs + genes)
+    int cur = 0;
+    for (int sd = 0; sd < 2; ++sd)
+        for (int g = 0; g < nu; ++g) cur = std::max(cur, deg[sd][g]);
+    std::vector<std::vector<int>> bucket(cur + 1);  // entries: gene * 2 + side
+    for (int sd = 1; sd >= 0; --sd)
+        for (int g = nu - 1; g >= 0; --g)
+            if (deg[sd][g] > 0) bucket[deg[sd][g]].push_back(g * 2 + sd);
+    while (cur > 0) {
+        if (bucket[cur].empty()) {
+            --cur;
+            continue;
+        }
+        const int e = bucket[cur].back();
+        bucket[cur].pop_back();
+        const int bg = e >> 1, bs = e & 1;
+        if (deg[bs][bg] != cur) continue;  // stale entry
         Star st;
         st.hub = bg;
         st.side = bs;
@@ -165,10 +177,11 @@ StarLayout build_star_layout(const int32_t *pairs, int np, int nu) {
             covered[i] = 1;
             const int other = pairs[2 * i + (bs == 0 ? 1 : 0)];
             st.others.push_back(other);
-            deg[1 - bs][other] -= 1;  // the pair leaves the other endpoint's opposite-side star
+            // the pair leaves the other endpoint's opposite-side star
+            if (--deg[1 - bs][other] > 0) bucket[deg[1 - bs][other]].push_back(other * 2 + (1 - bs));
         }
         deg[bs][bg] = 0;
-        stars.push_back(st);
+        stars.push_back(std::move(st));
     }
     StarLayout L;
     auto pad_to_chunk = [&]() {
@@ -238,9 +251,12 @@ struct ScoreParams {
     int n_classes;
     int iterations, min_iter, min_pairs;
     const ClassDesc *classes;
-    uint32_t *gtile;    // !FAST only: [gridDim.x][n_union][32] scratch
+    const uint32_t *gtile;  // !FAST only: the launch's ranks as [n_tiles][n_union][32] words (pack_tiles_kernel)
     const int32_t *class_order;  // classes by decreasing cost: work unit u = (class_order[u / n_tiles], tile u % n_tiles)
     int *unit_counter;           // dynamic work-unit counter (zeroed before the launch)
+    int n_slices;                // > 1: the iterations of a (class, tile) are split over n_slices work units
+    int slice_len;               // iterations per slice (a multiple of the warps per CTA)
+    int32_t *below;              // n_slices > 1 only: [n_classes][out_ld] partial counts, finished by finalize_kernel
     double *scores;     // [n_classes][n_cells]
     int32_t *obs_hits;  // [n_classes][n_cells]
     int32_t *obs_total;
@@ -264,8 +280,9 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 //        statistics are taken against the hub h, on two different pipes:
 //          X: (h >= v) as a 0xFFFF/0 mask per half   -- HSET2.GE (ALU pipe) + one 32-bit integer accumulate
 //          Z: (h >  v) as clamp(h - v, 0, 1) in fp16 -- HADD2.SAT + HADD2 (FMA pipe)
-//  !FAST (up to 32 768 marker genes): ranks are 15-bit integers, two per word, tile in a per-CTA global
-//        scratch (L1/L2 cached gathers); (x >= y) per half is bit 15/31 of (x | 0x80008000) - y.
+//  !FAST (up to 32 768 marker genes): ranks are 15-bit integers, two per word, tiles in global memory in the
+//        same [gene][lane] layout (pack_tiles_kernel; L1/L2 cached gathers, shared by all CTAs working on the
+//        tile); (x >= y) per half is bit 15/31 of (x | 0x80008000) - y.
 // Both flush their per-chunk counters into 32-bit per-cell counters, so a class may have any number of pairs.
 __device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<const __half2 *>(&x); }
 __device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) { return __hge2_mask(as_h2(x), as_h2(y)); }
@@ -274,7 +291,7 @@ __device__ __forceinline__ uint32_t ge_bits(uint32_t x, uint32_t y) {
 }
 template <bool FAST> __device__ __forceinline__ uint32_t tile_load(uint64_t base, uint32_t off) {
     if (FAST) return lds32((uint32_t)base + off);
-    return *reinterpret_cast<const uint32_t *>(base + off);  // written by this CTA: coherent load, not ld.nc
+    return __ldg(reinterpret_cast<const uint32_t *>(base + off));  // written by an earlier kernel
 }
 
 struct RowAcc {  // per-cell counters of one table row: section A / B, low / high cell of the lane
@@ -383,6 +400,27 @@ __device__ __forceinline__ void row_counts(const RowAcc &r, int s_all, int s_b, 
     t_hi = s_all - r.xa_hi + r.za_hi - r.xb_hi + r.zb_hi;
 }
 
+// !FAST: ranks [cell][rank_ld] u16 -> [tile][gene][lane] words (lane l = cells l and l + 32 of the 64-cell tile).
+// One CTA per (tile, 32-gene block): 64 coalesced 64-byte row reads, transposed through shared memory.
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld,
+                                                         int64_t n_cells, int n_union, uint32_t *__restrict__ out) {
+    __shared__ uint16_t s[TILE_CELLS][33];
+    const int64_t cell0 = (int64_t)blockIdx.x * TILE_CELLS;
+    const int g0 = blockIdx.y * 32, gl = threadIdx.x & 31;
+    for (int c = threadIdx.x >> 5; c < TILE_CELLS; c += 8)
+        s[c][gl] = (cell0 + c < n_cells && g0 + gl < n_union) ? rank[(cell0 + c) * rank_ld + g0 + gl] : (uint16_t)0;
+    __syncthreads();
+    uint32_t *o = out + ((size_t)blockIdx.x * n_union + g0) * 32;
+    for (int g = threadIdx.x >> 5; g < 32 && g0 + g < n_union; g += 8)
+        o[g * 32 + gl] = (uint32_t)s[gl][g] | ((uint32_t)s[gl + 32][g] << 16);
+}
+
+// total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
+__device__ __forceinline__ double final_score(uint32_t below, int iterations, int min_iter) {
+    if (iterations >= min_iter && iterations > 0) return (double)below / (double)iterations;
+    return nan("");
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
     extern __shared__ __align__(128) uint8_t smem_dyn[];
@@ -392,36 +430,40 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // FAST: [n_union][32] words in shared memory, followed by the per-warp staging buffers;
-    // !FAST: the tile is this CTA's slab of the global scratch, shared memory only holds the staging buffers
-    uint32_t *tile = FAST ? reinterpret_cast<uint32_t *>(smem_dyn) : P.gtile + (size_t)blockIdx.x * P.n_union * 32;
+    // !FAST: the tiles stay in global memory, shared memory only holds the staging buffers
+    uint32_t *tile = reinterpret_cast<uint32_t *>(smem_dyn);
     uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (FAST ? (size_t)P.n_union * 128 : 0) + (size_t)warp * STAGE_BYTES);
-    const uint64_t tile_lane = FAST ? (uint64_t)(smem_u32(tile) + lane * 4) : (uint64_t)(uintptr_t)(tile + lane);
+    uint64_t tile_lane = (uint64_t)(smem_u32(tile) + lane * 4);
     const int64_t n_tiles = (P.n_cells + TILE_CELLS - 1) / TILE_CELLS;
 
-    // Work units = (class, 64-cell tile), handed out dynamically, most expensive class first: equal-cost tiles would
-    // quantise the launch into whole waves (1 563 tiles on 148 SMs = 10.56 -> 11), units a third of that size don't.
-    const int64_t n_units = n_tiles * P.n_classes;
+    // Work units = (class, 64-cell tile, iteration slice), handed out dynamically, most expensive class first:
+    // equal-cost tiles would quantise the launch into whole waves (1 563 tiles on 148 SMs = 10.56 -> 11), units a
+    // third of that size don't.  Few cells (fewer units than SMs) are split further into iteration slices; every
+    // slice recomputes the observed row and adds its part of `below` to a global counter.
+    const int64_t n_units = n_tiles * P.n_classes * P.n_slices;
     for (;;) {
         if (tid == 0) s_unit = atomicAdd(P.unit_counter, 1);
         __syncthreads();
         const int64_t u = s_unit;
         if (u >= n_units) break;
-        const int cls = P.class_order[u / n_tiles];
-        const int64_t cell0 = (u % n_tiles) * TILE_CELLS;
+        const int slice = (int)(u % P.n_slices);
+        const int64_t ct = u / P.n_slices;
+        const int cls = P.class_order[ct / n_tiles];
+        const int64_t cell0 = (ct % n_tiles) * TILE_CELLS;
+        const int k_first = 1 + slice * P.slice_len;
+        const int k_last = min(P.iterations, k_first + P.slice_len - 1);
         const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
         // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
-        {
+        if (!FAST) {
+            tile_lane = (uint64_t)(uintptr_t)(P.gtile + (size_t)(ct % n_tiles) * P.n_union * 32 + lane);
+        } else {
             const uint16_t *r_lo = P.rank + (c_lo < P.n_cells ? c_lo : 0) * P.rank_ld;
             const uint16_t *r_hi = P.rank + (c_hi < P.n_cells ? c_hi : 0) * P.rank_ld;
             for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
                 const uint32_t lo = (c_lo < P.n_cells) ? r_lo[g] : 0u;
                 const uint32_t hi = (c_hi < P.n_cells) ? r_hi[g] : 0u;
-                if (FAST) {
-                    const __half2 v = __floats2half2_rn((float)lo, (float)hi);  // exact: ranks < 2048
-                    tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
-                } else {
-                    tile[g * 32 + lane] = lo | (hi << 16);
-                }
+                const __half2 v = __floats2half2_rn((float)lo, (float)hi);  // exact: ranks < 2048
+                tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
             }
         }
         {
@@ -430,7 +472,6 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
             if (tid < 32)
                 for (int j = 0; j < 8; ++j) s_obs[j][tid] = 0;
             if (tid < TILE_CELLS) s_below[tid] = 0;
-            if (!FAST) __threadfence_block();
             __syncthreads();  // also orders the tile stores before the first gather
             // ---- observed proportion (row 0): chunks dealt to the warps
             {
@@ -453,7 +494,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
             }
             const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
             const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
-            if (warp == 0) {
+            if (warp == 0 && slice == 0) {
                 if (c_lo < P.n_cells) {
                     if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_lo] = h0_lo;
                     if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_lo] = t0_lo;
@@ -465,7 +506,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
             }
             // ---- permutation null: iterations dealt round-robin to the warps
             uint32_t below_lo = 0, below_hi = 0;
-            for (int k = 1 + warp; k <= P.iterations; k += SCORE_WARPS) {
+            for (int k = k_first + warp; k <= k_last; k += SCORE_WARPS) {
                 const RowAcc r = eval_row<FAST>(tile_lane, cd.E + (size_t)k * s_all, cd, 0, 1, stage, lane);
                 int h_lo, h_hi, t_lo, t_hi;
                 row_counts(r, s_all, s_b, h_lo, h_hi, t_lo, t_hi);
@@ -479,14 +520,24 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
             atomicAdd(&s_below[32 + lane], below_hi);
             __syncthreads();
             if (tid < TILE_CELLS && cell0 + tid < P.n_cells) {
-                // total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
-                double sc = nan("");
-                if (P.iterations >= P.min_iter && P.iterations > 0) sc = (double)s_below[tid] / (double)P.iterations;
-                P.scores[(int64_t)cls * P.out_ld + P.out_off + cell0 + tid] = sc;
+                const int64_t o = (int64_t)cls * P.out_ld + P.out_off + cell0 + tid;
+                if (P.n_slices > 1) {
+                    if (s_below[tid]) atomicAdd(P.below + o, (int32_t)s_below[tid]);
+                } else {
+                    P.scores[o] = final_score(s_below[tid], P.iterations, P.min_iter);
+                }
             }
             __syncthreads();
         }
     }
+}
+
+// Sliced launches: scores of cells [out_off, out_off + n_cells) of every class from the summed partial counts.
+__global__ void finalize_kernel(const ScoreParams P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_cells * P.n_classes) return;
+    const int64_t o = (i / P.n_cells) * P.out_ld + P.out_off + i % P.n_cells;
+    P.scores[o] = final_score((uint32_t)P.below[o], P.iterations, P.min_iter);
 }
 
 struct PermKey {
@@ -663,7 +714,12 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_src(n_classes), d_mask(n_classes), d_map(n_classes);
     std::vector<ClassDesc> cds(n_classes);
     const int32_t *ext = perm_tables;
+    const bool trace = getenv("PP_TRACE") != nullptr;  // host-side phase times on stderr
+    auto now_ms = [] {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
     for (int c = 0; c < n_classes; ++c) {
+        const double t_a = now_ms();
         const int nu = (int)(used_off[c + 1] - used_off[c]);
         const int np = (int)(pair_off[c + 1] - pair_off[c]);
         std::vector<uint16_t> map(nu > 0 ? nu : 1);
@@ -690,11 +746,15 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, st));
             PP_CUDA(cudaStreamSynchronize(st));  // t is a local
         }
+        const double t_b = now_ms();
         PP_CUDA(d_map[c].alloc(sizeof(uint16_t) * map.size(), st));
         PP_CUDA(cudaMemcpyAsync(d_map[c].p, map.data(), sizeof(uint16_t) * map.size(), cudaMemcpyHostToDevice, st));
         PP_CUDA(cudaStreamSynchronize(st));  // map is a local
         const StarLayout L = build_star_layout(pairs + 2 * pair_off[c], np, nu);
         const int n_slots = (int)L.slot_src.size();
+        if (trace)
+            fprintf(stderr, "[pp_cyclone] class %d: %d genes, %d pairs -> %d slots; permutations %.1f ms, star layout %.1f ms\n",
+                    c, nu, np, n_slots, t_b - t_a, now_ms() - t_b);
         PP_CUDA(d_src[c].alloc(sizeof(int32_t) * n_slots, st));
         PP_CUDA(cudaMemcpyAsync(d_src[c].p, L.slot_src.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
         PP_CUDA(d_mask[c].alloc(sizeof(uint32_t) * L.n_chunks, st));
@@ -733,11 +793,13 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
     P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
     PP_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    const int slow_grid = ctx->n_sm * 2;  // persistent CTAs, one global tile slab each
-    P.gtile = nullptr;
-    if (!fast && !(P.gtile = (uint32_t *)pp_slab(ctx, SLAB_MISC, (size_t)slow_grid * U * 128))) return PP_ENOMEM;
+    const int slow_grid = ctx->n_sm * 2;  // persistent CTAs of the global-tile path
+    uint32_t *s_tiles = nullptr;          // !fast: packed tiles of one launch
+    if (!fast && !(s_tiles = (uint32_t *)pp_slab(ctx, SLAB_MISC, (size_t)((chunk_cells + TILE_CELLS - 1) / TILE_CELLS) * U * 128)))
+        return PP_ENOMEM;
+    P.gtile = s_tiles;
     // classes by decreasing cost (slots) + the dynamic work-unit counter
-    DevBuf d_order, d_counter;
+    DevBuf d_order, d_counter, d_below;
     {
         std::vector<int32_t> order(n_classes);
         for (int c = 0; c < n_classes; ++c) order[c] = c;
@@ -749,14 +811,42 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     P.class_order = d_order.as<int32_t>();
     P.unit_counter = d_counter.as<int>();
+    // Launches with fewer (class, tile) units than ~3 per SM (few cells, the reference's own use case) split each
+    // unit's iterations into slices of >= 2 iterations per warp, aiming at ~4 units per SM.
+    auto slices_for = [&](int64_t nc, int *slice_len) {
+        *slice_len = iterations;
+        const int64_t units0 = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes;
+        if (nc <= 0 || units0 >= 3 * (int64_t)ctx->n_sm || iterations < 4 * SCORE_WARPS) return 1;
+        const int64_t want = (4 * (int64_t)ctx->n_sm + units0 - 1) / units0;
+        const int64_t len = ((iterations + want - 1) / want + SCORE_WARPS - 1) / SCORE_WARPS * SCORE_WARPS;
+        *slice_len = (int)std::max<int64_t>(len, 2 * SCORE_WARPS);
+        return (iterations + *slice_len - 1) / *slice_len;
+    };
+    {
+        int len;
+        if (slices_for(chunk_cells, &len) > 1 || slices_for(n_cells % chunk_cells, &len) > 1) {
+            PP_CUDA(d_below.alloc(sizeof(int32_t) * out_cnt, st));
+            PP_CUDA(cudaMemsetAsync(d_below.p, 0, sizeof(int32_t) * out_cnt, st));
+        }
+    }
+    P.below = d_below.as<int32_t>();
     auto launch_score = [&](int64_t nc) {
-        const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes;
+        P.n_slices = slices_for(nc, &P.slice_len);
+        const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes * P.n_slices;
         cudaMemsetAsync(d_counter.p, 0, sizeof(int), st);
         const int64_t grid = std::min<int64_t>(n_units, fast ? ctx->n_sm : slow_grid);
-        if (fast)
+        if (fast) {
             score_kernel<true><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
-        else
+        } else {
+            ++ctx->launches;
+            pack_tiles_kernel<<<dim3((unsigned)((nc + TILE_CELLS - 1) / TILE_CELLS), (unsigned)((U + 31) / 32)), 256, 0, st>>>(
+                P.rank, rank_ld, nc, U, s_tiles);
             score_kernel<false><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
+        }
+        if (P.n_slices > 1) {
+            ++ctx->launches;
+            finalize_kernel<<<(unsigned)((nc * n_classes + 255) / 256), 256, 0, st>>>(P);
+        }
     };
     float score_ms = 0.f, copy_ms = 0.f;
     if (csr) {

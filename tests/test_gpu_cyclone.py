@@ -316,3 +316,22 @@ def test_repeated_and_mirrored_pairs():
     base = base[base[:, 0] != base[:, 1]]
     pairs = np.concatenate([base, base[:30], base[:40, ::-1]])
     _score_vs_oracle(x, pairs, used, 300, 100, 5)
+
+
+@pytest.mark.parametrize("n_cells,n_used,n_pairs,iterations", [(5, 300, 900, 1000), (213, 700, 3000, 1000),
+                                                               (70, 2500, 6000, 333), (130, 400, 500, 64)])
+def test_few_cells_split_iterations_over_ctas(n_cells, n_used, n_pairs, iterations):
+    """Fewer (class, tile) units than SMs: the iterations are split into slices over several CTAs (shared-memory and
+    global-tile paths); scores must not depend on how the work was cut."""
+    rng = np.random.default_rng(n_cells)
+    g = 3000
+    x = rng.poisson(1.5, (n_cells, g)).astype(np.float32)
+    used = np.zeros(g, dtype=np.uint8)
+    used[rng.choice(g, n_used, replace=False)] = 1
+    pairs = rng.integers(0, n_used, (n_pairs, 2))
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    got = _score_vs_oracle(x, pairs, used, iterations, 10, 5)
+    assert np.isfinite(got).all()
+    sc, tm, oh, ot = _ffi().cyclone(x, [np.where(used)[0]], [pairs], iterations, 10, 5, want_observed=True)
+    _, eh, et = orc.phase_scores(x, 1, 1, 1, pairs, used, return_observed=True)
+    assert np.array_equal(sc[0], got) and np.array_equal(oh[0], eh) and np.array_equal(ot[0], et)
