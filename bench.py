@@ -293,7 +293,8 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
     out = {
         "metric": "sandbag gene-pair x cell compares/s", "unit": "pair*cell/s", "scaling": "strong",
         "config": {"workload": "configs[2]: sandbag synthetic 20k genes x 10k cells, 3 classes, fraction=0.65",
-                   "dtype_in": "float32 Poisson counts", "markers_found": n_markers, "bit_planes": tm["n_planes"]},
+                   "dtype_in": "float32 Poisson counts", "markers_found": n_markers, "bit_planes": tm["n_planes"],
+                   "bit_planes_compared_per_pair": tm["avg_planes"]},
         "value": units / (ms_step * 1e-3), "ms_per_step": ms_step, "device_ms_per_step": max_over_ranks(dev_ms / args.steps, world),
         "kernel_ms": {"pair": main_step, "rank_and_bitslice": prep_step}, "gpu_launches": launches, "clocks": clocks,
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "pair*cell/s", "ms_per_step": e2e_ms,
@@ -306,7 +307,7 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
                      "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],
                      "peak_source": "pp_alu_peak micro-benchmark (independent LOP3 stream), measured in this run",
                      "algorithmic_ops_per_unit": 2, "units_per_launch": my_pairs * n,
-                     "machine_lop3_per_unit": 2.0 * tm["n_planes"] / 32.0,
+                     "machine_lop3_per_unit": tm["avg_planes"] / 32.0,
                      "traffic": ncu_traffic("pair_kernel") if world == 1 else None},
     }
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -83,6 +83,8 @@ typedef struct pp_timings {
     int32_t n_launches; /* kernels launched by this call */
     int64_t n_units;  /* sandbag: gene pairs evaluated by this shard; cyclone: cells scored by this shard */
     int64_t h2d_bytes; /* bytes of the expression matrix actually copied host -> device by this call */
+    float avg_planes;  /* sandbag: mean number of bit planes compared per gene pair of this shard (<= n_planes) */
+    int32_t reserved;
 } pp_timings;
 
 int pp_version(void);

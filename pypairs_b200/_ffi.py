@@ -29,7 +29,8 @@ class Csr(ctypes.Structure):
 class Timings(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_float), ("prep_ms", ctypes.c_float), ("main_ms", ctypes.c_float),
                 ("post_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("n_planes", ctypes.c_int32),
-                ("n_launches", ctypes.c_int32), ("n_units", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64)]
+                ("n_launches", ctypes.c_int32), ("n_units", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
+                ("avg_planes", ctypes.c_float), ("reserved", ctypes.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -4,14 +4,16 @@
 // Data layout in HBM
 //   rank   u16 [32*W][G]     per-cell dense ranks, cells class-sorted, every class padded
 //                            to a multiple of 32 cells with all-tie cells (pp_rank.cu)
-//   planes u32 [NB][W][B][64] bit-sliced ranks: gene block nb (64 genes), cell word w (32
-//                            cells of ONE class), plane p (bit p of the rank); bit c of the
-//                            word belongs to cell 32*w + c.  A (gene block, run of words) is
-//                            one contiguous byte range -> one 1-D TMA bulk copy.
-// Pair kernel (pair_kernel): CTA tile = 128 a-genes x 64 b-genes, every thread owns an
-// 8x4 register tile of gene pairs and walks all cell words.  For one word the two
-// predicates of sandbag.py:179-182 are evaluated for 32 cells at once with the
-// LSB->MSB recurrences
+//   planes u32, per gene block nb (64 gene positions; positions sorted by the planes a gene's
+//                            ranks need, widest first): [2*Bn - 1][W][64] -- Bn low planes
+//                            (bit p of the rank) and the suffix planes "rank >= 2^j"; bit c of
+//                            cell word w belongs to cell 32*w + c (cells of ONE class).  A
+//                            (block, plane, run of words) is one contiguous byte range -> one
+//                            1-D TMA bulk copy.
+// Pair kernel (pair_kernel): CTA tile = 128 a-positions x 64 b-positions, every thread owns a
+// 4x4 register tile of gene pairs and walks all cell words.  For one word the predicate
+// x[a] > x[b] (x[a] < x[b] in the second sweep) of sandbag.py:179-182 is evaluated for 32
+// cells at once with the LSB->MSB recurrences
 //        gt' = (a & ~b) | (~(a ^ b) & gt)        lt' = (~a & b) | (~(a ^ b) & lt)
 // -- one LOP3 per plane per predicate -- and accumulated per class with POPC.  Ties set
 // neither bit, padding cells tie everywhere, exactly the reference's "add to neither".
@@ -41,39 +43,61 @@ col_nonzero_kernel(const T *__restrict__ x, int64_t ld, int64_t n_rows, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------
-// bit-slice: rank[32W][G] -> planes[NB][W][B][64]
+// orbits[g] = OR over all cell slots of rank[slot][g]: bit_length(orbits[g]) = planes gene g needs
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes, int n_words, int n_planes,
-                uint32_t *__restrict__ planes) {
-    const int w = blockIdx.x;
+col_or_kernel(const uint16_t *__restrict__ rank, int64_t n_slots, int n_genes, uint32_t *__restrict__ orbits) {
+    const int g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_genes) return;
+    uint32_t v = 0;
+    for (int64_t s = blockIdx.y; s < n_slots; s += gridDim.y) v |= rank[s * n_genes + g];
+    if (v) atomicOr(orbits + g, v);
+}
+
+// ------------------------------------------------------------------------------------------
+// bit-slice: rank[32W][G] -> per gene block nb (64 gene POSITIONS, genes sorted by the planes they need):
+//   planes[blk_off[nb] + (q * W + w) * 64 + (position & 63)]
+//     q <  Bn            low plane q   (bit q of the rank)
+//     q >= Bn            suffix plane S_j, j = q - Bn + 1 (1 <= j < Bn): OR of the planes >= j, i.e. "rank >= 2^j"
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes, int n_words,
+                const int32_t *__restrict__ pos_gene, const int64_t *__restrict__ blk_off,
+                const int32_t *__restrict__ blk_bits, uint32_t *__restrict__ planes) {
     const int lane = threadIdx.x & 31;
-    const int g = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 32 + lane;  // this lane's gene
-    if (g - lane >= n_genes) return;
-    uint32_t r[32];
-    const uint16_t *src = rank + (int64_t)w * 32 * rank_ld + g;
+    const int pos = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + lane;  // this lane's gene position
+    if (pos - lane >= n_genes) return;
+    const int g = pos < n_genes ? __ldg(pos_gene + pos) : 0;
+    const int nb = pos >> 6, bn = __ldg(blk_bits + nb);
+    const int64_t ps = (int64_t)n_words * 64;  // words per plane
+    for (int w = blockIdx.y; w < n_words; w += gridDim.y) {
+        uint32_t r[32];
+        const uint16_t *src = rank + (int64_t)w * 32 * rank_ld + g;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) r[c] = (g < n_genes) ? (uint32_t)src[(int64_t)c * rank_ld] : 0u;
-    uint32_t *dst = planes + (((int64_t)(g >> 6) * n_words + w) * n_planes) * 64 + (g & 63);
-    for (int p = 0; p < n_planes; ++p) {
-        uint32_t word = 0;
+        for (int c = 0; c < 32; ++c) r[c] = (pos < n_genes) ? (uint32_t)src[(int64_t)c * rank_ld] : 0u;
+        uint32_t *dst = planes + __ldg(blk_off + nb) + (int64_t)w * 64 + (pos & 63);
+        uint32_t suffix = 0;
+        for (int p = bn - 1; p >= 0; --p) {
+            uint32_t word = 0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) word |= ((r[c] >> p) & 1u) << c;
-        dst[(int64_t)p * 64] = word;
+            for (int c = 0; c < 32; ++c) word |= ((r[c] >> p) & 1u) << c;
+            dst[p * ps] = word;
+            suffix |= word;
+            if (p >= 1) dst[(bn + p - 1) * ps] = suffix;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // pair kernel
 // ------------------------------------------------------------------------------------------
-#ifndef PP_TILE_A
-#define PP_TILE_A 128
-#endif
-constexpr int TILE_A = PP_TILE_A;     // a-genes per CTA = 1 or 2 gene blocks
+constexpr int TILE_A = 128;  // a-gene positions per CTA = 2 gene blocks
 constexpr int A_BLOCKS = TILE_A / 64;
-constexpr int CTAS_PER_SM = TILE_A == 64 ? 2 : 1;  // 64 x 64 tiles: two CTAs share an SM, one can be in sweep 2
-constexpr int TILE_B = 64;   // b-genes per CTA = 1 gene block
+constexpr int TILE_B = 64;   // b-gene positions per CTA = 1 gene block
 constexpr int STAGES = 3;
+constexpr int MAX_PLANES = 16;         // ranks are u16
+constexpr int STAGE_PLANE_WORDS = 72;  // planes x cell words per gene block and stage: 3 x 72 x 256 B = 54 KB per stage
+__host__ __device__ constexpr int words_per_chunk(int bp) { return bp <= 4 ? 16 : STAGE_PLANE_WORDS / bp; }
 
 // a * b + c as an IMAD: keeps the counter updates off the ALU pipe, which the LOP3 stream saturates
 __device__ __forceinline__ uint32_t fma_pipe_mad(uint32_t a, uint32_t b, uint32_t c) {
@@ -97,183 +121,189 @@ struct Chunk {  // a run of cell words of one class
     int32_t pad;
 };
 
-struct PairParams {
-    const uint32_t *planes;
-    const Chunk *chunks;
-    const int2 *tiles;       // (ta, tb) per CTA
-    const int32_t *thr;      // per class, clipped to int32
-    const int32_t *max_pos_dn;  // per class n_k - thr_k: num_neg >= thr_k needs num_pos <= this
-    unsigned long long *out; // compacted (key << 16 | class)
-    unsigned long long *out_count;
-    unsigned long long out_cap;
-    int n_genes, n_words, n_planes, n_chunks, n_classes, wc_max;
+struct TileDesc {
+    int32_t ta, tb;  // a-tile (128 positions) and b-block (64 positions), tb >= 2 * ta
+    int32_t bp;      // planes compared: m low planes, plus one "rank >= 2^m" plane when the two sides differ
+    int32_t m;       // min(planes of the a-tile, planes of the b-block)
 };
 
-// Two sweeps over the cell words of a 128 x 64 gene tile, one kernel.
-//  Sweep 1 (all pairs): only num_pos = #(x[g1] > x[g2]) is accumulated -- ONE LOP3 per plane per pair and word -- and
-//     thresholded per class (nup, up_idx).  The decision of sandbag.py:192-197 can only emit when nup == 1 or
-//     nup == C-1; and since num_pos + num_neg <= n_k, a class can only count as "down" if num_pos <= n_k - thr_k
-//     (ncd = number of such classes): emitting needs ncd >= C-1 (first branch) or ncd >= 1 (second).  Pairs passing
-//     these necessary conditions are the "candidates" -- well under 1 % of the pairs on expression data.
+struct PairParams {
+    const uint32_t *planes;
+    const uint32_t *zeros;      // words_per_chunk(1) * 64 zero words: source of planes a block does not have
+    const int64_t *blk_off;     // [gene blocks] first word of the block's planes
+    const int32_t *blk_bits;    // [gene blocks] Bn = planes the block's genes need (>= 1)
+    const int32_t *pos_gene;    // [n_genes] kept-gene index sitting at a position
+    const Chunk *chunks;        // chunk tables, one per plane count
+    const TileDesc *tiles;      // per CTA
+    const int32_t *thr;         // per class, clipped to int32
+    const int32_t *max_pos_dn;  // per class n_k - thr_k: num_neg >= thr_k needs num_pos <= this
+    unsigned long long *out;    // compacted (key << 16 | class)
+    unsigned long long *out_count;
+    unsigned long long out_cap;
+    int n_genes, n_words, n_classes;
+    int32_t chunk_off[MAX_PLANES + 1], chunk_cnt[MAX_PLANES + 1];  // table of plane count bp
+};
+
+// Two sweeps over the cell words of a 128 x 64 tile of gene positions, one kernel.
+//  Sweep 1 (all pairs): only #(x[a] > x[b]) is accumulated -- ONE LOP3 per plane per pair and word -- and
+//     thresholded per class (nup, up_idx).  The decision of sandbag.py:192-197 can only emit when one of the two
+//     counts reaches its threshold in exactly 1 or exactly C-1 classes; and since num_pos + num_neg <= n_k, the other
+//     count can only reach thr_k if this one is <= n_k - thr_k (ncd = number of such classes): emitting needs
+//     ncd >= C-1 resp. ncd >= 1.  Pairs passing these necessary conditions are the "candidates" -- well under 1 %
+//     of the pairs on expression data.  The conditions are symmetric in the two counts, so they hold whichever of
+//     the two genes is the reference's g1.
 //  Sweep 2 (candidates only, 512 per round = one per consumer thread): the same operand stream is replayed and
-//     num_neg = #(x[g1] < x[g2]) is accumulated for the candidates, thresholded (ndn, dn_idx), and the decision emits.
+//     #(x[a] < x[b]) is accumulated for the candidates, thresholded (ndn, dn_idx), and the decision emits.
 // So the second predicate of sandbag.py:179-182 is evaluated exactly where it can matter, halving the LOP3 work.
 // Per-pair counters are plain 32-bit registers (any class size), the state packs nup | up_idx << 16 (<= 65 534 classes).
 //
-// TI x TJ = per-thread register tile of gene pairs (4 x 4), consumer thread grid (128/TI) x (64/TJ) = 512 threads.
-// Warps 0 .. 15 consume; one extra warp is the TMA producer.  full[s] (1 arrival + transaction bytes) hands a stage to
-// the consumers, empty[s] (one arrival per consumer warp) hands it back, so the consumer warps never meet at a CTA-wide
-// barrier inside a sweep and drift up to STAGES-1 chunks apart.
-constexpr int CAND_PER_ROUND = (TILE_A / 4) * (TILE_B / 4);  // = consumer threads
+// Planes.  Gene positions are sorted by the number of planes their ranks need, so a tile compares only
+// m = min(planes of its a-side, planes of its b-side) low planes; if the sides differ, the wider side adds its
+// "rank >= 2^m" plane (the narrower side has no such bits): in the recurrence that plane simply is plane m.
+// BP = planes compared is a template parameter of the tile body (plane loops fully unrolled); the kernel dispatches
+// per tile.
+//
+// 4 x 4 = per-thread register tile of gene pairs, consumer thread grid 32 x 16 = 512 threads.
+// Warps 0 .. 15 consume; one extra warp is the TMA producer: per chunk of cell words and per (block, plane) one 1-D
+// bulk copy into the stage [block][plane][word][64 genes].  full[s] (1 arrival + transaction bytes) hands a stage to
+// the consumers, empty[s] (one arrival per consumer warp) hands it back, so the consumer warps never meet at a
+// CTA-wide barrier inside a sweep and drift up to STAGES-1 chunks apart.
+constexpr int TI = 4, TJ = 4;
+constexpr int NTJ = TILE_B / TJ;
+constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;  // consumer threads
+constexpr int CONSUMER_WARPS = PAIR_THREADS / 32;
+constexpr int CAND_PER_ROUND = PAIR_THREADS;  // one candidate per consumer thread and round
+constexpr int CHUNK_CACHE = 192;              // chunk descriptors kept in shared memory (global beyond that)
 
-// BP = number of bit planes when known at compile time (plane loops fully unrolled), 0 = run-time P.n_planes.
-template <int TI, int TJ, int BP>
-__global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_SM) pair_kernel(const PairParams P) {
-    constexpr int NTJ = TILE_B / TJ;
-    constexpr int PAIR_THREADS = (TILE_A / TI) * NTJ;  // consumer threads
-    constexpr int CONSUMER_WARPS = PAIR_THREADS / 32;
-    static_assert(TJ == 4 && (TI == 4 || TI == 8), "shared loads below are written for these tiles");
-    static_assert(PAIR_THREADS == CAND_PER_ROUND, "one candidate per consumer thread and round");
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    __shared__ uint2 cand[CAND_PER_ROUND];  // .x = la | lb << 8 (tile-local genes), .y = nup | up_idx << 16
-    __shared__ int s_total;
-    constexpr int CHUNK_CACHE = 192;         // chunk descriptors kept in shared memory (global beyond that)
-    __shared__ Chunk s_chunks[CHUNK_CACHE];
+// shared state of a pair_kernel CTA (namespace scope so that the tile bodies address it directly)
+extern __shared__ __align__(128) uint8_t pk_stage_raw[];  // dynamic: STAGES stages of [block][plane][word][64]
+__shared__ __align__(8) uint64_t pk_full_bar[STAGES];
+__shared__ __align__(8) uint64_t pk_empty_bar[STAGES];
+__shared__ uint2 pk_cand[CAND_PER_ROUND];  // .x = la | lb << 8 (tile-local positions), .y = nup | up_idx << 16
+__shared__ int pk_total;
+__shared__ Chunk pk_chunks[CHUNK_CACHE];
 
+template <int BP>
+__device__ __forceinline__ void tile_body(const PairParams &P, const TileDesc td) {
+    constexpr int WC = words_per_chunk(BP);
+    constexpr uint32_t BLK_WORDS = (uint32_t)BP * WC * 64;  // u32 per gene block per stage
+    constexpr uint32_t STAGE_WORDS = (A_BLOCKS + 1) * BLK_WORDS;
+    constexpr int PLANE = WC * 64;  // u32 between two planes of a block inside a stage
     const int tid = threadIdx.x;
     const int ti = tid / NTJ, tj = tid % NTJ;
-    const int2 tile = P.tiles[blockIdx.x];
-    const int B = BP > 0 ? BP : P.n_planes;
-    const int blk_words = P.wc_max * B * 64;  // u32 per gene block per stage
-    const uint32_t stage_words = (uint32_t)(A_BLOCKS + 1) * blk_words;
-    uint32_t *smem = reinterpret_cast<uint32_t *>(smem_raw);
+    const int n_chunks = P.chunk_cnt[BP];
+    uint32_t *smem = reinterpret_cast<uint32_t *>(pk_stage_raw);
 
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CONSUMER_WARPS);
-        }
-        fence_mbar_init();
-        s_total = 0;
-    }
-    for (int c = tid; c < min(P.n_chunks, CHUNK_CACHE); c += blockDim.x) s_chunks[c] = P.chunks[c];
+    for (int c = tid; c < min(n_chunks, CHUNK_CACHE); c += blockDim.x) pk_chunks[c] = P.chunks[P.chunk_off[BP] + c];
     __syncthreads();
-    auto chunk_at = [&](int c) -> Chunk { return c < CHUNK_CACHE ? s_chunks[c] : P.chunks[c]; };
+    auto chunk_at = [&](int c) -> Chunk { return c < CHUNK_CACHE ? pk_chunks[c] : P.chunks[P.chunk_off[BP] + c]; };
 
-    const int64_t blk_stride = (int64_t)P.n_words * B * 64;  // u32 per gene block in HBM
-    const uint32_t *gA0 = P.planes + (int64_t)(A_BLOCKS * tile.x) * blk_stride;
-    const uint32_t *gA1 = gA0 + blk_stride;
-    const uint32_t *gB = P.planes + (int64_t)tile.y * blk_stride;
-
-    if (tid >= PAIR_THREADS) {  // ---- producer warp: one elected lane streams the chunk sequence once per sweep
-        int q = 0;              // running chunk number over all sweeps (stage = q % STAGES)
+    if (tid >= PAIR_THREADS) {  // ---- producer warp: streams the chunk sequence once per sweep
+        const int lane = tid - PAIR_THREADS;
+        // copy i = (block i / BP, plane i % BP) of every chunk belongs to lane i % 32
+        constexpr int N_COPIES = (A_BLOCKS + 1) * BP, PER_LANE = (N_COPIES + 31) / 32;
+        const uint32_t *src[PER_LANE];
+        bool real[PER_LANE];
+#pragma unroll
+        for (int j = 0; j < PER_LANE; ++j) {
+            const int i = lane + 32 * j;
+            src[j] = P.zeros;
+            real[j] = false;
+            if (i < N_COPIES) {
+                const int blk = i / BP, q = i % BP;
+                const int nb = blk < A_BLOCKS ? A_BLOCKS * td.ta + blk : td.tb;
+                const int bn = __ldg(P.blk_bits + nb);
+                int plane = -1;
+                if (q < td.m) {
+                    if (q < bn) plane = q;
+                } else if (bn > td.m) {
+                    plane = bn + td.m - 1;  // suffix plane S_m
+                }
+                if (plane >= 0) {
+                    src[j] = P.planes + __ldg(P.blk_off + nb) + (int64_t)plane * P.n_words * 64;
+                    real[j] = true;
+                }
+            }
+        }
+        int q = 0;  // running chunk number over all sweeps (stage = q % STAGES)
         auto stream_sweep = [&]() {
-            for (int c = 0; c < P.n_chunks; ++c, ++q) {
+            for (int c = 0; c < n_chunks; ++c, ++q) {
                 const int s = q % STAGES;
-                if (q >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(q / STAGES - 1) & 1u);  // consumers released it
                 const Chunk ch = chunk_at(c);
-                uint32_t *dst = smem + (size_t)s * stage_words;
-                const uint32_t bytes = (uint32_t)ch.n_words * B * 64 * 4;
-                const int64_t off = (int64_t)ch.w_begin * B * 64;
-                mbar_arrive_expect_tx(&full_bar[s], (A_BLOCKS + 1) * bytes);
-                bulk_g2s(dst, gA0 + off, bytes, &full_bar[s]);
-                if (A_BLOCKS == 2) bulk_g2s(dst + blk_words, gA1 + off, bytes, &full_bar[s]);
-                bulk_g2s(dst + A_BLOCKS * blk_words, gB + off, bytes, &full_bar[s]);
+                const uint32_t bytes = (uint32_t)ch.n_words * 64 * 4;
+                if (lane == 0) {
+                    if (q >= STAGES) mbar_wait(&pk_empty_bar[s], (uint32_t)(q / STAGES - 1) & 1u);  // consumers released it
+                    mbar_arrive_expect_tx(&pk_full_bar[s], N_COPIES * bytes);
+                }
+                __syncwarp();
+                uint32_t *dst = smem + (size_t)s * STAGE_WORDS;
+#pragma unroll
+                for (int j = 0; j < PER_LANE; ++j) {
+                    const int i = lane + 32 * j;
+                    if (i < N_COPIES)
+                        bulk_g2s(dst + i * PLANE, src[j] + (real[j] ? (int64_t)ch.w_begin * 64 : 0), bytes, &pk_full_bar[s]);
+                }
             }
         };
-        if (tid == PAIR_THREADS) stream_sweep();
+        stream_sweep();
         __syncthreads();  // (A) sweep 1 is consumed and the candidates are counted
-        const int rounds = (s_total + CAND_PER_ROUND - 1) / CAND_PER_ROUND;
-        if (tid == PAIR_THREADS)
-            for (int r = 0; r < rounds; ++r) stream_sweep();
+        const int rounds = (pk_total + CAND_PER_ROUND - 1) / CAND_PER_ROUND;
+        for (int r = 0; r < rounds; ++r) stream_sweep();
         return;
     }
 
-    // =============================== sweep 1: num_pos of every pair of the tile
+    // =============================== sweep 1: #(a > b) of every pair of the tile
     uint32_t acc[TI][TJ], st[TI][TJ], ncd[TI][TJ];
 #pragma unroll
     for (int i = 0; i < TI; ++i)
 #pragma unroll
         for (int j = 0; j < TJ; ++j) acc[i][j] = 0, st[i][j] = 0, ncd[i][j] = 0;
 
-    const int la = ti * TI;  // first local a-gene (0..127), never straddles a 64-gene block
-    const uint32_t a_off = (uint32_t)(la >> 6) * blk_words + (la & 63);
-    const uint32_t b_off = (uint32_t)A_BLOCKS * blk_words + tj * TJ;
+    const int la = ti * TI;  // first local a-position (0..127), never straddles a 64-gene block
+    const uint32_t a_off = (uint32_t)(la >> 6) * BLK_WORDS + (la & 63);
+    const uint32_t b_off = (uint32_t)A_BLOCKS * BLK_WORDS + tj * TJ;
     int q = 0;
 
-    for (int c = 0; c < P.n_chunks; ++c, ++q) {
+    for (int c = 0; c < n_chunks; ++c, ++q) {
         const int s = q % STAGES;
         const Chunk ch = chunk_at(c);
-        mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
-        const uint32_t *sa = smem + (size_t)s * stage_words + a_off;
-        const uint32_t *sb = smem + (size_t)s * stage_words + b_off;
-        if (BP > 0) {
-            // compile-time plane count: software-pipelined -- the operands of plane p+1 (or of plane 0 of the next
-            // word) are requested before the 16 LOP3 of plane p issue, so the LDS latency hides behind them
-            uint32_t a[TI], b[TJ];
-            load_words<TI>(sa, a);
-            load_words<TJ>(sb, b);
-            for (int w = 0; w < ch.n_words; ++w) {
-                uint32_t gt[TI][TJ];
+        mbar_wait(&pk_full_bar[s], (uint32_t)(q / STAGES) & 1u);
+        const uint32_t *sa = smem + (size_t)s * STAGE_WORDS + a_off;
+        const uint32_t *sb = smem + (size_t)s * STAGE_WORDS + b_off;
+        // software-pipelined: the operands of plane p+1 (or of plane 0 of the next word) are requested before the
+        // 16 LOP3 of plane p issue, so the LDS latency hides behind them
+        uint32_t a[TI], b[TJ];
+        load_words<TI>(sa, a);
+        load_words<TJ>(sb, b);
+        for (int w = 0; w < ch.n_words; ++w) {
+            uint32_t gt[TI][TJ];
 #pragma unroll
-                for (int p = 0; p < (BP > 0 ? BP : 1); ++p) {
-                    uint32_t an[TI], bn[TJ];
-                    const int nxt = (p + 1 < BP) ? (p + 1) * 64 : BP * 64;  // next plane, or plane 0 of the next word
-                    if (p + 1 < BP || w + 1 < ch.n_words) {
-                        load_words<TI>(sa + nxt, an);
-                        load_words<TJ>(sb + nxt, bn);
-                    }
-#pragma unroll
-                    for (int i = 0; i < TI; ++i)
-#pragma unroll
-                        for (int j = 0; j < TJ; ++j)
-                            gt[i][j] = (p == 0) ? (a[i] & ~b[j]) : lop3_gt(a[i], b[j], gt[i][j]);
-#pragma unroll
-                    for (int i = 0; i < TI; ++i) a[i] = an[i];
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) b[j] = bn[j];
+            for (int p = 0; p < BP; ++p) {
+                uint32_t an[TI], bn[TJ];
+                const int nxt = (p + 1 < BP) ? (p + 1) * PLANE : 64;  // next plane, or plane 0 of the next word
+                if (p + 1 < BP || w + 1 < ch.n_words) {
+                    load_words<TI>(sa + nxt, an);
+                    load_words<TJ>(sb + nxt, bn);
                 }
 #pragma unroll
                 for (int i = 0; i < TI; ++i)
 #pragma unroll
-                    for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
-                sa += BP * 64;
-                sb += BP * 64;
+                    for (int j = 0; j < TJ; ++j)
+                        gt[i][j] = (p == 0) ? (a[i] & ~b[j]) : lop3_gt(a[i], b[j], gt[i][j]);
+#pragma unroll
+                for (int i = 0; i < TI; ++i) a[i] = an[i];
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) b[j] = bn[j];
             }
-        } else {
-            for (int w = 0; w < ch.n_words; ++w) {
-                uint32_t gt[TI][TJ];
-                {
-                    uint32_t a[TI], b[TJ];
-                    load_words<TI>(sa, a);
-                    load_words<TJ>(sb, b);
 #pragma unroll
-                    for (int i = 0; i < TI; ++i)
+            for (int i = 0; i < TI; ++i)
 #pragma unroll
-                        for (int j = 0; j < TJ; ++j) gt[i][j] = a[i] & ~b[j];
-                }
-#pragma unroll 4
-                for (int p = 1; p < B; ++p) {
-                    uint32_t a[TI], b[TJ];
-                    load_words<TI>(sa + p * 64, a);
-                    load_words<TJ>(sb + p * 64, b);
-#pragma unroll
-                    for (int i = 0; i < TI; ++i)
-#pragma unroll
-                        for (int j = 0; j < TJ; ++j) gt[i][j] = lop3_gt(a[i], b[j], gt[i][j]);
-                }
-#pragma unroll
-                for (int i = 0; i < TI; ++i)
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
-                sa += B * 64;
-                sb += B * 64;
-            }
+                for (int j = 0; j < TJ; ++j) acc[i][j] = fma_pipe_mad((uint32_t)__popc(gt[i][j]), 1u, acc[i][j]);
+            sa += 64;
+            sb += 64;
         }
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done reading stage s
+        if ((tid & 31) == 0) mbar_arrive(&pk_empty_bar[s]);  // this warp is done reading stage s
         if (ch.class_end >= 0) {  // CTA-uniform: `num_pos[i] >= thresholds[i]` of sandbag.py:185-187, last class wins
             const uint32_t k = (uint32_t)ch.class_end;
             const int64_t thr = (int64_t)__ldg(P.thr + k), mpd = (int64_t)__ldg(P.max_pos_dn + k);
@@ -288,8 +318,8 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_S
         }
     }
 
-    // =============================== candidates: pairs whose decision can still emit (nup == 1 or nup == C-1)
-    const int ga0 = tile.x * TILE_A + la, gb0 = tile.y * TILE_B + tj * TJ;
+    // =============================== candidates: pairs whose decision can still emit
+    const int pa0 = td.ta * TILE_A + la, pb0 = td.tb * TILE_B + tj * TJ;
     const uint32_t C = (uint32_t)P.n_classes;
     const int lane = tid & 31;
     uint32_t cmask = 0;
@@ -299,14 +329,14 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_S
         for (int j = 0; j < TJ; ++j) {
             const uint32_t nup = st[i][j] & 0xffffu;
             const bool can = (nup == 1u) ? (ncd[i][j] >= C - 1u) : (nup == C - 1u && ncd[i][j] >= 1u);
-            if (ga0 + i < gb0 + j && gb0 + j < P.n_genes && can) cmask |= 1u << (i * TJ + j);
+            if (pa0 + i < pb0 + j && pb0 + j < P.n_genes && can) cmask |= 1u << (i * TJ + j);
         }
-    const int my_first = cmask ? atomicAdd(&s_total, __popc(cmask)) : 0;  // tickets of this thread's candidates
+    const int my_first = cmask ? atomicAdd(&pk_total, __popc(cmask)) : 0;  // tickets of this thread's candidates
     __syncthreads();  // (A)
-    const int total = s_total;
+    const int total = pk_total;
     const int rounds = (total + CAND_PER_ROUND - 1) / CAND_PER_ROUND;
 
-    // =============================== sweep 2: num_neg of the candidates, CAND_PER_ROUND per replay of the stream
+    // =============================== sweep 2: #(a < b) of the candidates, CAND_PER_ROUND per replay of the stream
     for (int r = 0; r < rounds; ++r) {
         {
             int t = my_first;
@@ -316,33 +346,34 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_S
                 for (int j = 0; j < TJ; ++j)
                     if (cmask & (1u << (i * TJ + j))) {
                         if (t / CAND_PER_ROUND == r)
-                            cand[t % CAND_PER_ROUND] = make_uint2((uint32_t)(la + i) | ((uint32_t)(tj * TJ + j) << 8), st[i][j]);
+                            pk_cand[t % CAND_PER_ROUND] = make_uint2((uint32_t)(la + i) | ((uint32_t)(tj * TJ + j) << 8), st[i][j]);
                         ++t;
                     }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(PAIR_THREADS) : "memory");  // consumers only: the list is complete
         const bool have = tid < min(CAND_PER_ROUND, total - r * CAND_PER_ROUND);
-        const uint2 me = have ? cand[tid] : make_uint2(0u, 0u);
+        const uint2 me = have ? pk_cand[tid] : make_uint2(0u, 0u);
         const uint32_t ca = me.x & 0xffu, cb = me.x >> 8;
-        const uint32_t ca_off = (ca >> 6) * blk_words + (ca & 63), cb_off = (uint32_t)A_BLOCKS * blk_words + cb;
+        const uint32_t ca_off = (ca >> 6) * BLK_WORDS + (ca & 63), cb_off = (uint32_t)A_BLOCKS * BLK_WORDS + cb;
         uint32_t neg = 0, ndn = 0, dn_idx = 0;
-        for (int c = 0; c < P.n_chunks; ++c, ++q) {
+        for (int c = 0; c < n_chunks; ++c, ++q) {
             const int s = q % STAGES;
             const Chunk ch = chunk_at(c);
-            mbar_wait(&full_bar[s], (uint32_t)(q / STAGES) & 1u);
+            mbar_wait(&pk_full_bar[s], (uint32_t)(q / STAGES) & 1u);
             if (have) {
-                const uint32_t *sa = smem + (size_t)s * stage_words + ca_off;
-                const uint32_t *sb = smem + (size_t)s * stage_words + cb_off;
+                const uint32_t *sa = smem + (size_t)s * STAGE_WORDS + ca_off;
+                const uint32_t *sb = smem + (size_t)s * STAGE_WORDS + cb_off;
                 for (int w = 0; w < ch.n_words; ++w) {
                     uint32_t lt = 0;
-                    for (int p = 0; p < B; ++p) lt = lop3_lt(sa[p * 64], sb[p * 64], lt);
+#pragma unroll
+                    for (int p = 0; p < BP; ++p) lt = lop3_lt(sa[p * PLANE], sb[p * PLANE], lt);
                     neg += __popc(lt);
-                    sa += B * 64;
-                    sb += B * 64;
+                    sa += 64;
+                    sb += 64;
                 }
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);
+            if ((tid & 31) == 0) mbar_arrive(&pk_empty_bar[s]);
             if (ch.class_end >= 0) {  // `num_neg[i] >= thresholds[i]` of sandbag.py:188-190
                 if ((int64_t)neg >= (int64_t)__ldg(P.thr + ch.class_end)) {
                     ++ndn;
@@ -351,22 +382,26 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_S
                 neg = 0;
             }
         }
-        // decision of sandbag.py:192-197 + warp-aggregated compaction
-        const uint32_t nup = me.y & 0xffffu, up_idx = me.y >> 16;
-        const unsigned long long ga = (unsigned long long)(tile.x * TILE_A + (int)ca);
-        const unsigned long long gb = (unsigned long long)(tile.y * TILE_B + (int)cb);
+        // decision of sandbag.py:192-197 + warp-aggregated compaction.  The reference's g1 is the gene with the
+        // smaller index: if that is the b-position, the two counts (and their class tallies) swap roles.
         unsigned long long key = 0;
         bool emit = false;
         if (have) {
+            const unsigned long long ga = (unsigned long long)__ldg(P.pos_gene + td.ta * TILE_A + (int)ca);
+            const unsigned long long gb = (unsigned long long)__ldg(P.pos_gene + td.tb * TILE_B + (int)cb);
+            const bool a_first = ga < gb;
+            const unsigned long long g1 = a_first ? ga : gb, g2 = a_first ? gb : ga;
+            const uint32_t nup = a_first ? (me.y & 0xffffu) : ndn, up_idx = a_first ? (me.y >> 16) : dn_idx;
+            const uint32_t ndn_c = a_first ? ndn : (me.y & 0xffffu), dn_idx_c = a_first ? dn_idx : (me.y >> 16);
             if (nup == 1u) {
-                if (ndn == C - 1u) {
+                if (ndn_c == C - 1u) {
                     emit = true;
-                    key = ((ga * P.n_genes + gb) << 16) | up_idx;
+                    key = ((g1 * P.n_genes + g2) << 16) | up_idx;
                 }
-            } else if (ndn == 1u) {
+            } else if (ndn_c == 1u) {
                 if (nup == C - 1u) {
                     emit = true;
-                    key = ((gb * P.n_genes + ga) << 16) | dn_idx;
+                    key = ((g2 * P.n_genes + g1) << 16) | dn_idx_c;
                 }
             }
         }
@@ -382,24 +417,57 @@ __global__ void __launch_bounds__((TILE_A / TI) * (TILE_B / TJ) + 32, CTAS_PER_S
     }
 }
 
+__global__ void __launch_bounds__(PAIR_THREADS + 32, 1) pair_kernel(const PairParams P) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&pk_full_bar[s], 1);
+            mbar_init(&pk_empty_bar[s], CONSUMER_WARPS);
+        }
+        fence_mbar_init();
+        pk_total = 0;
+    }
+    const TileDesc td = P.tiles[blockIdx.x];
+    switch (td.bp) {  // tile_body starts with a CTA barrier that also publishes the mbarrier initialisation
+        case 1: tile_body<1>(P, td); break;
+        case 2: tile_body<2>(P, td); break;
+        case 3: tile_body<3>(P, td); break;
+        case 4: tile_body<4>(P, td); break;
+        case 5: tile_body<5>(P, td); break;
+        case 6: tile_body<6>(P, td); break;
+        case 7: tile_body<7>(P, td); break;
+        case 8: tile_body<8>(P, td); break;
+        case 9: tile_body<9>(P, td); break;
+        case 10: tile_body<10>(P, td); break;
+        case 11: tile_body<11>(P, td); break;
+        case 12: tile_body<12>(P, td); break;
+        case 13: tile_body<13>(P, td); break;
+        case 14: tile_body<14>(P, td); break;
+        case 15: tile_body<15>(P, td); break;
+        default: tile_body<16>(P, td); break;
+    }
+}
+
 // per-class counters of selected pairs straight from the planes (one warp per probe pair)
-__global__ void probe_kernel(const uint32_t *__restrict__ planes, const Chunk *__restrict__ chunks, int n_chunks,
-                             int n_words, int n_planes, int n_classes, const int64_t *__restrict__ pairs,
-                             int64_t n_probe, int32_t *__restrict__ pos_out, int32_t *__restrict__ neg_out) {
+__global__ void probe_kernel(const uint32_t *__restrict__ planes, const int64_t *__restrict__ blk_off,
+                             const int32_t *__restrict__ blk_bits, const int32_t *__restrict__ gene_pos,
+                             const Chunk *__restrict__ chunks, int n_chunks, int n_words, int n_classes,
+                             const int64_t *__restrict__ pairs, int64_t n_probe, int32_t *__restrict__ pos_out,
+                             int32_t *__restrict__ neg_out) {
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= n_probe) return;
-    const int g1 = (int)pairs[2 * q], g2 = (int)pairs[2 * q + 1];
-    const int64_t bs = (int64_t)n_words * n_planes * 64;
-    const uint32_t *pa = planes + (int64_t)(g1 >> 6) * bs + (g1 & 63);
-    const uint32_t *pb = planes + (int64_t)(g2 >> 6) * bs + (g2 & 63);
+    const int p1 = gene_pos[(int)pairs[2 * q]], p2 = gene_pos[(int)pairs[2 * q + 1]];
+    const int b1 = blk_bits[p1 >> 6], b2 = blk_bits[p2 >> 6];
+    const uint32_t *pa = planes + blk_off[p1 >> 6] + (p1 & 63);
+    const uint32_t *pb = planes + blk_off[p2 >> 6] + (p2 & 63);
+    const int64_t ps = (int64_t)n_words * 64;
     int pos = 0, neg = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const Chunk ch = chunks[c];
         for (int w = ch.w_begin + lane; w < ch.w_begin + ch.n_words; w += 32) {
             uint32_t gt = 0, lt = 0;
-            for (int p = 0; p < n_planes; ++p) {
-                const uint32_t a = pa[((int64_t)w * n_planes + p) * 64], b = pb[((int64_t)w * n_planes + p) * 64];
+            for (int p = 0; p < max(b1, b2); ++p) {
+                const uint32_t a = p < b1 ? pa[p * ps + (int64_t)w * 64] : 0u, b = p < b2 ? pb[p * ps + (int64_t)w * 64] : 0u;
                 gt = lop3_gt(a, b, gt);
                 lt = lop3_lt(a, b, lt);
             }
@@ -710,51 +778,114 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const int B = std::max(1, bit_length64((uint64_t)flags[0]));
     ctx->tm.n_planes = B;
 
-    // ---- bit-slice
-    const size_t plane_words = (size_t)NB_alloc * W * B * 64;
-    if (!(s_planes = pp_slab(ctx, SLAB_PLANES, plane_words * 4))) return PP_ENOMEM;
-    PP_CUDA(cudaMemsetAsync(s_planes, 0, plane_words * 4, st));
+    // ---- planes every gene needs; gene positions sorted by it (widest first, so the expensive tiles start first)
+    DevBuf d_orbits;
+    PP_CUDA(d_orbits.alloc(sizeof(uint32_t) * n_genes, st));
+    PP_CUDA(cudaMemsetAsync(d_orbits.p, 0, sizeof(uint32_t) * n_genes, st));
     {
-        dim3 grid(W, (unsigned)((n_genes + 255) / 256));
-        bitslice_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_genes, (int)n_genes, W, B, (uint32_t *)s_planes);
+        dim3 grid((unsigned)((n_genes + 255) / 256), (unsigned)std::min<int64_t>(std::max<int64_t>(n_slots / 128, 1), 128));
+        col_or_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_slots, (int)n_genes, d_orbits.as<uint32_t>());
+        PP_CHECK_LAUNCH();
+    }
+    std::vector<uint32_t> orbits((size_t)n_genes);
+    PP_CUDA(cudaMemcpyAsync(orbits.data(), d_orbits.p, sizeof(uint32_t) * n_genes, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> pos_gene((size_t)n_genes), gene_pos((size_t)n_genes);
+    {
+        std::vector<int32_t> start(MAX_PLANES + 2, 0);  // counting sort by descending plane count, stable
+        for (int64_t g = 0; g < n_genes; ++g) ++start[MAX_PLANES - bit_length64(orbits[g]) + 1];
+        for (int i = 0; i <= MAX_PLANES; ++i) start[i + 1] += start[i];
+        for (int64_t g = 0; g < n_genes; ++g) {
+            const int32_t p = start[MAX_PLANES - bit_length64(orbits[g])]++;
+            pos_gene[p] = (int32_t)g;
+            gene_pos[g] = p;
+        }
+    }
+    std::vector<int32_t> blk_bits((size_t)NB_alloc, 1);
+    std::vector<int64_t> blk_off((size_t)NB_alloc, 0);
+    size_t plane_words = 0;
+    for (int nb = 0; nb < NB_alloc; ++nb) {
+        int bn = 1;
+        for (int64_t p = (int64_t)nb * 64; p < std::min<int64_t>((int64_t)nb * 64 + 64, n_genes); ++p)
+            bn = std::max(bn, bit_length64(orbits[pos_gene[p]]));
+        blk_bits[nb] = bn;
+        blk_off[nb] = (int64_t)plane_words;
+        plane_words += (size_t)(2 * bn - 1) * W * 64;  // bn low planes + suffix planes S_1 .. S_{bn-1}
+    }
+    const size_t zero_words = (size_t)words_per_chunk(1) * 64;
+    if (!(s_planes = pp_slab(ctx, SLAB_PLANES, (plane_words + zero_words) * 4))) return PP_ENOMEM;
+    PP_CUDA(cudaMemsetAsync(s_planes, 0, (plane_words + zero_words) * 4, st));
+    DevBuf d_pos_gene, d_gene_pos, d_blk_bits, d_blk_off;
+    PP_CUDA(d_pos_gene.alloc(sizeof(int32_t) * n_genes, st));
+    PP_CUDA(cudaMemcpyAsync(d_pos_gene.p, pos_gene.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_blk_bits.alloc(sizeof(int32_t) * NB_alloc, st));
+    PP_CUDA(cudaMemcpyAsync(d_blk_bits.p, blk_bits.data(), sizeof(int32_t) * NB_alloc, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_blk_off.alloc(sizeof(int64_t) * NB_alloc, st));
+    PP_CUDA(cudaMemcpyAsync(d_blk_off.p, blk_off.data(), sizeof(int64_t) * NB_alloc, cudaMemcpyHostToDevice, st));
+
+    // ---- bit-slice
+    {
+        dim3 grid((unsigned)((n_genes + 255) / 256), (unsigned)std::min(W, 32768));
+        bitslice_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_genes, (int)n_genes, W, d_pos_gene.as<int32_t>(),
+                                              d_blk_off.as<int64_t>(), d_blk_bits.as<int32_t>(), (uint32_t *)s_planes);
         PP_CHECK_LAUNCH();
     }
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
 
-    // ---- chunks (runs of <= wc_max words inside one class)
-    const int smem_budget = std::min(ctx->smem_optin, 227 * 1024) - 8192;  // static: barriers + candidate list
-    int wc_max = (smem_budget / CTAS_PER_SM - (CTAS_PER_SM > 1 ? 6144 : 0)) / (STAGES * (A_BLOCKS + 1) * B * 64 * 4);
-    wc_max = std::max(1, std::min(wc_max, 16));
-    const size_t dyn_smem = (size_t)STAGES * (A_BLOCKS + 1) * wc_max * B * 64 * 4;
-    std::vector<Chunk> chunks;
-    for (int k = 0; k < n_classes; ++k)
-        for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc_max) {
-            Chunk c;
-            c.w_begin = w;
-            c.n_words = std::min(wc_max, class_w0[k + 1] - w);
-            c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
-            c.pad = 0;
-            chunks.push_back(c);
-        }
-    // ---- tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain pairs g1 < g2)
+    // ---- tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain position pairs a < b)
     const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB;
-    std::vector<int2> tiles;
+    std::vector<TileDesc> tiles;
     int64_t t_index = 0, n_pairs_shard = 0;
+    double plane_pairs = 0.0;  // sum over the shard's gene pairs of the planes compared
+    bool bp_used[MAX_PLANES + 1] = {false};
     // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
     // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
     // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
-    constexpr int SUP_A = 8 * (128 / TILE_A), SUP_B = 18;
+    constexpr int SUP_A = 8, SUP_B = 18;
     for (int sa = 0; sa < TA; sa += SUP_A)
         for (int sb = A_BLOCKS * sa; sb < TB; sb += SUP_B)
             for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
                 for (int tb = std::max(sb, A_BLOCKS * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
                     if (t_index % n_shards != shard) continue;
-                    tiles.push_back(make_int2(ta, tb));
+                    TileDesc td;
+                    td.ta = ta;
+                    td.tb = tb;
+                    const int ba = std::max(blk_bits[A_BLOCKS * ta], blk_bits[A_BLOCKS * ta + 1]), bb = blk_bits[tb];
+                    td.m = std::min(ba, bb);
+                    td.bp = td.m + (ba != bb ? 1 : 0);
+                    bp_used[td.bp] = true;
+                    tiles.push_back(td);
                     const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
                     const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
-                    for (int64_t a = a0; a < a1; ++a) n_pairs_shard += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                    int64_t np_tile = 0;
+                    for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                    n_pairs_shard += np_tile;
+                    plane_pairs += (double)np_tile * td.bp;
                 }
     ctx->tm.n_units = n_pairs_shard;
+    ctx->tm.avg_planes = n_pairs_shard > 0 ? (float)(plane_pairs / (double)n_pairs_shard) : 0.f;
+
+    // ---- chunks (runs of <= words_per_chunk(bp) words inside one class), one table per plane count in use;
+    //      table 0 (one chunk per class) serves the probe kernel
+    std::vector<Chunk> chunks;
+    PairParams P;
+    for (int bp = 0; bp <= MAX_PLANES; ++bp) {
+        P.chunk_off[bp] = (int32_t)chunks.size();
+        P.chunk_cnt[bp] = 0;
+        if (bp > 0 && !bp_used[bp]) continue;
+        const int wc = bp == 0 ? W : words_per_chunk(bp);
+        for (int k = 0; k < n_classes; ++k)
+            for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc) {
+                Chunk c;
+                c.w_begin = w;
+                c.n_words = std::min(wc, class_w0[k + 1] - w);
+                c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
+                c.pad = 0;
+                chunks.push_back(c);
+            }
+        P.chunk_cnt[bp] = (int32_t)chunks.size() - P.chunk_off[bp];
+    }
+    const size_t dyn_smem = (size_t)STAGES * (A_BLOCKS + 1) * STAGE_PLANE_WORDS * 64 * 4;
     std::vector<int32_t> thr32(n_classes), mpd32(n_classes);
     for (int k = 0; k < n_classes; ++k) {
         thr32[k] = (int32_t)std::max<int64_t>(INT32_MIN, std::min<int64_t>(INT32_MAX, thresholds[k]));
@@ -763,8 +894,8 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
 
     PP_CUDA(d_chunks.alloc(sizeof(Chunk) * chunks.size(), st));
     PP_CUDA(cudaMemcpyAsync(d_chunks.p, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, st));
-    PP_CUDA(d_tiles.alloc(sizeof(int2) * tiles.size(), st));
-    PP_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_tiles.alloc(sizeof(TileDesc) * std::max<size_t>(tiles.size(), 1), st));
+    PP_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), sizeof(TileDesc) * tiles.size(), cudaMemcpyHostToDevice, st));
     PP_CUDA(d_thr.alloc(sizeof(int32_t) * n_classes, st));
     PP_CUDA(cudaMemcpyAsync(d_thr.p, thr32.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
     DevBuf d_mpd;
@@ -775,24 +906,18 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     unsigned long long cap = (unsigned long long)std::min<int64_t>(std::max<int64_t>(n_pairs_shard, 1),
                                                                      std::max<int64_t>(1 << 22, n_pairs_shard / 16));
     unsigned long long count = 0;
-    // 4x4 register tiles, 512 threads (16 warps/SM): measured 75.0 ms on cfg3 vs 87.8 ms for 8x4 / 256 threads
-    // plane count known at compile time for 1..16 (fully unrolled plane loops)
-    typedef void (*PairFn)(const PairParams);
-    static const PairFn pair_fns[17] = {
-        pair_kernel<4, 4, 0>,  pair_kernel<4, 4, 1>,  pair_kernel<4, 4, 2>,  pair_kernel<4, 4, 3>,  pair_kernel<4, 4, 4>,
-        pair_kernel<4, 4, 5>,  pair_kernel<4, 4, 6>,  pair_kernel<4, 4, 7>,  pair_kernel<4, 4, 8>,  pair_kernel<4, 4, 9>,
-        pair_kernel<4, 4, 10>, pair_kernel<4, 4, 11>, pair_kernel<4, 4, 12>, pair_kernel<4, 4, 13>, pair_kernel<4, 4, 14>,
-        pair_kernel<4, 4, 15>, pair_kernel<4, 4, 16>};
-    const PairFn pair_fn = pair_fns[B <= 16 ? B : 0];
-    PP_CUDA(cudaFuncSetAttribute(pair_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!(s_out = pp_slab(ctx, SLAB_OUT, sizeof(unsigned long long) * cap))) return PP_ENOMEM;
         PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
         if (!tiles.empty()) {
-            PairParams P;
             P.planes = (uint32_t *)s_planes;
+            P.zeros = (uint32_t *)s_planes + plane_words;
+            P.blk_off = d_blk_off.as<int64_t>();
+            P.blk_bits = d_blk_bits.as<int32_t>();
+            P.pos_gene = d_pos_gene.as<int32_t>();
             P.chunks = d_chunks.as<Chunk>();
-            P.tiles = d_tiles.as<int2>();
+            P.tiles = d_tiles.as<TileDesc>();
             P.thr = d_thr.as<int32_t>();
             P.max_pos_dn = d_mpd.as<int32_t>();
             P.out = (unsigned long long *)s_out;
@@ -800,11 +925,8 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             P.out_cap = cap;
             P.n_genes = (int)n_genes;
             P.n_words = W;
-            P.n_planes = B;
-            P.n_chunks = (int)chunks.size();
             P.n_classes = n_classes;
-            P.wc_max = wc_max;
-            pair_fn<<<(unsigned)tiles.size(), CAND_PER_ROUND + 32, dyn_smem, st>>>(P);
+            pair_kernel<<<(unsigned)tiles.size(), PAIR_THREADS + 32, dyn_smem, st>>>(P);
             PP_CHECK_LAUNCH();
         }
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -827,10 +949,12 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(d_pos.alloc(cb, st));
         PP_CUDA(d_neg.alloc(cb, st));
         PP_CUDA(cudaMemcpyAsync(d_pp.p, probe_pairs, sizeof(int64_t) * 2 * n_probe, cudaMemcpyHostToDevice, st));
-        probe_kernel<<<(unsigned)((n_probe + 3) / 4), 128, 0, st>>>((uint32_t *)s_planes, d_chunks.as<Chunk>(),
-                                                                   (int)chunks.size(), W, B, n_classes,
-                                                                   d_pp.as<int64_t>(), n_probe, d_pos.as<int32_t>(),
-                                                                   d_neg.as<int32_t>());
+        PP_CUDA(d_gene_pos.alloc(sizeof(int32_t) * n_genes, st));
+        PP_CUDA(cudaMemcpyAsync(d_gene_pos.p, gene_pos.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
+        probe_kernel<<<(unsigned)((n_probe + 3) / 4), 128, 0, st>>>(
+            (uint32_t *)s_planes, d_blk_off.as<int64_t>(), d_blk_bits.as<int32_t>(), d_gene_pos.as<int32_t>(),
+            d_chunks.as<Chunk>() + P.chunk_off[0], P.chunk_cnt[0], W, n_classes, d_pp.as<int64_t>(), n_probe,
+            d_pos.as<int32_t>(), d_neg.as<int32_t>());
         PP_CHECK_LAUNCH();
         PP_CUDA(cudaMemcpyAsync(probe_pos, d_pos.p, cb, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaMemcpyAsync(probe_neg, d_neg.p, cb, cudaMemcpyDeviceToHost, st));
