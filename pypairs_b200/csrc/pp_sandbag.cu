@@ -857,8 +857,11 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                     tiles.push_back(td);
                     const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
                     const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
-                    int64_t np_tile = 0;
-                    for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                    int64_t np_tile = std::max<int64_t>(0, a1 - a0) * std::max<int64_t>(0, b1 - b0);  // all a < all b
+                    if (b0 < a1) {  // the tile touches the diagonal
+                        np_tile = 0;
+                        for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                    }
                     n_pairs_shard += np_tile;
                     plane_pairs += (double)np_tile * td.bp;
                 }
