@@ -334,6 +334,9 @@ def bench_sandbag(args, rank, local_rank, world, peaks):
 
 
 def run_b200(args):
+    # libraries (NCCL's version banner, build output) write to fd 1: keep stdout for the one JSON line
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     rank, local_rank, world = env_world()
     torch.cuda.set_device(local_rank)
@@ -373,7 +376,9 @@ def run_b200(args):
         import torch.distributed as dist
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
