@@ -373,3 +373,38 @@ def test_single_cell_classes_and_tiny_inputs():
     _check_against_oracle(x, lab, np.array([1, 1, 1]))
     x2 = rng.poisson(2.0, (5, 2)).astype(np.float64)  # two genes: one pair
     _check_against_oracle(x2, np.array([0, 0, 1, 1, 1]), np.array([2, 2]))
+
+
+@pytest.mark.parametrize("c,frac", [(2, 0.3), (2, 0.5), (3, 0.34), (5, 0.2)])
+def test_mixed_rank_widths_and_gene_order(c, frac):
+    """Genes of very different rank widths (constant, binary, low counts, high counts, tie-free) interleaved, so the
+    width-sorted positions invert the gene order of many pairs, and thresholds low enough that a class can be 'up' and
+    'down' at once: with two classes both branches of sandbag.py:192-197 then hold and the if/elif order decides,
+    which depends on which gene the reference calls g1."""
+    rng = np.random.default_rng(100 + c)
+    n, g = 240, 520
+    lab = rng.integers(0, c, n)
+    lab[:c] = np.arange(c)
+    kind = rng.integers(0, 5, g)
+    x = np.empty((n, g))
+    shift = rng.normal(0, 1.0, (c, g))
+    for j in range(g):
+        s = shift[lab, j]
+        if kind[j] == 0:
+            x[:, j] = 3.0                                         # constant
+        elif kind[j] == 1:
+            x[:, j] = (rng.random(n) < 0.3 + 0.2 * np.tanh(s)).astype(float)   # binary
+        elif kind[j] == 2:
+            x[:, j] = rng.poisson(np.exp(0.5 * s))                # low counts
+        elif kind[j] == 3:
+            x[:, j] = rng.poisson(200.0 * np.exp(0.5 * s))        # high counts
+        else:
+            x[:, j] = rng.lognormal(0.3 * s, 1.0)                 # continuous, tie-free
+    thr = orc.calc_thresholds(np.bincount(lab, minlength=c), frac)
+    n_hits, tm = _check_against_oracle(x, lab, thr)
+    assert n_hits > 0 and tm["avg_planes"] < tm["n_planes"]
+    probes = np.sort(rng.integers(0, g, (300, 2)), axis=1)
+    probes = probes[probes[:, 0] < probes[:, 1]]
+    _, _, _, ppos, pneg = run_kernel(x, lab, c, thr, probe_pairs=probes)
+    epos, eneg = orc.pair_counts(x, lab, c, probes)
+    assert np.array_equal(ppos, epos) and np.array_equal(pneg, eneg)
