@@ -217,10 +217,10 @@ StarLayout build_star_layout(const int32_t *pairs, int np, int nu) {
 }
 
 __global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int32_t *__restrict__ slot_src,
-                                   const uint16_t *__restrict__ map, int n_used, int n_slots,
+                                   const uint16_t *__restrict__ map, int n_used, int n_slots, int k_base,
                                    uint32_t *__restrict__ E) {
-    const int k = blockIdx.y;
-    const uint16_t *pk = perm + (size_t)(k > 0 ? k - 1 : 0) * n_used;
+    const int k = blockIdx.y;  // row of this pass: 0 = identity, k > 0 = permutation k_base + k (1-based)
+    const uint16_t *pk = perm + (size_t)(k > 0 ? k_base + k - 1 : 0) * n_used;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += gridDim.x * blockDim.x) {
         int g = slot_src[s];
         if (k > 0) g = pk[g];
@@ -236,7 +236,7 @@ constexpr int SCORE_WARPS = SCORE_THREADS / 32;
 constexpr int TILE_CELLS = 64;
 
 struct ClassDesc {
-    const uint32_t *E;           // [iters+1][n_slots]
+    const uint32_t *E;           // [1 + permutations of this pass][n_slots], row 0 = identity
     const uint32_t *start_mask;  // [n_chunks]
     int32_t n_slots, n_chunks, n_chunks_a, pad;
 };
@@ -256,7 +256,9 @@ struct ScoreParams {
     int *unit_counter;           // dynamic work-unit counter (zeroed before the launch)
     int n_slices;                // > 1: the iterations of a (class, tile) are split over n_slices work units
     int slice_len;               // iterations per slice (a multiple of the warps per CTA)
-    int32_t *below;              // n_slices > 1 only: [n_classes][out_ld] partial counts, finished by finalize_kernel
+    int k_count;                 // permutations held by the tables of this launch (rows 1 .. k_count of E)
+    int accumulate;              // 1: add the partial counts to `below` (slices and / or several table passes)
+    int32_t *below;              // accumulate only: [n_classes][out_ld] partial counts, finished by finalize_kernel
     double *scores;     // [n_classes][n_cells]
     int32_t *obs_hits;  // [n_classes][n_cells]
     int32_t *obs_total;
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         const int cls = P.class_order[ct / n_tiles];
         const int64_t cell0 = (ct % n_tiles) * TILE_CELLS;
         const int k_first = 1 + slice * P.slice_len;
-        const int k_last = min(P.iterations, k_first + P.slice_len - 1);
+        const int k_last = min(P.k_count, k_first + P.slice_len - 1);
         const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
         // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
         if (!FAST) {
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
             __syncthreads();
             if (tid < TILE_CELLS && cell0 + tid < P.n_cells) {
                 const int64_t o = (int64_t)cls * P.out_ld + P.out_off + cell0 + tid;
-                if (P.n_slices > 1) {
+                if (P.accumulate) {
                     if (s_below[tid]) atomicAdd(P.below + o, (int32_t)s_below[tid]);
                 } else {
                     P.scores[o] = final_score(s_below[tid], P.iterations, P.min_iter);
@@ -532,7 +534,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
     }
 }
 
-// Sliced launches: scores of cells [out_off, out_off + n_cells) of every class from the summed partial counts.
+// Accumulating calls: scores of cells [out_off, out_off + n_cells) of every class from the summed partial counts.
 __global__ void finalize_kernel(const ScoreParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_cells * P.n_classes) return;
@@ -760,18 +762,48 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(d_mask[c].alloc(sizeof(uint32_t) * L.n_chunks, st));
         PP_CUDA(cudaMemcpyAsync(d_mask[c].p, L.start_mask.data(), sizeof(uint32_t) * L.n_chunks, cudaMemcpyHostToDevice, st));
         PP_CUDA(cudaStreamSynchronize(st));  // L is a local
-        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(iterations + 1) * n_slots, st));
-        dim3 grid((n_slots + 255) / 256, iterations + 1);
-        build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_src[c].as<int32_t>(), d_map[c].as<uint16_t>(),
-                                                 nu, n_slots, d_T[c].as<uint32_t>());
-        PP_CHECK_LAUNCH();
-        cds[c].E = d_T[c].as<uint32_t>();
+        cds[c].E = nullptr;  // allocated below, once the size of a pass is known
         cds[c].start_mask = d_mask[c].as<uint32_t>();
         cds[c].n_slots = n_slots;
         cds[c].n_chunks = L.n_chunks;
         cds[c].n_chunks_a = L.n_chunks_a;
         cds[c].pad = 0;
     }
+    // E holds one row per permutation: iterations x slots x 4 B (41 MB for the default markers, 16 GB for 4 M pairs).
+    // It is kept under a third of the free device memory by scoring the iterations in passes of k_pass permutations.
+    int k_pass = iterations;
+    {
+        size_t total_slots = 0, free_b = 0, total_b = 0;
+        for (int c = 0; c < n_classes; ++c) total_slots += (size_t)cds[c].n_slots;
+        size_t budget = (size_t)1 << 30;  // tables up to 1 GB are simply built; beyond that, ask the device
+        const char *e = getenv("PP_TABLE_BUDGET_MB");  // tests
+        if (e) {
+            budget = (size_t)std::max(1, atoi(e)) << 20;
+        } else if (total_slots * sizeof(uint32_t) * ((size_t)iterations + 1) > budget) {
+            PP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            budget = std::max(budget, free_b / 3);
+        }
+        const size_t rows = budget / (total_slots * sizeof(uint32_t));
+        k_pass = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(iterations, 1), rows > 1 ? rows - 1 : 1));
+    }
+    const int n_passes = iterations > 0 ? (iterations + k_pass - 1) / k_pass : 1;
+    for (int c = 0; c < n_classes; ++c) {
+        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(k_pass + 1) * cds[c].n_slots, st));
+        cds[c].E = d_T[c].as<uint32_t>();
+    }
+    auto build_tables = [&](int k_base, int k_count) -> int {
+        for (int c = 0; c < n_classes; ++c) {
+            const int nu = (int)(used_off[c + 1] - used_off[c]);
+            dim3 grid((cds[c].n_slots + 255) / 256, k_count + 1);
+            build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_src[c].as<int32_t>(),
+                                                     d_map[c].as<uint16_t>(), nu, cds[c].n_slots, k_base,
+                                                     d_T[c].as<uint32_t>());
+            PP_CHECK_LAUNCH();
+        }
+        return PP_OK;
+    };
+    rc = build_tables(0, std::min(k_pass, iterations));
+    if (rc) return rc;
     PP_CUDA(d_cd.alloc(sizeof(ClassDesc) * n_classes, st));
     PP_CUDA(cudaMemcpyAsync(d_cd.p, cds.data(), sizeof(ClassDesc) * n_classes, cudaMemcpyHostToDevice, st));
     const size_t out_cnt = (size_t)n_classes * n_cells;
@@ -813,25 +845,28 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.unit_counter = d_counter.as<int>();
     // Launches with fewer (class, tile) units than ~3 per SM (few cells, the reference's own use case) split each
     // unit's iterations into slices of >= 2 iterations per warp, aiming at ~4 units per SM.
-    auto slices_for = [&](int64_t nc, int *slice_len) {
-        *slice_len = iterations;
+    auto slices_for = [&](int64_t nc, int k_count, int *slice_len) {
+        *slice_len = std::max(k_count, 1);
         const int64_t units0 = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes;
-        if (nc <= 0 || units0 >= 3 * (int64_t)ctx->n_sm || iterations < 4 * SCORE_WARPS) return 1;
+        if (nc <= 0 || units0 >= 3 * (int64_t)ctx->n_sm || k_count < 4 * SCORE_WARPS) return 1;
         const int64_t want = (4 * (int64_t)ctx->n_sm + units0 - 1) / units0;
-        const int64_t len = ((iterations + want - 1) / want + SCORE_WARPS - 1) / SCORE_WARPS * SCORE_WARPS;
+        const int64_t len = ((k_count + want - 1) / want + SCORE_WARPS - 1) / SCORE_WARPS * SCORE_WARPS;
         *slice_len = (int)std::max<int64_t>(len, 2 * SCORE_WARPS);
-        return (iterations + *slice_len - 1) / *slice_len;
+        return (k_count + *slice_len - 1) / *slice_len;
     };
+    P.k_count = std::min(k_pass, iterations);
     {
         int len;
-        if (slices_for(chunk_cells, &len) > 1 || slices_for(n_cells % chunk_cells, &len) > 1) {
+        P.accumulate = (n_passes > 1 || slices_for(chunk_cells, P.k_count, &len) > 1 ||
+                        slices_for(n_cells % chunk_cells, P.k_count, &len) > 1) ? 1 : 0;
+        if (P.accumulate) {
             PP_CUDA(d_below.alloc(sizeof(int32_t) * out_cnt, st));
             PP_CUDA(cudaMemsetAsync(d_below.p, 0, sizeof(int32_t) * out_cnt, st));
         }
     }
     P.below = d_below.as<int32_t>();
     auto launch_score = [&](int64_t nc) {
-        P.n_slices = slices_for(nc, &P.slice_len);
+        P.n_slices = slices_for(nc, P.k_count, &P.slice_len);
         const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes * P.n_slices;
         cudaMemsetAsync(d_counter.p, 0, sizeof(int), st);
         const int64_t grid = std::min<int64_t>(n_units, fast ? ctx->n_sm : slow_grid);
@@ -843,10 +878,30 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 P.rank, rank_ld, nc, U, s_tiles);
             score_kernel<false><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
         }
-        if (P.n_slices > 1) {
-            ++ctx->launches;
-            finalize_kernel<<<(unsigned)((nc * n_classes + 255) / 256), 256, 0, st>>>(P);
+    };
+    // After every cell has been ranked and scored against the first pass of tables: the remaining passes over the
+    // resident rank matrix, then the division for accumulating calls.
+    auto finish_scoring = [&]() -> int {
+        for (int pass = 1; pass < n_passes; ++pass) {
+            const int k_base = pass * k_pass;
+            P.k_count = std::min(k_pass, iterations - k_base);
+            const int brc = build_tables(k_base, P.k_count);
+            if (brc) return brc;
+            for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells) {
+                P.rank = (uint16_t *)s_rank + c0 * rank_ld;
+                P.n_cells = std::min(chunk_cells, n_cells - c0);
+                P.out_off = c0;
+                launch_score(P.n_cells);
+                PP_CHECK_LAUNCH();
+            }
         }
+        if (P.accumulate) {
+            P.n_cells = n_cells;
+            P.out_off = 0;
+            finalize_kernel<<<(unsigned)((n_cells * n_classes + 255) / 256), 256, 0, st>>>(P);
+            PP_CHECK_LAUNCH();
+        }
+        return PP_OK;
     };
     float score_ms = 0.f, copy_ms = 0.f;
     if (csr) {
@@ -888,6 +943,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             launch_score(nc);
             PP_CHECK_LAUNCH();
         }
+        rc = finish_scoring();
+        if (rc) return rc;
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
         PP_CUDA(cudaStreamSynchronize(st));  // dcsr goes out of scope
     } else if (!pipelined) {
@@ -910,6 +967,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         P.out_off = 0;
         launch_score(n_cells);
         PP_CHECK_LAUNCH();
+        rc = finish_scoring();
+        if (rc) return rc;
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
     } else {
         // Two ways for a chunk of cells to reach the device, through one double-buffered lane:
@@ -1002,6 +1061,17 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             PP_CUDA(cudaEventRecord(e1, st));
         }
         PP_CUDA(cudaEventRecord(ev_c1, cs));
+        {
+            cudaEvent_t e0, e1;
+            PP_CUDA(events.make(&e0, cudaEventDefault));
+            PP_CUDA(events.make(&e1, cudaEventDefault));
+            ev_s.push_back(e0);
+            ev_s.push_back(e1);
+            PP_CUDA(cudaEventRecord(e0, st));
+            rc = finish_scoring();
+            if (rc) return rc;
+            PP_CUDA(cudaEventRecord(e1, st));
+        }
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
         PP_CUDA(cudaStreamSynchronize(cs));
         PP_CUDA(cudaStreamSynchronize(st));

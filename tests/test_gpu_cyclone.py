@@ -335,3 +335,30 @@ def test_few_cells_split_iterations_over_ctas(n_cells, n_used, n_pairs, iteratio
     sc, tm, oh, ot = _ffi().cyclone(x, [np.where(used)[0]], [pairs], iterations, 10, 5, want_observed=True)
     _, eh, et = orc.phase_scores(x, 1, 1, 1, pairs, used, return_observed=True)
     assert np.array_equal(sc[0], got) and np.array_equal(oh[0], eh) and np.array_equal(ot[0], et)
+
+
+@pytest.mark.parametrize("n_cells,n_genes,n_used,n_pairs,host", [(300, 2500, 400, 3000, False),
+                                                                (150, 3000, 2200, 5000, False),
+                                                                (10500, 400, 120, 300, True)])
+def test_table_passes_give_identical_scores(monkeypatch, n_cells, n_genes, n_used, n_pairs, host):
+    """The permutation tables are built for k_pass iterations at a time when they would not fit the memory budget;
+    forcing a 1 MB budget (many passes) must not change a single score or observed counter."""
+    import torch
+    rng = np.random.default_rng(n_cells)
+    x = rng.poisson(1.5, (n_cells, n_genes)).astype(np.float32)
+    used = np.sort(rng.choice(n_genes, n_used, replace=False))
+    pairs = rng.integers(0, n_used, (n_pairs, 2))
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    xin = x if host else torch.from_numpy(x).cuda()
+    ref = _ffi().cyclone(xin, [used, used[: n_used // 2]], [pairs, pairs[pairs.max(axis=1) < n_used // 2]], 500, 10, 5,
+                         want_observed=True)
+    monkeypatch.setenv("PP_TABLE_BUDGET_MB", "1")
+    got = _ffi().cyclone(xin, [used, used[: n_used // 2]], [pairs, pairs[pairs.max(axis=1) < n_used // 2]], 500, 10, 5,
+                         want_observed=True)
+    assert got[1]["n_launches"] > ref[1]["n_launches"]
+    assert np.array_equal(got[0], ref[0], equal_nan=True)
+    assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+    um = np.zeros(n_genes, dtype=np.uint8)
+    um[used] = 1
+    sub = slice(0, 64)
+    assert np.array_equal(got[0][0][sub], orc.phase_scores(x[sub], 500, 10, 5, pairs, um))
