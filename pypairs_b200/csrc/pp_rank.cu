@@ -276,12 +276,19 @@ int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const 
     const size_t ksz = (x_dtype == PP_F64) ? 8 : 4;
     const size_t n_al = ((size_t)n_genes + 15) & ~(size_t)15;
     const size_t per_cta = 2 * n_al * ksz + 2 * n_al * 2;
-    int grid = (int)((n_slots < (int64_t)ctx->n_sm * 3) ? n_slots : (int64_t)ctx->n_sm * 3);
-    uint8_t *scratch = (uint8_t *)pp_slab(ctx, SLAB_SORT, per_cta * (size_t)grid);  // sort path only; stream-ordered reuse
-    if (!scratch) return PP_ENOMEM;
     const size_t dyn = ((size_t)n_genes * 2 + 15) & ~(size_t)15;
     PP_CUDA(cudaFuncSetAttribute(rank_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     PP_CUDA(cudaFuncSetAttribute(rank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    // persistent CTAs: exactly as many as are resident at once (a partial second wave would idle half the SMs)
+    int per_sm = 1;
+    if (x_dtype == PP_F64)
+        PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_kernel<double>, RANK_THREADS, dyn));
+    else
+        PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_kernel<float>, RANK_THREADS, dyn));
+    const int64_t resident = (int64_t)ctx->n_sm * std::max(per_sm, 1);
+    int grid = (int)std::min<int64_t>(n_slots, resident);
+    uint8_t *scratch = (uint8_t *)pp_slab(ctx, SLAB_SORT, per_cta * (size_t)grid);  // sort path only; stream-ordered reuse
+    if (!scratch) return PP_ENOMEM;
     if (x_dtype == PP_F64)
         rank_kernel<double><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
             (const double *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
