@@ -233,7 +233,6 @@ __global__ void build_table_kernel(const uint16_t *__restrict__ perm, const int3
 // ------------------------------------------------------------------------------------------
 constexpr int SCORE_THREADS = 512;
 constexpr int SCORE_WARPS = SCORE_THREADS / 32;
-constexpr int TILE_CELLS = 64;
 
 struct ClassDesc {
     const uint32_t *E;           // [1 + permutations of this pass][n_slots], row 0 = identity
@@ -251,11 +250,14 @@ struct ScoreParams {
     int n_classes;
     int iterations, min_iter, min_pairs;
     const ClassDesc *classes;
-    const uint32_t *gtile;  // !FAST only: the launch's ranks as [n_tiles][n_union][32] words (pack_tiles_kernel)
+    const uint32_t *gtile;  // MODE_GLOBAL only: the launch's ranks as [n_tiles][n_union][32] words (pack_tiles_kernel)
     const int32_t *class_order;  // classes by decreasing cost: work unit u = (class_order[u / n_tiles], tile u % n_tiles)
-    int *unit_counter;           // dynamic work-unit counter (zeroed before the launch)
+    int *unit_counter;           // dynamic work-unit counters (zeroed before the launch): [0] 64-cell tiles, [1] MODE_B8
     int n_slices;                // > 1: the iterations of a (class, tile) are split over n_slices work units
     int slice_len;               // iterations per slice (a multiple of the warps per CTA)
+    int n_slices_b8, slice_len_b8;  // the same for the 128-cell tiles of MODE_B8
+    int try_b8;                  // 1: a MODE_B8 and a MODE_F16 launch follow each other, max_rank picks the one that runs
+    const int32_t *max_rank;     // largest dense rank of any cell ranked so far (flags[0] of the rank kernel)
     int k_count;                 // permutations held by the tables of this launch (rows 1 .. k_count of E)
     int accumulate;              // 1: add the partial counts to `below` (slices and / or several table passes)
     int32_t *below;              // accumulate only: [n_classes][out_ld] partial counts, finished by finalize_kernel
@@ -276,37 +278,56 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-// Two tile representations (template parameter FAST):
-//  FAST  (all marker genes of the call fit the shared-memory tile, <= 1 680 genes): ranks are integer-valued
-//        fp16 numbers (exact up to 2048), two cells per 32-bit word, tile in shared memory.  Per slot two
-//        statistics are taken against the hub h, on two different pipes:
+// Three tile representations (template parameter MODE):
+//  MODE_F16 (all marker genes of the call fit the shared-memory tile, <= 1 680 genes): ranks are integer-valued
+//        fp16 numbers (exact up to 2048), two cells per 32-bit word = 64 cells per tile, tile in shared memory.
+//        Per slot two statistics are taken against the hub h, on two different pipes:
 //          X: (h >= v) as a 0xFFFF/0 mask per half   -- HSET2.GE (ALU pipe) + one 32-bit integer accumulate
 //          Z: (h >  v) as clamp(h - v, 0, 1) in fp16 -- HADD2.SAT + HADD2 (FMA pipe)
-//  !FAST (up to 32 768 marker genes): ranks are 15-bit integers, two per word, tiles in global memory in the
+//  MODE_B8 (same tile, and no cell ranked so far holds 128 or more distinct values among its marker genes -- count
+//        data): ranks are 7-bit integers, FOUR cells per word = 128 cells per tile.  With H1 = h | 0x80808080 and
+//        H2 = H1 - 0x01010101, bit 7 of every byte of H1 - v is (h >= v) and of H2 - v is (h > v) (no borrow crosses
+//        a byte: every byte stays >= 0); PRMT with sign replication turns the four bits into 0xFF/0 bytes, which are
+//        subtracted from a packed accumulator: 2 IADD + 2 PRMT + 1 IADD3 per slot for both statistics of 4 cells.
+//  MODE_GLOBAL (up to 32 768 marker genes): ranks are 15-bit integers, two per word, tiles in global memory in the
 //        same [gene][lane] layout (pack_tiles_kernel; L1/L2 cached gathers, shared by all CTAs working on the
 //        tile); (x >= y) per half is bit 15/31 of (x | 0x80008000) - y.
-// Both flush their per-chunk counters into 32-bit per-cell counters, so a class may have any number of pairs.
+// All flush their per-chunk counters into 32-bit per-cell counters, so a class may have any number of pairs.
+enum { MODE_GLOBAL = 0, MODE_F16 = 1, MODE_B8 = 2 };
+constexpr int B8_MAX_RANK = 127;
+template <int MODE> struct Mode {
+    static constexpr int NC = MODE == MODE_B8 ? 4 : 2;  // cells per lane
+    static constexpr int CELLS = 32 * NC;               // cells per tile
+    static constexpr bool SMEM = MODE != MODE_GLOBAL;   // tile in shared memory
+};
+constexpr int TILE_CELLS = 64;  // MODE_F16 / MODE_GLOBAL
+
 __device__ __forceinline__ __half2 as_h2(uint32_t x) { return *reinterpret_cast<const __half2 *>(&x); }
 __device__ __forceinline__ uint32_t ge_mask(uint32_t x, uint32_t y) { return __hge2_mask(as_h2(x), as_h2(y)); }
 __device__ __forceinline__ uint32_t ge_bits(uint32_t x, uint32_t y) {
     return (((x | 0x80008000u) - y) >> 15) & 0x00010001u;
 }
-template <bool FAST> __device__ __forceinline__ uint32_t tile_load(uint64_t base, uint32_t off) {
-    if (FAST) return lds32((uint32_t)base + off);
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t d) {  // 0xFF in every byte whose bit 7 is set, else 0x00
+    uint32_t m;
+    asm("prmt.b32 %0, %1, 0, 0xba98;" : "=r"(m) : "r"(d));  // selector msb = replicate the sign of the selected byte
+    return m;
+}
+template <int MODE> __device__ __forceinline__ uint32_t tile_load(uint64_t base, uint32_t off) {
+    if (Mode<MODE>::SMEM) return lds32((uint32_t)base + off);
     return __ldg(reinterpret_cast<const uint32_t *>(base + off));  // written by an earlier kernel
 }
 
-struct RowAcc {  // per-cell counters of one table row: section A / B, low / high cell of the lane
-    int xa_lo, xa_hi, za_lo, za_hi, xb_lo, xb_hi, zb_lo, zb_hi;
+template <int NC> struct RowAcc {  // per-cell counters of one table row: [section A / B][cell of the lane]
+    int x[2][NC], z[2][NC];
 };
 
-// For the two cells packed in this lane add, over the slots of chunks first, first + stride, ... < last of one
+// For the cells packed in this lane add, over the slots of chunks first, first + stride, ... < last of one
 // table row, X += (hub >= v) and Z += (hub > v).  Chunks are staged into this warp's private double buffer with
 // cp.async; one broadcast LDS.128 fetches four slot offsets.
-template <bool FAST>
+template <int MODE>
 __device__ __forceinline__ void eval_chunks(uint64_t tile_lane, const uint32_t *__restrict__ Erow,
                                             const uint32_t *__restrict__ start_mask, int first, int stride, int last,
-                                            uint4 *stage, int lane, int &x_lo, int &x_hi, int &z_lo, int &z_hi) {
+                                            uint4 *stage, int lane, int (&x)[Mode<MODE>::NC], int (&z)[Mode<MODE>::NC]) {
     if (first >= last) return;
     const uint4 *src = reinterpret_cast<const uint4 *>(Erow) + lane;  // 32 lanes x 16 B = one chunk
     cp_async16(stage + lane, src + (size_t)first * 32);
@@ -324,14 +345,14 @@ __device__ __forceinline__ void eval_chunks(uint64_t tile_lane, const uint32_t *
         }
         __syncwarp();
         const uint4 *sb = stage + buf * 32;
-        if (FAST) {
+        if (MODE == MODE_F16) {
             uint32_t X = 0;                               // sum of -(mask), decoded below
             __half2 z0 = __float2half2_rn(0.f), z1 = z0;  // <= 64 each per chunk: exact
 #pragma unroll 8
             for (int q = 0; q < 32; ++q) {
                 const uint4 v = sb[q];  // broadcast: four slots
-                const uint32_t e0 = tile_load<true>(tile_lane, v.x), e1 = tile_load<true>(tile_lane, v.y);
-                const uint32_t e2 = tile_load<true>(tile_lane, v.z), e3 = tile_load<true>(tile_lane, v.w);
+                const uint32_t e0 = tile_load<MODE>(tile_lane, v.x), e1 = tile_load<MODE>(tile_lane, v.y);
+                const uint32_t e2 = tile_load<MODE>(tile_lane, v.z), e3 = tile_load<MODE>(tile_lane, v.w);
                 if ((sm >> q) & 1u) h = e0;  // warp-uniform: this vector opens a star
                 const __half2 hh = as_h2(h);
                 X -= ge_mask(h, e0);
@@ -346,26 +367,50 @@ __device__ __forceinline__ void eval_chunks(uint64_t tile_lane, const uint32_t *
             // a true low half adds 1 to the low field and -1 to the high field, a true high half adds 1 to the
             // high field  =>  lo16 = n_lo, hi16 = n_hi - n_lo (mod 2^16)
             const int n_lo = (int)(X & 0xffffu);
-            x_lo += n_lo;
-            x_hi += (int)(((X >> 16) + (uint32_t)n_lo) & 0xffffu);
-            const __half2 z = __hadd2(z0, z1);
-            z_lo += __half2int_rz(__low2half(z));
-            z_hi += __half2int_rz(__high2half(z));
+            x[0] += n_lo;
+            x[1] += (int)(((X >> 16) + (uint32_t)n_lo) & 0xffffu);
+            const __half2 zz = __hadd2(z0, z1);
+            z[0] += __half2int_rz(__low2half(zz));
+            z[1] += __half2int_rz(__high2half(zz));
+        } else if (MODE == MODE_B8) {
+            // a true byte i adds 256^i - 256^(i+1) to the accumulator: X = N - (N << 8) with N the packed byte counts
+            // (<= 128 per chunk), so N = X * 0x01010101 (mod 2^32)
+            uint32_t X = 0, Z = 0, h1 = 0x80808080u, h2 = 0x7f7f7f7fu;
+#pragma unroll 8
+            for (int q = 0; q < 32; ++q) {
+                const uint4 v = sb[q];
+                const uint32_t e0 = tile_load<MODE>(tile_lane, v.x), e1 = tile_load<MODE>(tile_lane, v.y);
+                const uint32_t e2 = tile_load<MODE>(tile_lane, v.z), e3 = tile_load<MODE>(tile_lane, v.w);
+                if ((sm >> q) & 1u) {
+                    h1 = e0 | 0x80808080u;
+                    h2 = h1 - 0x01010101u;
+                }
+                X = X - sign_bytes(h1 - e0) - sign_bytes(h1 - e1);
+                X = X - sign_bytes(h1 - e2) - sign_bytes(h1 - e3);
+                Z = Z - sign_bytes(h2 - e0) - sign_bytes(h2 - e1);
+                Z = Z - sign_bytes(h2 - e2) - sign_bytes(h2 - e3);
+            }
+            const uint32_t nx = X * 0x01010101u, nz = Z * 0x01010101u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                x[i] += (int)((nx >> (8 * i)) & 0xffu);
+                z[i] += (int)((nz >> (8 * i)) & 0xffu);
+            }
         } else {
             uint32_t X = 0, W = 0;  // packed plain counts of (h >= v) and (v >= h); <= 128 per chunk
 #pragma unroll 4
             for (int q = 0; q < 32; ++q) {
                 const uint4 v = sb[q];
-                const uint32_t e0 = tile_load<false>(tile_lane, v.x), e1 = tile_load<false>(tile_lane, v.y);
-                const uint32_t e2 = tile_load<false>(tile_lane, v.z), e3 = tile_load<false>(tile_lane, v.w);
+                const uint32_t e0 = tile_load<MODE>(tile_lane, v.x), e1 = tile_load<MODE>(tile_lane, v.y);
+                const uint32_t e2 = tile_load<MODE>(tile_lane, v.z), e3 = tile_load<MODE>(tile_lane, v.w);
                 if ((sm >> q) & 1u) h = e0;
                 X += ge_bits(h, e0) + ge_bits(h, e1) + ge_bits(h, e2) + ge_bits(h, e3);
                 W += ge_bits(e0, h) + ge_bits(e1, h) + ge_bits(e2, h) + ge_bits(e3, h);
             }
-            x_lo += (int)(X & 0xffffu);
-            x_hi += (int)(X >> 16);
-            z_lo += CHUNK_SLOTS - (int)(W & 0xffffu);  // (h > v) = !(v >= h)
-            z_hi += CHUNK_SLOTS - (int)(W >> 16);
+            x[0] += (int)(X & 0xffffu);
+            x[1] += (int)(X >> 16);
+            z[0] += CHUNK_SLOTS - (int)(W & 0xffffu);  // (h > v) = !(v >= h)
+            z[1] += CHUNK_SLOTS - (int)(W >> 16);
         }
         __syncwarp();  // every lane is done with `buf` before it is refilled
         buf ^= 1;
@@ -373,36 +418,35 @@ __device__ __forceinline__ void eval_chunks(uint64_t tile_lane, const uint32_t *
 }
 
 // One table row.  Section A: the hub is the pair's first gene; section B: its second gene.
-template <bool FAST>
-__device__ __forceinline__ RowAcc eval_row(uint64_t tile_lane, const uint32_t *__restrict__ Erow, const ClassDesc &cd,
-                                           int first, int stride, uint4 *stage, int lane) {
-    RowAcc r = {0, 0, 0, 0, 0, 0, 0, 0};
-    eval_chunks<FAST>(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, r.xa_lo, r.xa_hi,
-                      r.za_lo, r.za_hi);
+template <int MODE>
+__device__ __forceinline__ RowAcc<Mode<MODE>::NC> eval_row(uint64_t tile_lane, const uint32_t *__restrict__ Erow,
+                                                         const ClassDesc &cd, int first, int stride, uint4 *stage,
+                                                         int lane) {
+    RowAcc<Mode<MODE>::NC> r;
+#pragma unroll
+    for (int i = 0; i < Mode<MODE>::NC; ++i) r.x[0][i] = r.x[1][i] = r.z[0][i] = r.z[1][i] = 0;
+    eval_chunks<MODE>(tile_lane, Erow, cd.start_mask, first, stride, cd.n_chunks_a, stage, lane, r.x[0], r.z[0]);
     int fb = first;  // first chunk of this warp's stride pattern inside section B
     if (stride > 1) {
         while (fb < cd.n_chunks_a) fb += stride;
     } else {
         fb = cd.n_chunks_a;
     }
-    eval_chunks<FAST>(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, r.xb_lo, r.xb_hi, r.zb_lo,
-                      r.zb_hi);
+    eval_chunks<MODE>(tile_lane, Erow, cd.start_mask, fb, stride, cd.n_chunks, stage, lane, r.x[1], r.z[1]);
     return r;
 }
 
-// (hits, total) of get_proportion (cyclone.py:206-215) for the two cells of a lane.  Over the slots of
-// section A (pair = (h, v)) and B (pair = (v, h)), with ties = hub / padding slots and genuine ties:
+// (hits, total) of get_proportion (cyclone.py:206-215) for cell i of a lane.  Over the slots of section A
+// (pair = (h, v)) and B (pair = (v, h)), with ties = hub / padding slots and genuine ties:
 //   hits  = #(first > second) = Z_A + (S_B - X_B)          ties are inside X_B, so they drop out
 //   total = #(first != second) = S - (X_A - Z_A) - (X_B - Z_B)
-__device__ __forceinline__ void row_counts(const RowAcc &r, int s_all, int s_b, int &h_lo, int &h_hi, int &t_lo,
-                                           int &t_hi) {
-    h_lo = r.za_lo + s_b - r.xb_lo;
-    h_hi = r.za_hi + s_b - r.xb_hi;
-    t_lo = s_all - r.xa_lo + r.za_lo - r.xb_lo + r.zb_lo;
-    t_hi = s_all - r.xa_hi + r.za_hi - r.xb_hi + r.zb_hi;
+template <int NC>
+__device__ __forceinline__ void row_counts(const RowAcc<NC> &r, int i, int s_all, int s_b, int &hits, int &total) {
+    hits = r.z[0][i] + s_b - r.x[1][i];
+    total = s_all - r.x[0][i] + r.z[0][i] - r.x[1][i] + r.z[1][i];
 }
 
-// !FAST: ranks [cell][rank_ld] u16 -> [tile][gene][lane] words (lane l = cells l and l + 32 of the 64-cell tile).
+// MODE_GLOBAL: ranks [cell][rank_ld] u16 -> [tile][gene][lane] words (lane l = cells l and l + 32 of the 64-cell tile).
 // One CTA per (tile, 32-gene block): 64 coalesced 64-byte row reads, transposed through shared memory.
 __global__ void __launch_bounds__(256) pack_tiles_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld,
                                                          int64_t n_cells, int n_union, uint32_t *__restrict__ out) {
@@ -423,105 +467,136 @@ __device__ __forceinline__ double final_score(uint32_t below, int iterations, in
     return nan("");
 }
 
-template <bool FAST>
+template <int MODE>
 __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
+    constexpr int NC = Mode<MODE>::NC, CELLS = Mode<MODE>::CELLS;
+    constexpr bool SMEM = Mode<MODE>::SMEM;
     extern __shared__ __align__(128) uint8_t smem_dyn[];
-    __shared__ int s_obs[8][32];  // observed counters
-    __shared__ uint32_t s_below[TILE_CELLS];
+    __shared__ int s_obs[4 * NC][32];  // observed counters: [x A, z A, x B, z B][cell of the lane]
+    __shared__ uint32_t s_below[CELLS];
     __shared__ int s_unit;
 
+    // the 7-bit path runs iff every cell ranked so far has at most 128 distinct values; the fp16 launch that
+    // follows it on the stream takes the other case
+    if (P.try_b8) {
+        const bool small = __ldg(P.max_rank) <= B8_MAX_RANK;
+        if ((MODE == MODE_B8) != small) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // FAST: [n_union][32] words in shared memory, followed by the per-warp staging buffers;
-    // !FAST: the tiles stay in global memory, shared memory only holds the staging buffers
+    // shared-memory modes: [n_union][32] words in shared memory, followed by the per-warp staging buffers;
+    // MODE_GLOBAL: the tiles stay in global memory, shared memory only holds the staging buffers
     uint32_t *tile = reinterpret_cast<uint32_t *>(smem_dyn);
-    uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (FAST ? (size_t)P.n_union * 128 : 0) + (size_t)warp * STAGE_BYTES);
+    uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (SMEM ? (size_t)P.n_union * 128 : 0) + (size_t)warp * STAGE_BYTES);
     uint64_t tile_lane = (uint64_t)(smem_u32(tile) + lane * 4);
-    const int64_t n_tiles = (P.n_cells + TILE_CELLS - 1) / TILE_CELLS;
+    const int64_t n_tiles = (P.n_cells + CELLS - 1) / CELLS;
+    const int n_slices = MODE == MODE_B8 ? P.n_slices_b8 : P.n_slices;
+    const int slice_len = MODE == MODE_B8 ? P.slice_len_b8 : P.slice_len;
+    int *unit_counter = P.unit_counter + (MODE == MODE_B8 ? 1 : 0);
 
-    // Work units = (class, 64-cell tile, iteration slice), handed out dynamically, most expensive class first:
+    // Work units = (class, cell tile, iteration slice), handed out dynamically, most expensive class first:
     // equal-cost tiles would quantise the launch into whole waves (1 563 tiles on 148 SMs = 10.56 -> 11), units a
     // third of that size don't.  Few cells (fewer units than SMs) are split further into iteration slices; every
     // slice recomputes the observed row and adds its part of `below` to a global counter.
-    const int64_t n_units = n_tiles * P.n_classes * P.n_slices;
+    const int64_t n_units = n_tiles * P.n_classes * n_slices;
     for (;;) {
-        if (tid == 0) s_unit = atomicAdd(P.unit_counter, 1);
+        if (tid == 0) s_unit = atomicAdd(unit_counter, 1);
         __syncthreads();
         const int64_t u = s_unit;
         if (u >= n_units) break;
-        const int slice = (int)(u % P.n_slices);
-        const int64_t ct = u / P.n_slices;
+        const int slice = (int)(u % n_slices);
+        const int64_t ct = u / n_slices;
         const int cls = P.class_order[ct / n_tiles];
-        const int64_t cell0 = (ct % n_tiles) * TILE_CELLS;
-        const int k_first = 1 + slice * P.slice_len;
-        const int k_last = min(P.k_count, k_first + P.slice_len - 1);
-        const int64_t c_lo = cell0 + lane, c_hi = cell0 + 32 + lane;
+        const int64_t cell0 = (ct % n_tiles) * CELLS;
+        const int k_first = 1 + slice * slice_len;
+        const int k_last = min(P.k_count, k_first + slice_len - 1);
         // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
-        if (!FAST) {
+        if (!SMEM) {
             tile_lane = (uint64_t)(uintptr_t)(P.gtile + (size_t)(ct % n_tiles) * P.n_union * 32 + lane);
         } else {
-            const uint16_t *r_lo = P.rank + (c_lo < P.n_cells ? c_lo : 0) * P.rank_ld;
-            const uint16_t *r_hi = P.rank + (c_hi < P.n_cells ? c_hi : 0) * P.rank_ld;
+            const uint16_t *r[NC];
+            bool in[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                in[i] = cell0 + 32 * i + lane < P.n_cells;
+                r[i] = P.rank + (in[i] ? cell0 + 32 * i + lane : 0) * P.rank_ld;
+            }
             for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
-                const uint32_t lo = (c_lo < P.n_cells) ? r_lo[g] : 0u;
-                const uint32_t hi = (c_hi < P.n_cells) ? r_hi[g] : 0u;
-                const __half2 v = __floats2half2_rn((float)lo, (float)hi);  // exact: ranks < 2048
-                tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
+                if (MODE == MODE_B8) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) w |= (in[i] ? (uint32_t)r[i][g] : 0u) << (8 * i);
+                    tile[g * 32 + lane] = w;
+                } else {
+                    const uint32_t lo = in[0] ? r[0][g] : 0u, hi = in[1] ? r[1][g] : 0u;
+                    const __half2 v = __floats2half2_rn((float)lo, (float)hi);  // exact: ranks < 2048
+                    tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
+                }
             }
         }
         {
             const ClassDesc cd = P.classes[cls];
             const int s_all = cd.n_slots, s_b = (cd.n_chunks - cd.n_chunks_a) * CHUNK_SLOTS;
             if (tid < 32)
-                for (int j = 0; j < 8; ++j) s_obs[j][tid] = 0;
-            if (tid < TILE_CELLS) s_below[tid] = 0;
+                for (int j = 0; j < 4 * NC; ++j) s_obs[j][tid] = 0;
+            if (tid < CELLS) s_below[tid] = 0;
             __syncthreads();  // also orders the tile stores before the first gather
             // ---- observed proportion (row 0): chunks dealt to the warps
             {
-                const RowAcc r = eval_row<FAST>(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane);
-                atomicAdd(&s_obs[0][lane], r.xa_lo);
-                atomicAdd(&s_obs[1][lane], r.xa_hi);
-                atomicAdd(&s_obs[2][lane], r.za_lo);
-                atomicAdd(&s_obs[3][lane], r.za_hi);
-                atomicAdd(&s_obs[4][lane], r.xb_lo);
-                atomicAdd(&s_obs[5][lane], r.xb_hi);
-                atomicAdd(&s_obs[6][lane], r.zb_lo);
-                atomicAdd(&s_obs[7][lane], r.zb_hi);
+                const RowAcc<NC> r = eval_row<MODE>(tile_lane, cd.E, cd, warp, SCORE_WARPS, stage, lane);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    atomicAdd(&s_obs[0 * NC + i][lane], r.x[0][i]);
+                    atomicAdd(&s_obs[1 * NC + i][lane], r.z[0][i]);
+                    atomicAdd(&s_obs[2 * NC + i][lane], r.x[1][i]);
+                    atomicAdd(&s_obs[3 * NC + i][lane], r.z[1][i]);
+                }
             }
             __syncthreads();
-            int h0_lo, h0_hi, t0_lo, t0_hi;
+            int h0[NC], t0[NC];
+            bool ok[NC];
             {
-                const RowAcc r = {s_obs[0][lane], s_obs[1][lane], s_obs[2][lane], s_obs[3][lane],
-                                  s_obs[4][lane], s_obs[5][lane], s_obs[6][lane], s_obs[7][lane]};
-                row_counts(r, s_all, s_b, h0_lo, h0_hi, t0_lo, t0_hi);
-            }
-            const bool ok_lo = !(h0_lo < P.min_pairs || t0_lo == 0);  // observed proportion is not NaN
-            const bool ok_hi = !(h0_hi < P.min_pairs || t0_hi == 0);
-            if (warp == 0 && slice == 0) {
-                if (c_lo < P.n_cells) {
-                    if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_lo] = h0_lo;
-                    if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_lo] = t0_lo;
+                RowAcc<NC> r;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    r.x[0][i] = s_obs[0 * NC + i][lane];
+                    r.z[0][i] = s_obs[1 * NC + i][lane];
+                    r.x[1][i] = s_obs[2 * NC + i][lane];
+                    r.z[1][i] = s_obs[3 * NC + i][lane];
                 }
-                if (c_hi < P.n_cells) {
-                    if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + c_hi] = h0_hi;
-                    if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + c_hi] = t0_hi;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    row_counts(r, i, s_all, s_b, h0[i], t0[i]);
+                    ok[i] = !(h0[i] < P.min_pairs || t0[i] == 0);  // observed proportion is not NaN
+                }
+            }
+            if (warp == 0 && slice == 0) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int64_t cell = cell0 + 32 * i + lane;
+                    if (cell < P.n_cells) {
+                        if (P.obs_hits) P.obs_hits[(int64_t)cls * P.out_ld + P.out_off + cell] = h0[i];
+                        if (P.obs_total) P.obs_total[(int64_t)cls * P.out_ld + P.out_off + cell] = t0[i];
+                    }
                 }
             }
             // ---- permutation null: iterations dealt round-robin to the warps
-            uint32_t below_lo = 0, below_hi = 0;
+            uint32_t below[NC];
+#pragma unroll
+            for (int i = 0; i < NC; ++i) below[i] = 0;
             for (int k = k_first + warp; k <= k_last; k += SCORE_WARPS) {
-                const RowAcc r = eval_row<FAST>(tile_lane, cd.E + (size_t)k * s_all, cd, 0, 1, stage, lane);
-                int h_lo, h_hi, t_lo, t_hi;
-                row_counts(r, s_all, s_b, h_lo, h_hi, t_lo, t_hi);
-                // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
-                if (ok_lo && !(h_lo < P.min_pairs || t_lo == 0) && (long long)h_lo * t0_lo < (long long)h0_lo * t_lo)
-                    ++below_lo;
-                if (ok_hi && !(h_hi < P.min_pairs || t_hi == 0) && (long long)h_hi * t0_hi < (long long)h0_hi * t_hi)
-                    ++below_hi;
+                const RowAcc<NC> r = eval_row<MODE>(tile_lane, cd.E + (size_t)k * s_all, cd, 0, 1, stage, lane);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    int h, t;
+                    row_counts(r, i, s_all, s_b, h, t);
+                    // new < cur with NaN on either side comparing false (cyclone.py:217-218, 239)
+                    if (ok[i] && !(h < P.min_pairs || t == 0) && (long long)h * t0[i] < (long long)h0[i] * t) ++below[i];
+                }
             }
-            atomicAdd(&s_below[lane], below_lo);
-            atomicAdd(&s_below[32 + lane], below_hi);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) atomicAdd(&s_below[32 * i + lane], below[i]);
             __syncthreads();
-            if (tid < TILE_CELLS && cell0 + tid < P.n_cells) {
+            if (tid < CELLS && cell0 + tid < P.n_cells) {
                 const int64_t o = (int64_t)cls * P.out_ld + P.out_off + cell0 + tid;
                 if (P.accumulate) {
                     if (s_below[tid]) atomicAdd(P.below + o, (int32_t)s_below[tid]);
@@ -824,7 +899,10 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.scores = d_scores.as<double>();
     P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
     P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
-    PP_CUDA(cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    P.try_b8 = fast ? 1 : 0;
+    P.max_rank = d_flags.as<int32_t>();
     const int slow_grid = ctx->n_sm * 2;  // persistent CTAs of the global-tile path
     uint32_t *s_tiles = nullptr;          // !fast: packed tiles of one launch
     if (!fast && !(s_tiles = (uint32_t *)pp_slab(ctx, SLAB_MISC, (size_t)((chunk_cells + TILE_CELLS - 1) / TILE_CELLS) * U * 128)))
@@ -838,16 +916,16 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cds[a].n_slots > cds[b].n_slots; });
         PP_CUDA(d_order.alloc(sizeof(int32_t) * n_classes, st));
         PP_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
-        PP_CUDA(d_counter.alloc(sizeof(int), st));
+        PP_CUDA(d_counter.alloc(2 * sizeof(int), st));
         PP_CUDA(cudaStreamSynchronize(st));  // order is a local
     }
     P.class_order = d_order.as<int32_t>();
     P.unit_counter = d_counter.as<int>();
     // Launches with fewer (class, tile) units than ~3 per SM (few cells, the reference's own use case) split each
     // unit's iterations into slices of >= 2 iterations per warp, aiming at ~4 units per SM.
-    auto slices_for = [&](int64_t nc, int k_count, int *slice_len) {
+    auto slices_for = [&](int64_t nc, int tile_cells, int k_count, int *slice_len) {
         *slice_len = std::max(k_count, 1);
-        const int64_t units0 = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes;
+        const int64_t units0 = (nc + tile_cells - 1) / tile_cells * n_classes;
         if (nc <= 0 || units0 >= 3 * (int64_t)ctx->n_sm || k_count < 4 * SCORE_WARPS) return 1;
         const int64_t want = (4 * (int64_t)ctx->n_sm + units0 - 1) / units0;
         const int64_t len = ((k_count + want - 1) / want + SCORE_WARPS - 1) / SCORE_WARPS * SCORE_WARPS;
@@ -857,8 +935,12 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.k_count = std::min(k_pass, iterations);
     {
         int len;
-        P.accumulate = (n_passes > 1 || slices_for(chunk_cells, P.k_count, &len) > 1 ||
-                        slices_for(n_cells % chunk_cells, P.k_count, &len) > 1) ? 1 : 0;
+        bool sliced = false;
+        for (const int64_t nc : {chunk_cells, n_cells % chunk_cells}) {
+            sliced = sliced || slices_for(nc, TILE_CELLS, P.k_count, &len) > 1;
+            sliced = sliced || (fast && slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &len) > 1);
+        }
+        P.accumulate = (n_passes > 1 || sliced) ? 1 : 0;
         if (P.accumulate) {
             PP_CUDA(d_below.alloc(sizeof(int32_t) * out_cnt, st));
             PP_CUDA(cudaMemsetAsync(d_below.p, 0, sizeof(int32_t) * out_cnt, st));
@@ -866,17 +948,22 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     P.below = d_below.as<int32_t>();
     auto launch_score = [&](int64_t nc) {
-        P.n_slices = slices_for(nc, P.k_count, &P.slice_len);
+        P.n_slices = slices_for(nc, TILE_CELLS, P.k_count, &P.slice_len);
+        P.n_slices_b8 = slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &P.slice_len_b8);
         const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes * P.n_slices;
-        cudaMemsetAsync(d_counter.p, 0, sizeof(int), st);
-        const int64_t grid = std::min<int64_t>(n_units, fast ? ctx->n_sm : slow_grid);
+        cudaMemsetAsync(d_counter.p, 0, 2 * sizeof(int), st);
         if (fast) {
-            score_kernel<true><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
+            // count data (<= 128 distinct values per cell) takes the 4-cells-per-word kernel, anything else the fp16
+            // kernel: both are enqueued, the device-side flag written by the rank kernel lets exactly one of them run
+            const int64_t n_units_b8 = (nc + Mode<MODE_B8>::CELLS - 1) / Mode<MODE_B8>::CELLS * n_classes * P.n_slices_b8;
+            ++ctx->launches;
+            score_kernel<MODE_B8><<<(unsigned)std::min<int64_t>(n_units_b8, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
+            score_kernel<MODE_F16><<<(unsigned)std::min<int64_t>(n_units, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
         } else {
             ++ctx->launches;
             pack_tiles_kernel<<<dim3((unsigned)((nc + TILE_CELLS - 1) / TILE_CELLS), (unsigned)((U + 31) / 32)), 256, 0, st>>>(
                 P.rank, rank_ld, nc, U, s_tiles);
-            score_kernel<false><<<(unsigned)grid, SCORE_THREADS, dyn_smem, st>>>(P);
+            score_kernel<MODE_GLOBAL><<<(unsigned)std::min<int64_t>(n_units, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
         }
     };
     // After every cell has been ranked and scored against the first pass of tables: the remaining passes over the
