@@ -250,13 +250,13 @@ struct ScoreParams {
     int n_classes;
     int iterations, min_iter, min_pairs;
     const ClassDesc *classes;
-    const uint32_t *gtile;  // MODE_GLOBAL only: the launch's ranks as [n_tiles][n_union][32] words (pack_tiles_kernel)
+    const uint32_t *gtile;     // MODE_GLOBAL: the launch's ranks as [64-cell tiles][n_union][32] words (pack_tiles_kernel)
+    const uint32_t *gtile_b8;  // MODE_GLOBAL_B8: as [128-cell tiles][n_union][32] words (pack_tiles_b8_kernel)
     const int32_t *class_order;  // classes by decreasing cost: work unit u = (class_order[u / n_tiles], tile u % n_tiles)
     int *unit_counter;           // dynamic work-unit counters (zeroed before the launch): [0] 64-cell tiles, [1] MODE_B8
     int n_slices;                // > 1: the iterations of a (class, tile) are split over n_slices work units
     int slice_len;               // iterations per slice (a multiple of the warps per CTA)
     int n_slices_b8, slice_len_b8;  // the same for the 128-cell tiles of MODE_B8
-    int try_b8;                  // 1: a MODE_B8 and a MODE_F16 launch follow each other, max_rank picks the one that runs
     const int32_t *max_rank;     // largest dense rank of any cell ranked so far (flags[0] of the rank kernel)
     int k_count;                 // permutations held by the tables of this launch (rows 1 .. k_count of E)
     int accumulate;              // 1: add the partial counts to `below` (slices and / or several table passes)
@@ -293,12 +293,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 //        same [gene][lane] layout (pack_tiles_kernel; L1/L2 cached gathers, shared by all CTAs working on the
 //        tile); (x >= y) per half is bit 15/31 of (x | 0x80008000) - y.
 // All flush their per-chunk counters into 32-bit per-cell counters, so a class may have any number of pairs.
-enum { MODE_GLOBAL = 0, MODE_F16 = 1, MODE_B8 = 2 };
+//  MODE_GLOBAL_B8: the 7-bit arithmetic of MODE_B8 on global-memory tiles (one 128 B line per gather now serves 128 cells).
+enum { MODE_GLOBAL = 0, MODE_F16 = 1, MODE_B8 = 2, MODE_GLOBAL_B8 = 3 };
 constexpr int B8_MAX_RANK = 127;
 template <int MODE> struct Mode {
-    static constexpr int NC = MODE == MODE_B8 ? 4 : 2;  // cells per lane
-    static constexpr int CELLS = 32 * NC;               // cells per tile
-    static constexpr bool SMEM = MODE != MODE_GLOBAL;   // tile in shared memory
+    static constexpr bool BYTES = MODE == MODE_B8 || MODE == MODE_GLOBAL_B8;  // 7-bit ranks, four cells per word
+    static constexpr int NC = BYTES ? 4 : 2;                                  // cells per lane
+    static constexpr int CELLS = 32 * NC;                                     // cells per tile
+    static constexpr bool SMEM = MODE == MODE_F16 || MODE == MODE_B8;         // tile in shared memory
 };
 constexpr int TILE_CELLS = 64;  // MODE_F16 / MODE_GLOBAL
 
@@ -372,11 +374,11 @@ __device__ __forceinline__ void eval_chunks(uint64_t tile_lane, const uint32_t *
             const __half2 zz = __hadd2(z0, z1);
             z[0] += __half2int_rz(__low2half(zz));
             z[1] += __half2int_rz(__high2half(zz));
-        } else if (MODE == MODE_B8) {
+        } else if (Mode<MODE>::BYTES) {
             // a true byte i adds 256^i - 256^(i+1) to the accumulator: X = N - (N << 8) with N the packed byte counts
             // (<= 128 per chunk), so N = X * 0x01010101 (mod 2^32)
             uint32_t X = 0, Z = 0, h1 = 0x80808080u, h2 = 0x7f7f7f7fu;
-#pragma unroll 8
+#pragma unroll(Mode<MODE>::SMEM ? 8 : 4)
             for (int q = 0; q < 32; ++q) {
                 const uint4 v = sb[q];
                 const uint32_t e0 = tile_load<MODE>(tile_lane, v.x), e1 = tile_load<MODE>(tile_lane, v.y);
@@ -461,6 +463,22 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(const uint16_t *__restr
         o[g * 32 + gl] = (uint32_t)s[gl][g] | ((uint32_t)s[gl + 32][g] << 16);
 }
 
+// MODE_GLOBAL_B8: the same with four cells per word (lane l = cells l, l + 32, l + 64, l + 96 of a 128-cell tile);
+// only read when every rank is <= 127.
+__global__ void __launch_bounds__(256) pack_tiles_b8_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld,
+                                                            int64_t n_cells, int n_union, uint32_t *__restrict__ out) {
+    __shared__ uint8_t s[128][33];
+    const int64_t cell0 = (int64_t)blockIdx.x * 128;
+    const int g0 = blockIdx.y * 32, gl = threadIdx.x & 31;
+    for (int c = threadIdx.x >> 5; c < 128; c += 8)
+        s[c][gl] = (cell0 + c < n_cells && g0 + gl < n_union) ? (uint8_t)rank[(cell0 + c) * rank_ld + g0 + gl] : (uint8_t)0;
+    __syncthreads();
+    uint32_t *o = out + ((size_t)blockIdx.x * n_union + g0) * 32;
+    for (int g = threadIdx.x >> 5; g < 32 && g0 + g < n_union; g += 8)
+        o[g * 32 + gl] = (uint32_t)s[gl][g] | ((uint32_t)s[gl + 32][g] << 8) | ((uint32_t)s[gl + 64][g] << 16) |
+                         ((uint32_t)s[gl + 96][g] << 24);
+}
+
 // total == iterations always (cyclone.py:238: NaN != -1); score per :243-249
 __device__ __forceinline__ double final_score(uint32_t below, int iterations, int min_iter) {
     if (iterations >= min_iter && iterations > 0) return (double)below / (double)iterations;
@@ -478,9 +496,10 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
 
     // the 7-bit path runs iff every cell ranked so far has at most 128 distinct values; the fp16 launch that
     // follows it on the stream takes the other case
-    if (P.try_b8) {
+    constexpr bool BYTES = Mode<MODE>::BYTES;
+    {
         const bool small = __ldg(P.max_rank) <= B8_MAX_RANK;
-        if ((MODE == MODE_B8) != small) return;
+        if (BYTES != small) return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // shared-memory modes: [n_union][32] words in shared memory, followed by the per-warp staging buffers;
@@ -489,9 +508,9 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
     uint4 *stage = reinterpret_cast<uint4 *>(smem_dyn + (SMEM ? (size_t)P.n_union * 128 : 0) + (size_t)warp * STAGE_BYTES);
     uint64_t tile_lane = (uint64_t)(smem_u32(tile) + lane * 4);
     const int64_t n_tiles = (P.n_cells + CELLS - 1) / CELLS;
-    const int n_slices = MODE == MODE_B8 ? P.n_slices_b8 : P.n_slices;
-    const int slice_len = MODE == MODE_B8 ? P.slice_len_b8 : P.slice_len;
-    int *unit_counter = P.unit_counter + (MODE == MODE_B8 ? 1 : 0);
+    const int n_slices = BYTES ? P.n_slices_b8 : P.n_slices;
+    const int slice_len = BYTES ? P.slice_len_b8 : P.slice_len;
+    int *unit_counter = P.unit_counter + (BYTES ? 1 : 0);
 
     // Work units = (class, cell tile, iteration slice), handed out dynamically, most expensive class first:
     // equal-cost tiles would quantise the launch into whole waves (1 563 tiles on 148 SMs = 10.56 -> 11), units a
@@ -511,7 +530,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         const int k_last = min(P.k_count, k_first + slice_len - 1);
         // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
         if (!SMEM) {
-            tile_lane = (uint64_t)(uintptr_t)(P.gtile + (size_t)(ct % n_tiles) * P.n_union * 32 + lane);
+            tile_lane = (uint64_t)(uintptr_t)((BYTES ? P.gtile_b8 : P.gtile) + (size_t)(ct % n_tiles) * P.n_union * 32 + lane);
         } else {
             const uint16_t *r[NC];
             bool in[NC];
@@ -521,7 +540,7 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
                 r[i] = P.rank + (in[i] ? cell0 + 32 * i + lane : 0) * P.rank_ld;
             }
             for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
-                if (MODE == MODE_B8) {
+                if (BYTES) {
                     uint32_t w = 0;
 #pragma unroll
                     for (int i = 0; i < NC; ++i) w |= (in[i] ? (uint32_t)r[i][g] : 0u) << (8 * i);
@@ -901,13 +920,13 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
     PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    P.try_b8 = fast ? 1 : 0;
     P.max_rank = d_flags.as<int32_t>();
     const int slow_grid = ctx->n_sm * 2;  // persistent CTAs of the global-tile path
-    uint32_t *s_tiles = nullptr;          // !fast: packed tiles of one launch
-    if (!fast && !(s_tiles = (uint32_t *)pp_slab(ctx, SLAB_MISC, (size_t)((chunk_cells + TILE_CELLS - 1) / TILE_CELLS) * U * 128)))
-        return PP_ENOMEM;
+    uint32_t *s_tiles = nullptr;          // !fast: packed tiles of one launch, 64-cell tiles then 128-cell tiles
+    const size_t tiles64 = (size_t)((chunk_cells + TILE_CELLS - 1) / TILE_CELLS), tiles128 = (tiles64 + 1) / 2;
+    if (!fast && !(s_tiles = (uint32_t *)pp_slab(ctx, SLAB_MISC, (tiles64 + tiles128) * U * 128))) return PP_ENOMEM;
     P.gtile = s_tiles;
+    P.gtile_b8 = s_tiles + tiles64 * U * 32;
     // classes by decreasing cost (slots) + the dynamic work-unit counter
     DevBuf d_order, d_counter, d_below;
     {
@@ -938,7 +957,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         bool sliced = false;
         for (const int64_t nc : {chunk_cells, n_cells % chunk_cells}) {
             sliced = sliced || slices_for(nc, TILE_CELLS, P.k_count, &len) > 1;
-            sliced = sliced || (fast && slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &len) > 1);
+            sliced = sliced || slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &len) > 1;
         }
         P.accumulate = (n_passes > 1 || sliced) ? 1 : 0;
         if (P.accumulate) {
@@ -951,18 +970,21 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         P.n_slices = slices_for(nc, TILE_CELLS, P.k_count, &P.slice_len);
         P.n_slices_b8 = slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &P.slice_len_b8);
         const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes * P.n_slices;
+        const int64_t n_units_b8 = (nc + Mode<MODE_B8>::CELLS - 1) / Mode<MODE_B8>::CELLS * n_classes * P.n_slices_b8;
         cudaMemsetAsync(d_counter.p, 0, 2 * sizeof(int), st);
+        // count data (<= 128 distinct values per cell) takes the 4-cells-per-word kernel, anything else the 2-cell
+        // kernel: both are enqueued, the device-side flag written by the rank kernel lets exactly one of them run
+        ++ctx->launches;
         if (fast) {
-            // count data (<= 128 distinct values per cell) takes the 4-cells-per-word kernel, anything else the fp16
-            // kernel: both are enqueued, the device-side flag written by the rank kernel lets exactly one of them run
-            const int64_t n_units_b8 = (nc + Mode<MODE_B8>::CELLS - 1) / Mode<MODE_B8>::CELLS * n_classes * P.n_slices_b8;
-            ++ctx->launches;
             score_kernel<MODE_B8><<<(unsigned)std::min<int64_t>(n_units_b8, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
             score_kernel<MODE_F16><<<(unsigned)std::min<int64_t>(n_units, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
         } else {
-            ++ctx->launches;
-            pack_tiles_kernel<<<dim3((unsigned)((nc + TILE_CELLS - 1) / TILE_CELLS), (unsigned)((U + 31) / 32)), 256, 0, st>>>(
-                P.rank, rank_ld, nc, U, s_tiles);
+            ctx->launches += 2;
+            const unsigned gy = (unsigned)((U + 31) / 32);
+            pack_tiles_kernel<<<dim3((unsigned)((nc + 63) / 64), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U, s_tiles);
+            pack_tiles_b8_kernel<<<dim3((unsigned)((nc + 127) / 128), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U,
+                                                                                      s_tiles + tiles64 * U * 32);
+            score_kernel<MODE_GLOBAL_B8><<<(unsigned)std::min<int64_t>(n_units_b8, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
             score_kernel<MODE_GLOBAL><<<(unsigned)std::min<int64_t>(n_units, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
         }
     };
