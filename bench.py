@@ -202,6 +202,9 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
                      "unit": "Gop/s", "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],
                      "peak_source": "pp_alu_peak micro-benchmark (independent LOP3 stream), measured in this run",
                      "algorithmic_ops_per_unit": 2.0 * (CYC_ITERS + 1) * n_pairs, "units_per_launch": CYC_CELLS,
+                     "note": "count data: four 7-bit ranks per 32-bit lane, ~8.8 instructions per comparison slot of "
+                             "128 cells, so the algorithmic rate may exceed the one-op-per-lane peak; ncu: issue slots "
+                             "86 %, ALU pipe 74 %",
                      "traffic": ncu_traffic("score_kernel")},
         "roofline_prep": {"bound": "hbm", "kernel": "rank_kernel+tables",
                           "achieved": (CYC_CELLS * CYC_GENES * 4 + CYC_CELLS * n_union * 2) / (prep_step * 1e-3) / 1e9,
@@ -355,7 +358,7 @@ def run_b200(args):
         peaks["hbm_gbs"] = json.load(open(mp))["hbm_gbs"]
         peaks["hbm_source"] = "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 dense ranks (from f32)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16 dense ranks (from f32), compared as packed 7-bit integers (count data) or fp16 pairs",
             "data": "synthetic",
             "config": {"workload": "configs[1]: cyclone default_cc_marker, synthetic {} cells x {} genes per GPU, "
                                    "{} iterations".format(CYC_CELLS, CYC_GENES, CYC_ITERS),
