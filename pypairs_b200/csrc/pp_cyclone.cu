@@ -29,6 +29,7 @@
 #include <thread>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <string.h>
 
 #include "pp_common.cuh"
 
@@ -805,8 +806,26 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
     PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
     int rc = PP_OK;
+    // One-launch inputs (device matrix, or a host matrix of at most one wave of tiles): copy + rank go first, the
+    // host-side table work below then overlaps them (tables are built on the copy stream).
+    if (!csr && !pipelined) {
+        const void *dx = x0;
+        if (!x_is_device) {
+            void *s_x = pp_slab(ctx, SLAB_X, (size_t)n_cells * ld * esz);
+            if (!s_x) return PP_ENOMEM;
+            PP_CUDA(cudaEventRecord(ctx->ev[6], st));
+            PP_CUDA(cudaMemcpyAsync(s_x, x0, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
+            ctx->tm.h2d_bytes += (int64_t)((size_t)n_cells * ld * esz);
+            PP_CUDA(cudaEventRecord(ctx->ev[7], st));
+            dx = s_x;
+        }
+        rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_uni.as<int32_t>(), U,
+                            (uint16_t *)s_rank, rank_ld, d_flags.as<int32_t>());
+        if (rc) return rc;
+    }
 
-    // ---- per-class permutation + pair tables (host MT19937 work overlaps the rank kernel)
+    // ---- per-class permutation + pair tables, on the copy stream
+    cudaStream_t ts = ctx->copy_stream;
     std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_src(n_classes), d_mask(n_classes), d_map(n_classes);
     std::vector<ClassDesc> cds(n_classes);
     const int32_t *ext = perm_tables;
@@ -822,16 +841,16 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         for (int i = 0; i < nu; ++i)
             map[i] = (uint16_t)(std::lower_bound(uni.begin(), uni.end(), used_idx[used_off[c] + i]) - uni.begin());
         const size_t pcnt = (size_t)nu * iterations;
-        PP_CUDA(d_perm[c].alloc(pcnt * 2, st));
+        PP_CUDA(d_perm[c].alloc(pcnt * 2, ts));
         if (rng_mode == PP_RNG_PHILOX) {
             if (pcnt) {
-                philox_perm_kernel<<<(iterations + 63) / 64, 64, 0, st>>>(d_perm[c].as<uint16_t>(), nu, iterations,
+                philox_perm_kernel<<<(iterations + 63) / 64, 64, 0, ts>>>(d_perm[c].as<uint16_t>(), nu, iterations,
                                                                          (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)c);
                 PP_CHECK_LAUNCH();
             }
         } else if (rng_mode == PP_RNG_MT19937) {
             const std::vector<uint16_t> &t = mt_table_cached((uint32_t)seed, nu, iterations);
-            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, st));
+            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, ts));
         } else {
             std::vector<uint16_t> t(pcnt);
             for (size_t i = 0; i < pcnt; ++i) {
@@ -839,23 +858,23 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 t[i] = (uint16_t)ext[i];
             }
             ext += pcnt;
-            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, st));
-            PP_CUDA(cudaStreamSynchronize(st));  // t is a local
+            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, ts));
+            PP_CUDA(cudaStreamSynchronize(ts));  // t is a local
         }
         const double t_b = now_ms();
-        PP_CUDA(d_map[c].alloc(sizeof(uint16_t) * map.size(), st));
-        PP_CUDA(cudaMemcpyAsync(d_map[c].p, map.data(), sizeof(uint16_t) * map.size(), cudaMemcpyHostToDevice, st));
-        PP_CUDA(cudaStreamSynchronize(st));  // map is a local
+        PP_CUDA(d_map[c].alloc(sizeof(uint16_t) * map.size(), ts));
+        PP_CUDA(cudaMemcpyAsync(d_map[c].p, map.data(), sizeof(uint16_t) * map.size(), cudaMemcpyHostToDevice, ts));
+        PP_CUDA(cudaStreamSynchronize(ts));  // map is a local
         const StarLayout L = build_star_layout(pairs + 2 * pair_off[c], np, nu);
         const int n_slots = (int)L.slot_src.size();
         if (trace)
             fprintf(stderr, "[pp_cyclone] class %d: %d genes, %d pairs -> %d slots; permutations %.1f ms, star layout %.1f ms\n",
                     c, nu, np, n_slots, t_b - t_a, now_ms() - t_b);
-        PP_CUDA(d_src[c].alloc(sizeof(int32_t) * n_slots, st));
-        PP_CUDA(cudaMemcpyAsync(d_src[c].p, L.slot_src.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
-        PP_CUDA(d_mask[c].alloc(sizeof(uint32_t) * L.n_chunks, st));
-        PP_CUDA(cudaMemcpyAsync(d_mask[c].p, L.start_mask.data(), sizeof(uint32_t) * L.n_chunks, cudaMemcpyHostToDevice, st));
-        PP_CUDA(cudaStreamSynchronize(st));  // L is a local
+        PP_CUDA(d_src[c].alloc(sizeof(int32_t) * n_slots, ts));
+        PP_CUDA(cudaMemcpyAsync(d_src[c].p, L.slot_src.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, ts));
+        PP_CUDA(d_mask[c].alloc(sizeof(uint32_t) * L.n_chunks, ts));
+        PP_CUDA(cudaMemcpyAsync(d_mask[c].p, L.start_mask.data(), sizeof(uint32_t) * L.n_chunks, cudaMemcpyHostToDevice, ts));
+        PP_CUDA(cudaStreamSynchronize(ts));  // L is a local
         cds[c].E = nullptr;  // allocated below, once the size of a pass is known
         cds[c].start_mask = d_mask[c].as<uint32_t>();
         cds[c].n_slots = n_slots;
@@ -882,29 +901,30 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     const int n_passes = iterations > 0 ? (iterations + k_pass - 1) / k_pass : 1;
     for (int c = 0; c < n_classes; ++c) {
-        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(k_pass + 1) * cds[c].n_slots, st));
+        PP_CUDA(d_T[c].alloc(sizeof(uint32_t) * (size_t)(k_pass + 1) * cds[c].n_slots, ts));
         cds[c].E = d_T[c].as<uint32_t>();
     }
-    auto build_tables = [&](int k_base, int k_count) -> int {
+    auto build_tables = [&](int k_base, int k_count, cudaStream_t bs) -> int {
         for (int c = 0; c < n_classes; ++c) {
             const int nu = (int)(used_off[c + 1] - used_off[c]);
             dim3 grid((cds[c].n_slots + 255) / 256, k_count + 1);
-            build_table_kernel<<<grid, 256, 0, st>>>(d_perm[c].as<uint16_t>(), d_src[c].as<int32_t>(),
+            build_table_kernel<<<grid, 256, 0, bs>>>(d_perm[c].as<uint16_t>(), d_src[c].as<int32_t>(),
                                                      d_map[c].as<uint16_t>(), nu, cds[c].n_slots, k_base,
                                                      d_T[c].as<uint32_t>());
             PP_CHECK_LAUNCH();
         }
         return PP_OK;
     };
-    rc = build_tables(0, std::min(k_pass, iterations));
+    rc = build_tables(0, std::min(k_pass, iterations), ts);
     if (rc) return rc;
-    PP_CUDA(d_cd.alloc(sizeof(ClassDesc) * n_classes, st));
-    PP_CUDA(cudaMemcpyAsync(d_cd.p, cds.data(), sizeof(ClassDesc) * n_classes, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_cd.alloc(sizeof(ClassDesc) * n_classes, ts));
+    PP_CUDA(cudaMemcpyAsync(d_cd.p, cds.data(), sizeof(ClassDesc) * n_classes, cudaMemcpyHostToDevice, ts));
     const size_t out_cnt = (size_t)n_classes * n_cells;
     PP_CUDA(d_scores.alloc(sizeof(double) * out_cnt, st));
     if (out_obs_hits) PP_CUDA(d_oh.alloc(sizeof(int32_t) * out_cnt, st));
     if (out_obs_total) PP_CUDA(d_ot.alloc(sizeof(int32_t) * out_cnt, st));
-    PP_CUDA(cudaEventRecord(ctx->ev[1], st));  // tables enqueued
+    PP_CUDA(cudaEventRecord(ctx->ev[1], ts));  // tables enqueued
+    bool tables_awaited = false;
 
     ScoreParams P;
     P.rank_ld = rank_ld;
@@ -967,6 +987,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     P.below = d_below.as<int32_t>();
     auto launch_score = [&](int64_t nc) {
+        if (!tables_awaited) cudaStreamWaitEvent(st, ctx->ev[1], 0);
+        tables_awaited = true;
         P.n_slices = slices_for(nc, TILE_CELLS, P.k_count, &P.slice_len);
         P.n_slices_b8 = slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &P.slice_len_b8);
         const int64_t n_units = (nc + TILE_CELLS - 1) / TILE_CELLS * n_classes * P.n_slices;
@@ -994,7 +1016,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         for (int pass = 1; pass < n_passes; ++pass) {
             const int k_base = pass * k_pass;
             P.k_count = std::min(k_pass, iterations - k_base);
-            const int brc = build_tables(k_base, P.k_count);
+            const int brc = build_tables(k_base, P.k_count, st);
             if (brc) return brc;
             for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells) {
                 P.rank = (uint16_t *)s_rank + c0 * rank_ld;
@@ -1056,20 +1078,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         if (rc) return rc;
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
         PP_CUDA(cudaStreamSynchronize(st));  // dcsr goes out of scope
-    } else if (!pipelined) {
-        const void *dx = x0;
-        if (!x_is_device) {
-            void *s_x = pp_slab(ctx, SLAB_X, (size_t)n_cells * ld * esz);
-            if (!s_x) return PP_ENOMEM;
-            PP_CUDA(cudaEventRecord(ctx->ev[6], st));
-            PP_CUDA(cudaMemcpyAsync(s_x, x0, (size_t)n_cells * ld * esz, cudaMemcpyHostToDevice, st));
-            ctx->tm.h2d_bytes += (int64_t)((size_t)n_cells * ld * esz);
-            PP_CUDA(cudaEventRecord(ctx->ev[7], st));
-            dx = s_x;
-        }
-        rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_uni.as<int32_t>(), U,
-                            (uint16_t *)s_rank, rank_ld, d_flags.as<int32_t>());
-        if (rc) return rc;
+    } else if (!pipelined) {  // copied and ranked above
+        PP_CUDA(cudaStreamWaitEvent(st, ctx->ev[1], 0));
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
         P.rank = (uint16_t *)s_rank;
         P.n_cells = n_cells;
@@ -1191,24 +1201,40 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             score_ms += ms;
         }
     }
-    PP_CUDA(cudaMemcpyAsync(out_scores, d_scores.p, sizeof(double) * out_cnt, cudaMemcpyDeviceToHost, st));
-    if (out_obs_hits) PP_CUDA(cudaMemcpyAsync(out_obs_hits, d_oh.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));
-    if (out_obs_total) PP_CUDA(cudaMemcpyAsync(out_obs_total, d_ot.p, sizeof(int32_t) * out_cnt, cudaMemcpyDeviceToHost, st));
-    int32_t flags[4];
-    PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    // results: device -> pinned staging -> the caller's (pageable) arrays; a direct copy would be staged by the driver
+    // at a fraction of the rate
+    const size_t sc_bytes = sizeof(double) * out_cnt, ob_bytes = sizeof(int32_t) * out_cnt;
+    const size_t stage_bytes = sc_bytes + (out_obs_hits ? ob_bytes : 0) + (out_obs_total ? ob_bytes : 0) + 16;
+    if (ctx->pin_out_bytes < stage_bytes) {
+        if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+        ctx->pin_out = nullptr;
+        ctx->pin_out_bytes = 0;
+        const size_t want = std::max<size_t>(stage_bytes * 2, (size_t)8 << 20);
+        PP_CUDA(cudaHostAlloc(&ctx->pin_out, want, cudaHostAllocDefault));
+        ctx->pin_out_bytes = want;
+    }
+    uint8_t *stage_p = (uint8_t *)ctx->pin_out;
+    int32_t *flags = (int32_t *)stage_p;
+    uint8_t *st_sc = stage_p + 16, *st_oh = st_sc + sc_bytes, *st_ot = st_oh + (out_obs_hits ? ob_bytes : 0);
+    PP_CUDA(cudaMemcpyAsync(st_sc, d_scores.p, sc_bytes, cudaMemcpyDeviceToHost, st));
+    if (out_obs_hits) PP_CUDA(cudaMemcpyAsync(st_oh, d_oh.p, ob_bytes, cudaMemcpyDeviceToHost, st));
+    if (out_obs_total) PP_CUDA(cudaMemcpyAsync(st_ot, d_ot.p, ob_bytes, cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaEventRecord(ctx->ev[5], st));
     PP_CUDA(cudaStreamSynchronize(st));
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_cyclone: NaN in the expression matrix");
+    memcpy(out_scores, st_sc, sc_bytes);
+    if (out_obs_hits) memcpy(out_obs_hits, st_oh, ob_bytes);
+    if (out_obs_total) memcpy(out_obs_total, st_ot, ob_bytes);
     if (pipelined) {  // copies overlap compute: h2d = copy-stream span, main = sum of the score launches
         ctx->tm.h2d_ms = copy_ms;
         ctx->tm.main_ms = score_ms;
         cudaEventElapsedTime(&ctx->tm.prep_ms, ctx->ev[0], ctx->ev[1]);
     } else {
-        float t_tab = 0.f, t_rank = 0.f;
+        float t_prep = 0.f;  // everything before the first score launch: copy, rank, tables
         if (!x_is_device || csr) cudaEventElapsedTime(&ctx->tm.h2d_ms, ctx->ev[6], ctx->ev[7]);
-        cudaEventElapsedTime(&t_tab, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&t_rank, ctx->ev[1], ctx->ev[3]);
-        ctx->tm.prep_ms = t_tab + t_rank - ctx->tm.h2d_ms;
+        cudaEventElapsedTime(&t_prep, ctx->ev[0], ctx->ev[3]);
+        ctx->tm.prep_ms = t_prep - ctx->tm.h2d_ms;
         cudaEventElapsedTime(&ctx->tm.main_ms, ctx->ev[3], ctx->ev[4]);
     }
     cudaEventElapsedTime(&ctx->tm.post_ms, ctx->ev[4], ctx->ev[5]);
