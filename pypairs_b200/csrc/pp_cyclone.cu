@@ -6,21 +6,22 @@
 // cell's used-gene vector IN PLACE (cumulatively) and re-score.  Because every cell
 // reseeds (:226), all cells of a class see the same permutation sequence, a function of
 // (seed, n_used, iterations) only.  We therefore build, once per class, the table
-//     T[k][p] = (perm_k[pair_p.0], perm_k[pair_p.1])      k = 0 (identity) .. iterations
-// and the k-th null score of ANY cell is the observed score evaluated through T[k] on the
-// un-permuted vector.  T is shared by all cells (L2 resident, 4 B per pair evaluation per
-// 64 cells), cells sit in the lanes of a warp so an index is a broadcast and a gather of
-// v[gene] is a conflict-free shared-memory row read.
+//     E[k][slot] = position of the slot's gene under permutation k   k = 0 (identity) .. iterations
+// (slots = the class's pairs regrouped into stars, see build_star_layout) and the k-th null
+// score of ANY cell is the observed score evaluated through E[k] on the un-permuted vector.
+// E is shared by all cells (L2 resident), cells sit in the lanes of a warp so a slot
+// offset is a broadcast and a gather of v[gene] is a conflict-free shared-memory row read.
 //
 // Data layout
 //   rank  u16 [n_cells][U]      per-cell dense ranks over the union of all classes' used
 //                               genes (pp_rank.cu); order and ties inside any class subset
 //                               are preserved, so every `a != b`, `a > b` is bit-exact
-//   tile  u32 smem [U][32]      one CTA = 64 cells: lane l holds cell l (low half) and cell
-//                               l + 32 (high half) of the tile
-//   T     u32 [iters+1][P_c]    union positions (lo16 | hi16) per class
+//   tile  u32 smem [U][32]      one CTA = 64 cells as two fp16 ranks per lane, or 128 cells as
+//                               four 7-bit ranks per lane (count data); global memory beyond
+//                               1 680 marker genes
+//   E     u32 [1+iters][S_c]    byte offset (128 * union position) of every slot, per class
 // Scores: hits_k/total_k < hits_0/total_0 is decided by exact integer cross
-// multiplication (counts < 2^16), NaN rules of get_proportion (:217-218) applied to both
+// multiplication in 64 bits, NaN rules of get_proportion (:217-218) applied to both
 // sides; score = below / iterations as one IEEE double division (:246).
 #include <algorithm>
 #include <chrono>
@@ -486,6 +487,7 @@ __device__ __forceinline__ double final_score(uint32_t below, int iterations, in
     return nan("");
 }
 
+// (two CTAs per SM for the global-tile modes were measured slower: 28 vs 24 ms, two tiles thrash one L1)
 template <int MODE>
 __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScoreParams P) {
     constexpr int NC = Mode<MODE>::NC, CELLS = Mode<MODE>::CELLS;
@@ -769,7 +771,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
     const int U = (int)uni.size();
     if (U > 32768) return pp_fail(ctx, PP_ELIMIT, "pp_cyclone: %d distinct marker genes (max 32768)", U);
-    // FAST path: the whole tile (128 B per gene) + staging buffers fit in shared memory and ranks < 2048
+    // shared-memory modes: the whole tile (128 B per gene) + staging buffers fit in shared memory and ranks < 2048
     const bool fast = U <= 2048 && (size_t)U * 128 + (size_t)SCORE_WARPS * STAGE_BYTES + 2048 <=
                                        (size_t)std::min(ctx->smem_optin, 227 * 1024);
     const size_t dyn_smem = (fast ? (size_t)U * 128 : 0) + (size_t)SCORE_WARPS * STAGE_BYTES;
