@@ -362,3 +362,31 @@ def test_table_passes_give_identical_scores(monkeypatch, n_cells, n_genes, n_use
     um[used] = 1
     sub = slice(0, 64)
     assert np.array_equal(got[0][0][sub], orc.phase_scores(x[sub], 500, 10, 5, pairs, um))
+
+
+def test_seven_bit_kernel_boundary_and_mid_call_switch():
+    """The four-cells-per-word kernel runs while no ranked cell has more than 128 distinct values (max dense rank 127);
+    one more distinct value switches to the fp16 kernel -- also in the middle of a chunked call, where early chunks
+    were scored by one kernel and later chunks by the other.  Scores must be the oracle's either way."""
+    rng = np.random.default_rng(77)
+    n_genes, n_used = 600, 300
+    used = np.sort(rng.choice(n_genes, n_used, replace=False))
+    um = np.zeros(n_genes, dtype=np.uint8)
+    um[used] = 1
+    pairs = rng.integers(0, n_used, (1500, 2))
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+
+    def cells(n, n_distinct):
+        x = rng.integers(0, n_distinct, (n, n_genes)).astype(np.float32)
+        x[:, used[:n_distinct]] = np.arange(n_distinct, dtype=np.float32)  # every cell really has n_distinct values
+        return x
+
+    for n_distinct in (128, 129):
+        x = cells(100, n_distinct)
+        got = _ffi().phase_scores(x, 300, 10, 5, pairs, um)
+        assert np.array_equal(got, orc.phase_scores(x, 300, 10, 5, pairs, um), equal_nan=True), n_distinct
+    # host input longer than one wave of tiles is chunked: 9 600 low-rank cells, then 400 cells with 200 distinct values
+    x = np.concatenate([cells(9600, 20), cells(400, 200)])
+    got = _ffi().phase_scores(x, 200, 10, 5, pairs, um)
+    for sl in (slice(0, 96), slice(9472, 9472 + 64), slice(9600, 9600 + 64), slice(9936, 10000)):
+        assert np.array_equal(got[sl], orc.phase_scores(x[sl], 200, 10, 5, pairs, um), equal_nan=True)
