@@ -131,6 +131,7 @@ __global__ void philox_perm_kernel(uint16_t *__restrict__ table, int n, int iter
 // (k = 0: identity = observed).
 constexpr int CHUNK_SLOTS = 128;                  // 128 slots * 4 B = 512 B = one 16-byte cp.async per lane
 constexpr int STAGE_BYTES = 2 * CHUNK_SLOTS * 4;  // double buffer per warp
+static_assert(CHUNK_SLOTS <= 255, "MODE_B8 keeps per-chunk counts in bytes");
 
 struct StarLayout {
     std::vector<int32_t> slot_src;     // class-compact gene index of every slot
