@@ -51,7 +51,17 @@ constexpr int BM_WORDS = 2048;  // 65 536-bit presence bitmap of the count fast 
 __device__ __forceinline__ bool is_small_count(float v) { return v >= 0.0f && v < 65536.0f && v == truncf(v); }
 __device__ __forceinline__ bool is_small_count(double v) { return v >= 0.0 && v < 65536.0 && v == trunc(v); }
 
-struct RankSmem {
+// "few distinct values" path: a cell whose kept genes take at most HT_MAX distinct values (normalised counts, log1p,
+// ...) is ranked by sorting only those values: shared-memory hash set -> compaction -> bitonic sort -> binary search
+constexpr int HT_SLOTS = 2048, HT_MAX = 1024;
+__device__ __forceinline__ uint32_t hash_slot(uint32_t k) { return (k * 0x9E3779B1u) >> 21; }
+__device__ __forceinline__ uint32_t hash_slot(uint64_t k) { return (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 53); }
+__device__ __forceinline__ uint32_t smem_cas(uint32_t *p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
+__device__ __forceinline__ uint64_t smem_cas(uint64_t *p, uint64_t cmp, uint64_t v) {
+    return (uint64_t)atomicCAS((unsigned long long *)p, (unsigned long long)cmp, (unsigned long long)v);
+}
+
+struct alignas(16) RankSmem {
     uint32_t bitmap[BM_WORDS];
     uint32_t bm_prefix[BM_WORDS];
     uint32_t whist[RANK_WARPS][256];  // per-warp digit histogram -> running scatter offsets
@@ -59,7 +69,10 @@ struct RankSmem {
     uint32_t wtot[RANK_WARPS];
     unsigned long long vary[RANK_WARPS];
     unsigned long long vary_all;
+    int n_distinct;
 };
+static_assert(sizeof(uint64_t) * HT_SLOTS <= sizeof(uint32_t) * 2 * BM_WORDS, "hash set overlays bitmap + bm_prefix");
+static_assert(sizeof(uint64_t) * HT_MAX <= sizeof(uint32_t) * RANK_WARPS * 256, "sorted values overlay whist");
 
 template <typename T>
 __global__ void __launch_bounds__(RANK_THREADS)
@@ -141,6 +154,104 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                     out[g] = (uint16_t)(sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & ((1u << (u & 31)) - 1u)));
                 }
                 __syncthreads();  // bitmap / prefix / vals reused by the next cell
+                continue;
+            }
+        }
+        // ---- 0b. few distinct values (any real numbers): hash set of the keys, sort the distinct ones, binary search
+        {
+            K *ht = reinterpret_cast<K *>(&sm.bitmap[0]);        // HT_SLOTS keys, ~K(0) = empty (a NaN pattern)
+            K *sorted = reinterpret_cast<K *>(&sm.whist[0][0]);  // HT_MAX keys
+            const K EMPTY = ~(K)0;
+            for (int i = tid; i < HT_SLOTS; i += RANK_THREADS) ht[i] = EMPTY;
+            if (tid == 0) sm.n_distinct = 0;
+            __syncthreads();
+            bool bad = false;  // NaN, or too many distinct values
+            for (int g0 = tid; g0 < n && !bad; g0 += RANK_THREADS * 4) {
+                T v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int g = g0 + j * RANK_THREADS;
+                    v[j] = g < n ? xr[gene_cols[g]] : (T)0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (g0 + j * RANK_THREADS >= n || bad) continue;
+                    const K k = key_of(v[j], bad);
+                    if (bad) break;
+                    uint32_t slot = hash_slot(k);
+                    for (;;) {
+                        const K cur = *(volatile K *)&ht[slot];
+                        if (cur == k) break;
+                        if (cur == EMPTY) {
+                            const K old = smem_cas(&ht[slot], EMPTY, k);
+                            if (old == EMPTY) {
+                                if (atomicAdd(&sm.n_distinct, 1) >= HT_MAX) bad = true;
+                                break;
+                            }
+                            if (old == k) break;
+                        }
+                        if (*(volatile int *)&sm.n_distinct > HT_MAX) {  // the set is being abandoned: stop probing
+                            bad = true;
+                            break;
+                        }
+                        slot = (slot + 1) & (HT_SLOTS - 1);
+                    }
+                }
+            }
+            if (!__syncthreads_or(bad)) {  // CTA-uniform
+                const int D = sm.n_distinct;
+                int P2 = 1;
+                while (P2 < D) P2 <<= 1;
+                // compaction of the non-empty slots: 4 slots per thread, warp scan + warp totals
+                K mine[4];
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mine[j] = ht[tid * 4 + j];
+                    cnt += mine[j] != EMPTY;
+                }
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) sm.wtot[warp] = incl;
+                for (int i = D + tid; i < P2; i += RANK_THREADS) sorted[i] = EMPTY;  // padding sorts to the end
+                __syncthreads();
+                uint32_t pos = incl - cnt;
+                for (int w = 0; w < warp; ++w) pos += sm.wtot[w];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (mine[j] != EMPTY) sorted[pos++] = mine[j];
+                __syncthreads();
+                // bitonic sort of P2 <= 1024 keys: at most one compare-exchange per thread and step
+                for (int size = 2; size <= P2; size <<= 1)
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        if (tid < (P2 >> 1)) {
+                            const int i = 2 * tid - (tid & (stride - 1));  // lower index of this thread's pair
+                            const bool up = ((i & size) == 0);
+                            const K a = sorted[i], b = sorted[i + stride];
+                            if ((a > b) == up) {
+                                sorted[i] = b;
+                                sorted[i + stride] = a;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                if (tid == 0) atomicMax(&flags[0], D - 1);
+                // dense rank = position of the value among the sorted distinct values (row re-read: L1/L2 hits)
+                for (int g = tid; g < n; g += RANK_THREADS) {
+                    bool dummy = false;
+                    const K k = key_of(xr[gene_cols[g]], dummy);
+                    int lo_i = 0, hi_i = D - 1;
+                    while (lo_i < hi_i) {
+                        const int mid = (lo_i + hi_i) >> 1;
+                        if (sorted[mid] < k) lo_i = mid + 1; else hi_i = mid;
+                    }
+                    out[g] = (uint16_t)lo_i;
+                }
+                __syncthreads();  // shared memory reused by the next cell
                 continue;
             }
         }
