@@ -253,8 +253,8 @@ struct ScoreParams {
     int n_classes;
     int iterations, min_iter, min_pairs;
     const ClassDesc *classes;
-    const uint32_t *gtile;     // MODE_GLOBAL: the launch's ranks as [64-cell tiles][n_union][32] words (pack_tiles_kernel)
-    const uint32_t *gtile_b8;  // MODE_GLOBAL_B8: as [128-cell tiles][n_union][32] words (pack_tiles_b8_kernel)
+    const uint32_t *gtile;     // the launch's ranks as [64-cell tiles][n_union][32] words, two 15-bit ranks each (pack_tiles_kernel)
+    const uint32_t *gtile_b8;  // as [128-cell tiles][n_union][32] words, four 7-bit ranks each (pack_tiles_b8_kernel)
     const int32_t *class_order;  // classes by decreasing cost: work unit u = (class_order[u / n_tiles], tile u % n_tiles)
     int *unit_counter;           // dynamic work-unit counters (zeroed before the launch): [0] 64-cell tiles, [1] MODE_B8
     int n_slices;                // > 1: the iterations of a (class, tile) are split over n_slices work units
@@ -532,28 +532,26 @@ __global__ void __launch_bounds__(SCORE_THREADS, 1) score_kernel(const ScorePara
         const int64_t cell0 = (ct % n_tiles) * CELLS;
         const int k_first = 1 + slice * slice_len;
         const int k_last = min(P.k_count, k_first + slice_len - 1);
-        // load the tile: lane = cell, consecutive genes of one cell hit the same sector (L1)
+        // the tile, already in [gene][lane] order (pack_tiles*_kernel): global-memory modes gather from it in place,
+        // shared-memory modes copy it with coalesced 16-byte loads (a strided read of the rank rows cost ~100 us per
+        // unit, which made small work units expensive)
+        const uint32_t *gt = (BYTES ? P.gtile_b8 : P.gtile) + (size_t)(ct % n_tiles) * P.n_union * 32;
         if (!SMEM) {
-            tile_lane = (uint64_t)(uintptr_t)((BYTES ? P.gtile_b8 : P.gtile) + (size_t)(ct % n_tiles) * P.n_union * 32 + lane);
+            tile_lane = (uint64_t)(uintptr_t)(gt + lane);
         } else {
-            const uint16_t *r[NC];
-            bool in[NC];
+            const uint4 *src4 = reinterpret_cast<const uint4 *>(gt);
+            uint4 *dst4 = reinterpret_cast<uint4 *>(tile);
+            for (int i = tid; i < P.n_union * 8; i += SCORE_THREADS) {
+                uint4 v = __ldg(src4 + i);
+                if (!BYTES) {  // two 15-bit integers -> two fp16 numbers (exact: ranks < 2048)
+                    uint32_t *w = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                in[i] = cell0 + 32 * i + lane < P.n_cells;
-                r[i] = P.rank + (in[i] ? cell0 + 32 * i + lane : 0) * P.rank_ld;
-            }
-            for (int g = warp; g < P.n_union; g += SCORE_WARPS) {
-                if (BYTES) {
-                    uint32_t w = 0;
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) w |= (in[i] ? (uint32_t)r[i][g] : 0u) << (8 * i);
-                    tile[g * 32 + lane] = w;
-                } else {
-                    const uint32_t lo = in[0] ? r[0][g] : 0u, hi = in[1] ? r[1][g] : 0u;
-                    const __half2 v = __floats2half2_rn((float)lo, (float)hi);  // exact: ranks < 2048
-                    tile[g * 32 + lane] = *reinterpret_cast<const uint32_t *>(&v);
+                    for (int j = 0; j < 4; ++j) {
+                        const __half2 h = __floats2half2_rn((float)(w[j] & 0xffffu), (float)(w[j] >> 16));
+                        w[j] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
                 }
+                dst4[i] = v;
             }
         }
         {
@@ -675,8 +673,22 @@ const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
 // [r0, r0 + nr) of a host matrix into a dense [nr, n_cols_kept] pinned buffer, rows split over threads.
 template <typename T>
 void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *cols, int n_kept, T *dst, int n_threads) {
+    // four rows at a time: four independent miss streams per thread (measured on the 16-core box, 100k x 20k f32,
+    // 1 479 columns: 65 ms row by row, 49 ms interleaved; software prefetch of the next row: 58 ms)
     auto work = [=](int64_t a, int64_t b) {
-        for (int64_t r = a; r < b; ++r) {
+        int64_t r = a;
+        for (; r + 4 <= b; r += 4) {
+            const T *s0 = x + (r0 + r) * ld, *s1 = s0 + ld, *s2 = s1 + ld, *s3 = s2 + ld;
+            T *d0 = dst + r * n_kept, *d1 = d0 + n_kept, *d2 = d1 + n_kept, *d3 = d2 + n_kept;
+            for (int j = 0; j < n_kept; ++j) {
+                const int64_t c = cols[j];
+                d0[j] = s0[c];
+                d1[j] = s1[c];
+                d2[j] = s2[c];
+                d3[j] = s3[c];
+            }
+        }
+        for (; r < b; ++r) {
             const T *src = x + (r0 + r) * ld;
             T *d = dst + r * n_kept;
             for (int j = 0; j < n_kept; ++j) d[j] = src[cols[j]];
@@ -945,9 +957,9 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     P.max_rank = d_flags.as<int32_t>();
     const int slow_grid = ctx->n_sm * 2;  // persistent CTAs of the global-tile path
-    uint32_t *s_tiles = nullptr;          // !fast: packed tiles of one launch, 64-cell tiles then 128-cell tiles
+    uint32_t *s_tiles = nullptr;          // packed tiles of one launch, 64-cell tiles then 128-cell tiles
     const size_t tiles64 = (size_t)((chunk_cells + TILE_CELLS - 1) / TILE_CELLS), tiles128 = (tiles64 + 1) / 2;
-    if (!fast && !(s_tiles = (uint32_t *)pp_slab(ctx, SLAB_MISC, (tiles64 + tiles128) * U * 128))) return PP_ENOMEM;
+    if (!(s_tiles = (uint32_t *)pp_slab(ctx, SLAB_MISC, (tiles64 + tiles128) * U * 128))) return PP_ENOMEM;
     P.gtile = s_tiles;
     P.gtile_b8 = s_tiles + tiles64 * U * 32;
     // classes by decreasing cost (slots) + the dynamic work-unit counter
@@ -963,13 +975,15 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     P.class_order = d_order.as<int32_t>();
     P.unit_counter = d_counter.as<int>();
-    // Launches with fewer (class, tile) units than ~3 per SM (few cells, the reference's own use case) split each
-    // unit's iterations into slices of >= 2 iterations per warp, aiming at ~4 units per SM.
+    // Launches with fewer (class, tile) units than ~8 per SM (few cells -- the reference's own use case -- and the chunks
+    // of the host pipeline) split each unit's iterations into slices of >= 2 iterations per warp, aiming at ~12 units per
+    // SM, so that the last, partly idle wave of units is short.  (A unit costs a tile copy of a few microseconds and one
+    // extra evaluation of the observed row.)
     auto slices_for = [&](int64_t nc, int tile_cells, int k_count, int *slice_len) {
         *slice_len = std::max(k_count, 1);
         const int64_t units0 = (nc + tile_cells - 1) / tile_cells * n_classes;
-        if (nc <= 0 || units0 >= 3 * (int64_t)ctx->n_sm || k_count < 4 * SCORE_WARPS) return 1;
-        const int64_t want = (4 * (int64_t)ctx->n_sm + units0 - 1) / units0;
+        if (nc <= 0 || units0 >= 8 * (int64_t)ctx->n_sm || k_count < 4 * SCORE_WARPS) return 1;
+        const int64_t want = (12 * (int64_t)ctx->n_sm + units0 - 1) / units0;
         const int64_t len = ((k_count + want - 1) / want + SCORE_WARPS - 1) / SCORE_WARPS * SCORE_WARPS;
         *slice_len = (int)std::max<int64_t>(len, 2 * SCORE_WARPS);
         return (k_count + *slice_len - 1) / *slice_len;
@@ -977,12 +991,9 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.k_count = std::min(k_pass, iterations);
     {
         int len;
-        bool sliced = false;
-        for (const int64_t nc : {chunk_cells, n_cells % chunk_cells}) {
-            sliced = sliced || slices_for(nc, TILE_CELLS, P.k_count, &len) > 1;
-            sliced = sliced || slices_for(nc, Mode<MODE_B8>::CELLS, P.k_count, &len) > 1;
-        }
-        P.accumulate = (n_passes > 1 || sliced) ? 1 : 0;
+        const bool sliced = slices_for(n_cells, TILE_CELLS, P.k_count, &len) > 1 ||
+                            slices_for(n_cells, Mode<MODE_B8>::CELLS, P.k_count, &len) > 1;
+        P.accumulate = (n_passes > 1 || sliced || chunk_cells < n_cells) ? 1 : 0;  // chunked calls: launches of any size
         if (P.accumulate) {
             PP_CUDA(d_below.alloc(sizeof(int32_t) * out_cnt, st));
             PP_CUDA(cudaMemsetAsync(d_below.p, 0, sizeof(int32_t) * out_cnt, st));
@@ -999,16 +1010,15 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         cudaMemsetAsync(d_counter.p, 0, 2 * sizeof(int), st);
         // count data (<= 128 distinct values per cell) takes the 4-cells-per-word kernel, anything else the 2-cell
         // kernel: both are enqueued, the device-side flag written by the rank kernel lets exactly one of them run
-        ++ctx->launches;
+        ctx->launches += 3;
+        const unsigned gy = (unsigned)((U + 31) / 32);
+        pack_tiles_kernel<<<dim3((unsigned)((nc + 63) / 64), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U, s_tiles);
+        pack_tiles_b8_kernel<<<dim3((unsigned)((nc + 127) / 128), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U,
+                                                                                  s_tiles + tiles64 * U * 32);
         if (fast) {
             score_kernel<MODE_B8><<<(unsigned)std::min<int64_t>(n_units_b8, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
             score_kernel<MODE_F16><<<(unsigned)std::min<int64_t>(n_units, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
         } else {
-            ctx->launches += 2;
-            const unsigned gy = (unsigned)((U + 31) / 32);
-            pack_tiles_kernel<<<dim3((unsigned)((nc + 63) / 64), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U, s_tiles);
-            pack_tiles_b8_kernel<<<dim3((unsigned)((nc + 127) / 128), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U,
-                                                                                      s_tiles + tiles64 * U * 32);
             score_kernel<MODE_GLOBAL_B8><<<(unsigned)std::min<int64_t>(n_units_b8, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
             score_kernel<MODE_GLOBAL><<<(unsigned)std::min<int64_t>(n_units, slow_grid), SCORE_THREADS, dyn_smem, st>>>(P);
         }
@@ -1148,17 +1158,22 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(cudaStreamWaitEvent(cs, ctx->ev[3], 0));  // buffers exist before the first copy
         PP_CUDA(cudaEventRecord(ev_c0, cs));
         int i = 0;
+        double gather_host_ms = 0.0, wait_host_ms = 0.0;
         for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, ++i) {
             const int b = i & 1;
             const int64_t nc = std::min(chunk_cells, n_cells - c0);
             const void *src = x0 + (size_t)c0 * ld * esz;
             if (host_gather) {
+                const double t_g0 = now_ms();
                 if (i >= 2) PP_CUDA(cudaEventSynchronize(copied[b]));  // H2D two chunks ago has drained pin[b]
+                const double t_g1 = now_ms();
                 if (x_dtype == PP_F64)
                     gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], n_thr);
                 else
                     gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], n_thr);
                 src = ctx->pin[b];
+                wait_host_ms += t_g1 - t_g0;
+                gather_host_ms += now_ms() - t_g1;
             }
             if (i >= 2) PP_CUDA(cudaStreamWaitEvent(cs, freed[b], 0));  // the rank kernel two chunks ago is done
             PP_CUDA(cudaMemcpyAsync(buf[b], src, (size_t)nc * dev_ld * esz, cudaMemcpyHostToDevice, cs));
@@ -1183,6 +1198,9 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             PP_CUDA(cudaEventRecord(e1, st));
         }
         PP_CUDA(cudaEventRecord(ev_c1, cs));
+        if (trace)
+            fprintf(stderr, "[pp_cyclone] %d chunks of %lld cells, %d host threads: gather %.1f ms, waiting for staging buffers %.1f ms\n",
+                    i, (long long)chunk_cells, n_thr, gather_host_ms, wait_host_ms);
         {
             cudaEvent_t e0, e1;
             PP_CUDA(events.make(&e0, cudaEventDefault));

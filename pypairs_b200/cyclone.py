@@ -46,6 +46,34 @@ def filter_marker_pairs(marker_pairs, gene_names):
     return out_pairs, out_used
 
 
+def _label_column(codes, labels):
+    """Column of labels[codes] (code -1 = missing) in the dtype pandas infers for a list of str.  With an Arrow-backed
+    default string dtype (pandas >= 3) the column is decoded from a dictionary array in C++ instead of converting
+    one Python str per row."""
+    import pandas as pd
+    dtype = pd.Series(["a"]).dtype
+    if isinstance(dtype, pd.StringDtype) and getattr(dtype, "storage", None) == "pyarrow":
+        try:
+            import pyarrow as pa
+            idx = pa.array(codes.astype(np.int32), mask=(codes < 0))
+            arr = pa.DictionaryArray.from_arrays(idx, pa.array(list(labels), type=pa.large_string())).dictionary_decode()
+            return pd.array(arr, dtype=dtype)
+        except Exception:  # pragma: no cover - fall back to the generic conversion
+            pass
+    col = np.array(list(labels) + [np.nan], dtype=object)[codes]
+    return col.tolist()
+
+
+def _first_argmax(cols):
+    """np.argmax over a handful of columns (first maximum wins), as column-wise passes: argmax along a short axis is slow."""
+    best = cols[0]
+    arg = np.zeros(len(best), dtype=np.int64)
+    for j in range(1, len(cols)):
+        arg = np.where(cols[j] > best, j, arg)
+        best = np.maximum(best, cols[j])
+    return arg, best
+
+
 def scores_to_frame(scores, keys, sample_names):
     """DataFrame epilogue of cyclone.py:169-181 with positional semantics.
 
@@ -55,22 +83,22 @@ def scores_to_frame(scores, keys, sample_names):
     keys = list(keys)
     df = DataFrame({k: scores[i] for i, k in enumerate(keys)}, columns=keys)
     df.index = sample_names
-    vals = np.asarray(scores, dtype=np.float64).T.reshape(len(sample_names), len(keys))
-    allnan = np.all(np.isnan(vals), axis=1)
-    safe = np.where(np.isnan(vals), -np.inf, vals)
-    arg = np.argmax(safe, axis=1)  # first maximum, NaN skipped (DataFrame.idxmax)
-    row_sum = np.nansum(vals, axis=1)  # DataFrame.sum skips NaN
-    names = np.array(keys, dtype=object)
-    df["max_class"] = np.where(row_sum > 0, names[arg], "N/A").tolist() if len(keys) else []
+    vals = np.asarray(scores, dtype=np.float64).reshape(len(keys), len(sample_names))  # [class, cell]
+    nan = np.isnan(vals)
+    safe = np.where(nan, -np.inf, vals)
+    if len(keys):
+        arg, _ = _first_argmax(safe)  # first maximum, NaN skipped (DataFrame.idxmax)
+        row_sum = np.where(nan, 0.0, vals).sum(axis=0)  # DataFrame.sum skips NaN
+        df["max_class"] = _label_column(np.where(row_sum > 0, arg, len(keys)), keys + ["N/A"])
+    else:
+        df["max_class"] = []
     if len(keys) == 3 and all(e in keys for e in ["G1", "S", "G2M"]):
-        sub = safe[:, [keys.index("G1"), keys.index("G2M")]]
-        sub_nan = np.all(np.isneginf(sub), axis=1)
-        mx = np.where(sub_nan, np.nan, sub.max(axis=1))
-        pick = np.array(["G1", "G2M"], dtype=object)[np.argmax(sub, axis=1)]
-        pred = np.where(mx < 0.5, "S", pick).astype(object)
-        pred[sub_nan] = np.nan  # NaN < 0.5 is False and idxmax of an all-NaN row is NaN
-        df["cc_prediction"] = pred.tolist()
-    del allnan
+        sub = safe[[keys.index("G1"), keys.index("G2M")]]
+        pick, mx = _first_argmax(sub)
+        sub_nan = np.isneginf(mx)
+        codes = np.where(mx < 0.5, 2, pick)
+        codes[sub_nan] = -1  # NaN < 0.5 is False and idxmax of an all-NaN row is NaN
+        df["cc_prediction"] = _label_column(codes, ["G1", "G2M", "S"])
     return df
 
 
