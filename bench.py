@@ -196,7 +196,7 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
                 "host_matrix_bytes": CYC_CELLS * CYC_GENES * 4,
                 "api": "pypairs_b200.pairs.cyclone(ndarray pinned) -> DataFrame; per chunk of cells the library gathers "
                        "the {} marker-gene columns on the host (threads, pinned staging), copies them and runs rank + "
-                       "score, all overlapped; bound by host DRAM bandwidth".format(n_union)},
+                       "score, all overlapped; the gather (16 host threads) and the kernels take about the same time".format(n_union)},
         "roofline": {"bound": "int_alu", "kernel": "score_kernel",
                      "achieved": alg_ops / (main_step * 1e-3) / 1e9, "peak": peaks["lop3_lane_ops_per_s"] / 1e9,
                      "unit": "Gop/s", "frac": alg_ops / (main_step * 1e-3) / peaks["lop3_lane_ops_per_s"],
