@@ -59,6 +59,26 @@ int main(int argc, char **argv) {
                 for (int j = 0; j < n_kept; ++j) { const int c = cols[j]; d0[j] = s0[c]; d1[j] = s1[c]; d2[j] = s2[c]; d3[j] = s3[c]; } }
             for (; r < b; ++r) { const float *s = x + r * ld; float *d = dst + r * n_kept; for (int j = 0; j < n_kept; ++j) d[j] = s[cols[j]]; } });
         printf("  4 rows interleaved:           %.1f ms  (%.1f GB/s of matrix)\n", t * 1e3, gb / t);
+        t = run(n_thr, rows, [&](int64_t a, int64_t b) {
+            int64_t r = a;
+            for (; r + 8 <= b; r += 8) {
+                const float *s0 = x + r * ld; float *d0 = dst + r * n_kept;
+                for (int j = 0; j < n_kept; ++j) { const int c = cols[j];
+#pragma GCC unroll 8
+                    for (int q = 0; q < 8; ++q) d0[q * n_kept + j] = s0[q * ld + c]; } }
+            for (; r < b; ++r) { const float *s = x + r * ld; float *d = dst + r * n_kept; for (int j = 0; j < n_kept; ++j) d[j] = s[cols[j]]; } });
+        printf("  8 rows interleaved:           %.1f ms  (%.1f GB/s of matrix)\n", t * 1e3, gb / t);
+        t = run(n_thr, rows, [&](int64_t a, int64_t b) {
+            int64_t r = a;
+            for (; r + 4 <= b; r += 4) {
+                const float *s0 = x + r * ld, *s1 = s0 + ld, *s2 = s1 + ld, *s3 = s2 + ld; float *d0 = dst + r * n_kept, *d1 = d0 + n_kept, *d2 = d1 + n_kept, *d3 = d2 + n_kept;
+                const float *p0 = s0 + 4 * ld;
+                for (int j = 0; j < n_kept; ++j) { const int c = cols[j];
+                    _mm_prefetch((const char *)(p0 + c), _MM_HINT_T0); _mm_prefetch((const char *)(p0 + ld + c), _MM_HINT_T0);
+                    _mm_prefetch((const char *)(p0 + 2 * ld + c), _MM_HINT_T0); _mm_prefetch((const char *)(p0 + 3 * ld + c), _MM_HINT_T0);
+                    d0[j] = s0[c]; d1[j] = s1[c]; d2[j] = s2[c]; d3[j] = s3[c]; } }
+            for (; r < b; ++r) { const float *s = x + r * ld; float *d = dst + r * n_kept; for (int j = 0; j < n_kept; ++j) d[j] = s[cols[j]]; } });
+        printf("  4 rows + prefetch next 4:     %.1f ms  (%.1f GB/s of matrix)\n", t * 1e3, gb / t);
     }
     return 0;
 }

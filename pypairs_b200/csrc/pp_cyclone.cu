@@ -25,6 +25,8 @@
 // sides; score = below / iterations as one IEEE double division (:246).
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -669,13 +671,70 @@ const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
     return v;
 }
 
+// Worker threads of one pp_cyclone call (spawning 16 threads per chunk cost ~0.5 ms per chunk).  run(fn) executes
+// fn(part, n_parts) on every member -- the calling thread is member 0 -- and returns when all parts are done.
+class HostCrew {
+  public:
+    explicit HostCrew(int n) : n_(std::max(1, n)) {
+        for (int t = 1; t < n_; ++t) threads_.emplace_back([this, t] { loop(t); });
+    }
+    ~HostCrew() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    void run(const std::function<void(int, int)> &fn) {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            fn_ = &fn;
+            pending_ = n_ - 1;
+            ++gen_;
+        }
+        cv_.notify_all();
+        fn(0, n_);
+        std::unique_lock<std::mutex> l(m_);
+        done_cv_.wait(l, [&] { return pending_ == 0; });
+    }
+
+  private:
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int, int)> *f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                f = fn_;
+            }
+            (*f)(t, n_);
+            std::lock_guard<std::mutex> l(m_);
+            if (--pending_ == 0) done_cv_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int, int)> *fn_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 // Host-side gene filtering (the north-star keeps it on the host): copy the marker-gene columns of rows
-// [r0, r0 + nr) of a host matrix into a dense [nr, n_cols_kept] pinned buffer, rows split over threads.
+// [r0, r0 + nr) of a host matrix into a dense [nr, n_cols_kept] pinned buffer, rows split over the crew.
 template <typename T>
-void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *cols, int n_kept, T *dst, int n_threads) {
-    // four rows at a time: four independent miss streams per thread (measured on the 16-core box, 100k x 20k f32,
-    // 1 479 columns: 65 ms row by row, 49 ms interleaved; software prefetch of the next row: 58 ms)
-    auto work = [=](int64_t a, int64_t b) {
+void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *cols, int n_kept, T *dst, HostCrew &crew) {
+    // four rows at a time: four independent miss streams per thread (profiles/hostbench/gather_bench.cpp on the
+    // 16-core box, 100k x 20k f32, 1 479 columns: 65 ms row by row, 49 ms interleaved; a streaming read takes 47 ms)
+    const std::function<void(int, int)> work = [=](int part, int n_parts) {
+        const int64_t a = nr * part / n_parts, b = nr * (part + 1) / n_parts;
         int64_t r = a;
         for (; r + 4 <= b; r += 4) {
             const T *s0 = x + (r0 + r) * ld, *s1 = s0 + ld, *s2 = s1 + ld, *s3 = s2 + ld;
@@ -694,14 +753,7 @@ void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *
             for (int j = 0; j < n_kept; ++j) d[j] = src[cols[j]];
         }
     };
-    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, nr / 64));
-    if (n_threads == 1) {
-        work(0, nr);
-        return;
-    }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, nr * t / n_threads, nr * (t + 1) / n_threads);
-    for (auto &th : pool) th.join();
+    crew.run(work);
 }
 
 int host_threads() {
@@ -1125,6 +1177,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         std::vector<cudaEvent_t> ev_s;
         DevBuf d_ident;
         const int n_thr = host_threads();
+        HostCrew crew(host_gather ? n_thr : 1);
         const int64_t dev_ld = host_gather ? U : ld;  // row length of the device chunk buffers
         const int32_t *dev_cols = d_uni.as<int32_t>();
         cudaStream_t cs = ctx->copy_stream;
@@ -1159,18 +1212,20 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(cudaEventRecord(ev_c0, cs));
         int i = 0;
         double gather_host_ms = 0.0, wait_host_ms = 0.0;
-        for (int64_t c0 = 0; c0 < n_cells; c0 += chunk_cells, ++i) {
+        // the first chunks are an eighth, a quarter and a half wave: the device starts after ~1 ms of host work, not ~5
+        for (int64_t c0 = 0, nc = 0; c0 < n_cells; c0 += nc, ++i) {
             const int b = i & 1;
-            const int64_t nc = std::min(chunk_cells, n_cells - c0);
+            nc = i < 3 ? chunk_cells >> (3 - i) : chunk_cells;
+            nc = std::min((nc + 127) / 128 * 128, n_cells - c0);
             const void *src = x0 + (size_t)c0 * ld * esz;
             if (host_gather) {
                 const double t_g0 = now_ms();
                 if (i >= 2) PP_CUDA(cudaEventSynchronize(copied[b]));  // H2D two chunks ago has drained pin[b]
                 const double t_g1 = now_ms();
                 if (x_dtype == PP_F64)
-                    gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], n_thr);
+                    gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], crew);
                 else
-                    gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], n_thr);
+                    gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], crew);
                 src = ctx->pin[b];
                 wait_host_ms += t_g1 - t_g0;
                 gather_host_ms += now_ms() - t_g1;
