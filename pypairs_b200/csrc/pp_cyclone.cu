@@ -1216,7 +1216,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         for (int64_t c0 = 0, nc = 0; c0 < n_cells; c0 += nc, ++i) {
             const int b = i & 1;
             nc = i < 3 ? chunk_cells >> (3 - i) : chunk_cells;
-            nc = std::min((nc + 127) / 128 * 128, n_cells - c0);
+            nc = std::min({(std::max<int64_t>(nc, 1) + 127) / 128 * 128, chunk_cells, n_cells - c0});
             const void *src = x0 + (size_t)c0 * ld * esz;
             if (host_gather) {
                 const double t_g0 = now_ms();
