@@ -174,6 +174,35 @@ def test_cyclone_epilogue_rules():
     assert list(df2.columns) == ["alpha", "beta", "max_class"]
 
 
+@pytest.mark.parametrize("keys", [["G1", "S", "G2M"], ["G2M", "G1", "S"], ["a", "b"], ["G1", "S", "G2M", "M"]])
+@pytest.mark.parametrize("arrow", [True, False])
+def test_cyclone_epilogue_random_tables(monkeypatch, keys, arrow):
+    """The vectorised epilogue (Arrow-decoded label columns, or the generic fallback) against the row-by-row
+    restatement of cyclone.py:169-181, on tables with NaN columns / rows, zero rows and exact ties."""
+    import pandas as pd
+    from pypairs_b200 import cyclone as cy
+    if not arrow:
+        monkeypatch.setattr(pd, "StringDtype", type("NoStringDtype", (), {}))  # isinstance() fails -> fallback branch
+    rng = np.random.default_rng(len(keys) * 2 + arrow)
+    n = 400
+    sc = rng.random((len(keys), n)).round(1)
+    sc[:, :20] = np.nan
+    sc[0, 20:40] = np.nan
+    sc[:, 40:60] = 0.0
+    sc[:, 60:90] = 0.4
+    if len(keys) > 2:
+        sc[[0, 2], 90:110] = np.nan
+    sn = ["s{}".format(i) for i in range(n)]
+    got = cy.scores_to_frame(sc, keys, sn)
+    exp = orc.cyclone_epilogue({k: sc[i] for i, k in enumerate(keys)}, sn)
+    assert list(got.columns) == list(exp.columns) and list(got.index) == sn
+    for col in exp.columns:
+        if col in keys:
+            assert np.array_equal(got[col].to_numpy(), exp[col].to_numpy(), equal_nan=True)
+        else:
+            assert [str(v) for v in got[col]] == [str(v) for v in exp[col]], col
+
+
 def test_default_marker_fixture(golden_dir):
     from pypairs_b200 import datasets
     d = datasets.default_cc_marker()
