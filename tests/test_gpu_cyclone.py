@@ -390,3 +390,24 @@ def test_seven_bit_kernel_boundary_and_mid_call_switch():
     got = _ffi().phase_scores(x, 200, 10, 5, pairs, um)
     for sl in (slice(0, 96), slice(9472, 9472 + 64), slice(9600, 9600 + 64), slice(9936, 10000)):
         assert np.array_equal(got[sl], orc.phase_scores(x[sl], 200, 10, 5, pairs, um), equal_nan=True)
+
+
+@pytest.mark.parametrize("n_cells", [1, 127, 129, 1184, 1185, 9472, 9473, 21000])
+def test_host_pipeline_chunk_boundaries(n_cells):
+    """Host input goes through the gather + ramped-chunk pipeline, device input through one launch: same scores
+    for cell counts around every chunk boundary (an eighth / quarter / half / full wave of 148 x 64 cells)."""
+    import torch
+    rng = np.random.default_rng(n_cells)
+    n_genes, n_used = 700, 90
+    x = rng.poisson(1.2, (n_cells, n_genes)).astype(np.float32)
+    used = np.sort(rng.choice(n_genes, n_used, replace=False))
+    pairs = rng.integers(0, n_used, (200, 2))
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    host = _ffi().cyclone(x, [used], [pairs], 120, 10, 3, want_observed=True)
+    dev = _ffi().cyclone(torch.from_numpy(x).cuda(), [used], [pairs], 120, 10, 3, want_observed=True)
+    assert np.array_equal(host[0], dev[0], equal_nan=True)
+    assert np.array_equal(host[2], dev[2]) and np.array_equal(host[3], dev[3])
+    um = np.zeros(n_genes, dtype=np.uint8)
+    um[used] = 1
+    k = min(n_cells, 40)
+    assert np.array_equal(host[0][0][-k:], orc.phase_scores(x[-k:], 120, 10, 3, pairs, um), equal_nan=True)
