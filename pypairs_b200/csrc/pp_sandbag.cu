@@ -21,6 +21,8 @@
 // if/elif decision (:192-197) at the end; survivors are compacted with warp-aggregated
 // atomics and radix-sorted into the row-major order np.where would produce.
 #include <algorithm>
+#include <thread>
+#include <vector>
 
 #include "pp_common.cuh"
 
@@ -998,11 +1000,19 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             free(hc);
             return pp_fail(ctx, PP_ECUDA, "pp_sandbag: result copy failed: %s", cudaGetErrorString(e));
         }
+        // unpack into the caller-owned arrays; fresh pages: a few threads take the page faults in parallel
         const uint64_t *packed = (const uint64_t *)ctx->pin_out;
-        for (unsigned long long i = 0; i < count; ++i) {
-            hc[i] = (int32_t)(packed[i] & 0xffffu);
-            hk[i] = packed[i] >> 16;
-        }
+        auto unpack = [=](unsigned long long a, unsigned long long b) {
+            for (unsigned long long i = a; i < b; ++i) {
+                hc[i] = (int32_t)(packed[i] & 0xffffu);
+                hk[i] = packed[i] >> 16;
+            }
+        };
+        const int n_thr = count >= (1u << 17) ? 4 : 1;
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; ++t) pool.emplace_back(unpack, count * t / n_thr, count * (t + 1) / n_thr);
+        unpack(0, count / n_thr);
+        for (auto &th : pool) th.join();
     }
     PP_CUDA(cudaEventRecord(ctx->ev[4], st));
     PP_CUDA(cudaEventSynchronize(ctx->ev[4]));
