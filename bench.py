@@ -204,7 +204,7 @@ def bench_cyclone(args, rank, local_rank, world, peaks):
                      "algorithmic_ops_per_unit": 2.0 * (CYC_ITERS + 1) * n_pairs, "units_per_launch": CYC_CELLS,
                      "note": "count data: four 7-bit ranks per 32-bit lane, ~8.8 instructions per comparison slot of "
                              "128 cells, so the algorithmic rate may exceed the one-op-per-lane peak; ncu: issue slots "
-                             "86 %, ALU pipe 74 %",
+                             "88 %, ALU pipe 76 %",
                      "traffic": ncu_traffic("score_kernel")},
         "roofline_prep": {"bound": "hbm", "kernel": "rank_kernel+tables",
                           "achieved": (CYC_CELLS * CYC_GENES * 4 + CYC_CELLS * n_union * 2) / (prep_step * 1e-3) / 1e9,
