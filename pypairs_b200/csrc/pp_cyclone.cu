@@ -456,8 +456,10 @@ __device__ __forceinline__ void row_counts(const RowAcc<NC> &r, int i, int s_all
 // MODE_GLOBAL: ranks [cell][rank_ld] u16 -> [tile][gene][lane] words (lane l = cells l and l + 32 of the 64-cell tile).
 // One CTA per (tile, 32-gene block): 64 coalesced 64-byte row reads, transposed through shared memory.
 __global__ void __launch_bounds__(256) pack_tiles_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld,
-                                                         int64_t n_cells, int n_union, uint32_t *__restrict__ out) {
+                                                         int64_t n_cells, int n_union, uint32_t *__restrict__ out,
+                                                         const int32_t *__restrict__ max_rank) {
     __shared__ uint16_t s[TILE_CELLS][33];
+    if (__ldg(max_rank) <= B8_MAX_RANK) return;  // the 7-bit kernels will run: nobody reads these tiles
     const int64_t cell0 = (int64_t)blockIdx.x * TILE_CELLS;
     const int g0 = blockIdx.y * 32, gl = threadIdx.x & 31;
     for (int c = threadIdx.x >> 5; c < TILE_CELLS; c += 8)
@@ -471,8 +473,10 @@ __global__ void __launch_bounds__(256) pack_tiles_kernel(const uint16_t *__restr
 // MODE_GLOBAL_B8: the same with four cells per word (lane l = cells l, l + 32, l + 64, l + 96 of a 128-cell tile);
 // only read when every rank is <= 127.
 __global__ void __launch_bounds__(256) pack_tiles_b8_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld,
-                                                            int64_t n_cells, int n_union, uint32_t *__restrict__ out) {
+                                                            int64_t n_cells, int n_union, uint32_t *__restrict__ out,
+                                                            const int32_t *__restrict__ max_rank) {
     __shared__ uint8_t s[128][33];
+    if (__ldg(max_rank) > B8_MAX_RANK) return;  // the two-cells-per-word kernels will run
     const int64_t cell0 = (int64_t)blockIdx.x * 128;
     const int g0 = blockIdx.y * 32, gl = threadIdx.x & 31;
     for (int c = threadIdx.x >> 5; c < 128; c += 8)
@@ -1064,9 +1068,9 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         // kernel: both are enqueued, the device-side flag written by the rank kernel lets exactly one of them run
         ctx->launches += 3;
         const unsigned gy = (unsigned)((U + 31) / 32);
-        pack_tiles_kernel<<<dim3((unsigned)((nc + 63) / 64), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U, s_tiles);
-        pack_tiles_b8_kernel<<<dim3((unsigned)((nc + 127) / 128), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U,
-                                                                                  s_tiles + tiles64 * U * 32);
+        pack_tiles_kernel<<<dim3((unsigned)((nc + 63) / 64), gy), 256, 0, st>>>(P.rank, rank_ld, nc, U, s_tiles, P.max_rank);
+        pack_tiles_b8_kernel<<<dim3((unsigned)((nc + 127) / 128), gy), 256, 0, st>>>(
+            P.rank, rank_ld, nc, U, s_tiles + tiles64 * U * 32, P.max_rank);
         if (fast) {
             score_kernel<MODE_B8><<<(unsigned)std::min<int64_t>(n_units_b8, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
             score_kernel<MODE_F16><<<(unsigned)std::min<int64_t>(n_units, ctx->n_sm), SCORE_THREADS, dyn_smem, st>>>(P);
