@@ -679,8 +679,14 @@ const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
 // fn(part, n_parts) on every member -- the calling thread is member 0 -- and returns when all parts are done.
 class HostCrew {
   public:
-    explicit HostCrew(int n) : n_(std::max(1, n)) {
-        for (int t = 1; t < n_; ++t) threads_.emplace_back([this, t] { loop(t); });
+    explicit HostCrew(int n) : n_(1) {
+        try {  // a thread that cannot be created just makes the crew smaller
+            for (int t = 1; t < std::max(1, n); ++t) {
+                threads_.emplace_back([this, t] { loop(t); });
+                n_ = t + 1;
+            }
+        } catch (const std::exception &) {
+        }
     }
     ~HostCrew() {
         {
