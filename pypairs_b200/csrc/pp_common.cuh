@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -54,6 +56,18 @@ enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, 
     do {                                                                                           \
         ctx->launches++;                                                                           \
         PP_CUDA(cudaGetLastError());                                                               \
+    } while (0)
+
+// No C++ exception may cross the C ABI: host-side allocations (std::vector, std::thread) are guarded at the entry points.
+#define PP_GUARD(ctx, call)                                                                         \
+    do {                                                                                            \
+        try {                                                                                       \
+            return (call);                                                                          \
+        } catch (const std::bad_alloc &) {                                                          \
+            return pp_fail(ctx, PP_ENOMEM, "%s: host allocation failed", __func__);                 \
+        } catch (const std::exception &e) {                                                         \
+            return pp_fail(ctx, PP_ECUDA, "%s: internal error: %s", __func__, e.what());            \
+        }                                                                                           \
     } while (0)
 
 // RAII device buffer on the ctx stream (stream-ordered allocator keeps repeated calls cheap).

@@ -783,6 +783,7 @@ PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t c
     if (n < 0 || n > 65535 || iterations < 0 || !out_table) return pp_fail(ctx, PP_EINVAL, "pp_perm_table: bad argument");
     const size_t cnt = (size_t)n * iterations;
     if (cnt == 0) return PP_OK;
+    auto body = [&]() -> int {
     if (rng_mode == PP_RNG_MT19937) {
         const std::vector<uint16_t> &t = mt_table_cached((uint32_t)seed, n, iterations);
         for (size_t i = 0; i < cnt; ++i) out_table[i] = t[i];
@@ -800,6 +801,8 @@ PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t c
     PP_CUDA(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < cnt; ++i) out_table[i] = h[i];
     return PP_OK;
+    };
+    PP_GUARD(ctx, body());
 }
 
 // Shared body of pp_cyclone (dense x, csr == NULL) and pp_cyclone_csr (csr != NULL, x / ld unused).
@@ -1336,9 +1339,9 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
                       const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits,
                       int32_t *out_obs_total) {
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
-    return cyclone_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, row_begin, n_cells, n_classes, used_idx,
-                        used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode, seed, perm_tables, out_scores,
-                        out_obs_hits, out_obs_total);
+    PP_GUARD(ctx, cyclone_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, row_begin, n_cells, n_classes,
+                               used_idx, used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode, seed,
+                               perm_tables, out_scores, out_obs_hits, out_obs_total));
 }
 
 PP_API int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, int64_t row_begin,
@@ -1347,9 +1350,9 @@ PP_API int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t 
                           int32_t min_pairs, int32_t rng_mode, uint64_t seed, const int32_t *perm_tables,
                           double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_csr: NULL argument");
-    return cyclone_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols, row_begin,
-                        n_cells, n_classes, used_idx, used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode,
-                        seed, perm_tables, out_scores, out_obs_hits, out_obs_total);
+    PP_GUARD(ctx, cyclone_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
+                               row_begin, n_cells, n_classes, used_idx, used_off, pairs, pair_off, iterations, min_iter,
+                               min_pairs, rng_mode, seed, perm_tables, out_scores, out_obs_hits, out_obs_total));
 }
 
 PP_API int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows,
@@ -1357,6 +1360,7 @@ PP_API int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_dev
                            const int64_t *pairs, int64_t n_pairs, const uint8_t *used_mask, double *out_scores) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
     if (!pairs || !used_mask) return pp_fail(ctx, PP_EINVAL, "pp_phase_scores: NULL argument");
+    auto body = [&]() -> int {
     std::vector<int32_t> used;
     for (int64_t g = 0; g < n_cols; ++g)
         if (used_mask[g]) used.push_back((int32_t)g);
@@ -1368,4 +1372,6 @@ PP_API int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_dev
     const int64_t uoff[2] = {0, (int64_t)used.size()}, poff[2] = {0, n_pairs};
     return pp_cyclone(ctx, x, x_dtype, x_is_device, n_rows, n_cols, ld, 0, n_rows, 1, used.data(), uoff, p32.data(), poff,
                       iterations, min_iter, min_pairs, PP_RNG_MT19937, 2803, nullptr, out_scores, nullptr, nullptr);
+    };
+    PP_GUARD(ctx, body());
 }

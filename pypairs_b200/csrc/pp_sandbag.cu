@@ -1035,9 +1035,9 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
                       const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
                       int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
-    return sandbag_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, cell_rows, n_cells, class_sizes,
-                        n_classes, gene_cols, n_genes, thresholds, shard, n_shards, out_keys, out_class, out_n,
-                        probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed, out_kept_genes, out_n_kept);
+    PP_GUARD(ctx, sandbag_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, cell_rows, n_cells, class_sizes,
+                               n_classes, gene_cols, n_genes, thresholds, shard, n_shards, out_keys, out_class, out_n,
+                               probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed, out_kept_genes, out_n_kept));
 }
 
 PP_API int pp_sandbag_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const int32_t *cell_rows,
@@ -1047,8 +1047,8 @@ PP_API int pp_sandbag_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t 
                           int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed,
                           int32_t **out_kept_genes, int64_t *out_n_kept) {
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag_csr: NULL argument");
-    return sandbag_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
-                        cell_rows, n_cells, class_sizes, n_classes, gene_cols, n_genes, thresholds, shard, n_shards,
-                        out_keys, out_class, out_n, probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed,
-                        out_kept_genes, out_n_kept);
+    PP_GUARD(ctx, sandbag_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
+                               cell_rows, n_cells, class_sizes, n_classes, gene_cols, n_genes, thresholds, shard,
+                               n_shards, out_keys, out_class, out_n, probe_pairs, n_probe, probe_pos, probe_neg,
+                               drop_unexpressed, out_kept_genes, out_n_kept));
 }
