@@ -299,7 +299,8 @@ def test_degenerate_cells_and_parameters():
     used[7] = 1
     pairs = rng.integers(0, int(used.sum()), (300, 2))
     pairs = pairs[pairs[:, 0] != pairs[:, 1]]
-    for iterations, min_iter, min_pairs in [(200, 50, 10), (200, 250, 10), (1, 1, 1), (64, 1, 400), (100, 100, 0)]:
+    for iterations, min_iter, min_pairs in [(200, 50, 10), (200, 250, 10), (1, 1, 1), (64, 1, 400), (100, 100, 0),
+                                            (0, 0, 1), (0, 1, 1), (3, 0, 1)]:
         _score_vs_oracle(x, pairs, used, iterations, min_iter, min_pairs)
     u1 = np.zeros(g, dtype=np.uint8)
     u1[[5, 9]] = 1
