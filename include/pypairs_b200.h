@@ -23,7 +23,14 @@
  *     ctx's device (x_is_device != 0); the caller owns every input;
  *   - variable-length outputs are malloc'ed by the library and released with
  *     pp_free(); fixed-size outputs are caller-allocated host buffers;
- *   - a pp_ctx is not thread-safe; calls block until results are on the host.
+ *   - a pp_ctx is not thread-safe; calls block until results are on the host;
+ *   - STREAM CONTRACT for device-resident inputs (x_is_device / pp_csr.is_device): the
+ *     library reads them on its own non-blocking streams, which do not synchronise with
+ *     the caller's streams (not even the legacy default stream).  Everything that
+ *     produces the buffers must have COMPLETED before the call (cudaStreamSynchronize /
+ *     cudaEventSynchronize on the producing stream); the Python binding does this for
+ *     torch tensors (pypairs_b200/_ffi.py:_order_after_torch).  Device buffers must live
+ *     on the ctx's device.  When a call returns, the library no longer touches them.
  */
 #ifndef PYPAIRS_B200_H
 #define PYPAIRS_B200_H

@@ -125,8 +125,26 @@ def _ptr(a):
     return None if a is None else ctypes.c_void_p(a.ctypes.data)
 
 
+def _order_after_torch(t):
+    """Stream contract of the C ABI (include/pypairs_b200.h): the library reads device inputs on its own
+    non-blocking streams, so everything torch has enqueued on the tensor's device -- the conversions made
+    here and whatever the caller launched to produce the tensor -- must have completed before the call."""
+    import torch
+    torch.cuda.current_stream(t.device).synchronize()
+
+
+def _pick_device(device, input_device):
+    """Context device of a call: the device the input lives on (an explicit `device` must agree with it)."""
+    if input_device is None:
+        return device
+    if device is not None and int(device) != int(input_device):
+        raise ValueError("device={} but the input tensor lives on cuda:{}".format(device, input_device))
+    return int(input_device)
+
+
 def matrix_arg(x):
-    """(keepalive, pointer, dtype code, is_device, n_rows, n_cols, ld) for an ndarray or a CUDA torch tensor.
+    """(keepalive, pointer, dtype code, is_device, n_rows, n_cols, ld, device index or None) for an ndarray or
+    a CUDA torch tensor.
 
     float32 stays float32 (widening to the reference's float64 is exact and order preserving);
     every other dtype is converted to float64 exactly as `data.astype(float)` does
@@ -144,7 +162,8 @@ def matrix_arg(x):
             if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
                 x = x.contiguous()
             code = PP_F32 if x.dtype == torch.float32 else PP_F64
-            return x, ctypes.c_void_p(x.data_ptr()), code, 1, x.shape[0], x.shape[1], x.stride(0)
+            _order_after_torch(x)
+            return x, ctypes.c_void_p(x.data_ptr()), code, 1, x.shape[0], x.shape[1], x.stride(0), x.device.index
     x = np.asarray(x)
     if x.ndim != 2:
         raise ValueError("expression matrix must be 2-D")
@@ -155,7 +174,7 @@ def matrix_arg(x):
         x = np.ascontiguousarray(x)
     ld = x.strides[0] // item if x.shape[0] > 1 else x.shape[1]
     code = PP_F32 if x.dtype == np.float32 else PP_F64
-    return x, ctypes.c_void_p(x.ctypes.data), code, 0, x.shape[0], x.shape[1], max(ld, x.shape[1])
+    return x, ctypes.c_void_p(x.ctypes.data), code, 0, x.shape[0], x.shape[1], max(ld, x.shape[1]), None
 
 
 def is_sparse(x):
@@ -171,14 +190,34 @@ def is_sparse(x):
 
 
 def csr_arg(x):
-    """(keepalive, Csr struct, n_rows, n_cols) for a scipy sparse matrix or a torch sparse-CSR tensor.
+    """(keepalive, Csr struct, n_rows, n_cols, device index or None) for a scipy sparse matrix or a torch
+    sparse-CSR tensor.
 
     float32 values stay float32, anything else becomes float64 (as `data.astype(float)` in the reference);
-    duplicate entries are summed first (what `.toarray()` would do), explicit zeros are kept.
+    duplicate entries are summed first (what `.toarray()` would do; a torch CSR tensor is rebuilt through COO
+    coalescing when a row holds a repeated column), explicit zeros are kept.  Device-resident arrays are
+    bounds-checked by the library (csr_validate_kernel).
     """
     if type(x).__module__.startswith("torch"):
         import torch
-        vals, crow, col = x.values(), x.crow_indices(), x.col_indices().to(torch.int32)
+        col64, crow0 = x.col_indices(), x.crow_indices()
+        if col64.numel() > 1:
+            # repeated (row, column) entries: adjacent after sorting; rows that are already sorted (the usual case)
+            # are checked with two element-wise passes, anything else through a sort of (row, column) keys
+            inner = torch.ones(col64.numel() - 1, dtype=torch.bool, device=col64.device)
+            starts = crow0[1:-1]
+            starts = starts[(starts > 0) & (starts < col64.numel())]
+            inner[starts - 1] = False  # pairs (k-1, k) that straddle a row boundary
+            dup = bool(((col64[1:] == col64[:-1]) & inner).any())
+            if not dup and bool(((col64[1:] < col64[:-1]) & inner).any()):
+                row_of = torch.repeat_interleave(torch.arange(x.shape[0], device=col64.device), crow0[1:] - crow0[:-1])
+                skey = torch.sort(row_of * x.shape[1] + col64).values
+                dup = bool((skey[1:] == skey[:-1]).any())
+            if dup:  # (to_sparse_coo() would mark the result coalesced without looking)
+                row_of = torch.repeat_interleave(torch.arange(x.shape[0], device=col64.device), crow0[1:] - crow0[:-1])
+                x = torch.sparse_coo_tensor(torch.stack([row_of, col64]), x.values(), x.shape).coalesce().to_sparse_csr()
+                col64 = x.col_indices()
+        vals, crow, col = x.values(), x.crow_indices(), col64.to(torch.int32)
         if vals.dtype not in (torch.float32, torch.float64):
             vals = vals.to(torch.float64)
         vals, crow, col = vals.contiguous(), crow.contiguous(), col.contiguous()
@@ -191,7 +230,9 @@ def csr_arg(x):
             ptr = lambda a: a.data_ptr()  # noqa: E731
             is64, f32 = crow.dtype == torch.int64, vals.dtype == torch.float32
         st = Csr(ptr(crow), 1 if is64 else 0, ptr(col), ptr(vals), PP_F32 if f32 else PP_F64, 1 if on_dev else 0)
-        return (vals, crow, col), st, x.shape[0], x.shape[1]
+        if on_dev:
+            _order_after_torch(vals)
+        return (vals, crow, col), st, x.shape[0], x.shape[1], (vals.device.index if on_dev else None)
     m = x.tocsr()
     if not m.has_canonical_format:
         m = m.copy()
@@ -204,7 +245,7 @@ def csr_arg(x):
         indptr = indptr.astype(np.int64)
     st = Csr(indptr.ctypes.data, 1 if indptr.dtype == np.int64 else 0, indices.ctypes.data, data.ctypes.data,
              PP_F32 if data.dtype == np.float32 else PP_F64, 0)
-    return (data, indices, indptr), st, m.shape[0], m.shape[1]
+    return (data, indices, indptr), st, m.shape[0], m.shape[1], None
 
 
 def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, device=None,
@@ -213,12 +254,13 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
 
     drop_unexpressed=True: `gene_cols` are candidates, genes that are zero in every row of x are dropped on
     the device and the kept columns are returned as the last element (keys index the kept list)."""
-    lib, h = load(), ctx(device)
+    lib = load()
     sparse = is_sparse(x)
     if sparse:
-        keep, csr, n_rows, n_cols = csr_arg(x)
+        keep, csr, n_rows, n_cols, xdev = csr_arg(x)
     else:
-        keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+        keep, px, code, is_dev, n_rows, n_cols, ld, xdev = matrix_arg(x)
+    h = ctx(_pick_device(device, xdev))
     cell_rows = np.ascontiguousarray(cell_rows, dtype=np.int32)
     class_sizes = np.ascontiguousarray(class_sizes, dtype=np.int64)
     gene_cols = np.ascontiguousarray(gene_cols, dtype=np.int32)
@@ -270,12 +312,13 @@ _RNG = {"mt19937": PP_RNG_MT19937, "philox": PP_RNG_PHILOX, "table": PP_RNG_TABL
 def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,
             perm_tables=None, row_begin=0, n_cells=None, want_observed=False, device=None):
     """-> (scores float64[C, n_cells], timings[, obs_hits, obs_total])"""
-    lib, h = load(), ctx(device)
+    lib = load()
     sparse = is_sparse(x)
     if sparse:
-        keep, csr, n_rows, n_cols = csr_arg(x)
+        keep, csr, n_rows, n_cols, xdev = csr_arg(x)
     else:
-        keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+        keep, px, code, is_dev, n_rows, n_cols, ld, xdev = matrix_arg(x)
+    h = ctx(_pick_device(device, xdev))
     if n_cells is None:
         n_cells = n_rows - row_begin
     nc = len(used_idx_list)
@@ -313,8 +356,9 @@ def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="
 def phase_scores(matrix, iterations, min_iter, min_pairs, pairs, used, device=None):
     """Reference-kernel-shaped call: get_phase_scores(matrix, iterations, min_iter, min_pairs, pairs, used)
     (pypairs/tools/cyclone.py:253-257)."""
-    lib, h = load(), ctx(device)
-    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(matrix)
+    lib = load()
+    keep, px, code, is_dev, n_rows, n_cols, ld, xdev = matrix_arg(matrix)
+    h = ctx(_pick_device(device, xdev))
     pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
     used = np.ascontiguousarray(used, dtype=np.uint8)
     if len(used) != n_cols:
@@ -334,8 +378,9 @@ def perm_table(rng, seed, class_index, n, iterations, device=None):
 
 
 def dense_rank(x, cell_rows, gene_cols, device=None):
-    lib, h = load(), ctx(device)
-    keep, px, code, is_dev, n_rows, n_cols, ld = matrix_arg(x)
+    lib = load()
+    keep, px, code, is_dev, n_rows, n_cols, ld, xdev = matrix_arg(x)
+    h = ctx(_pick_device(device, xdev))
     cell_rows = np.ascontiguousarray(cell_rows, dtype=np.int32)
     gene_cols = np.ascontiguousarray(gene_cols, dtype=np.int32)
     out = np.empty((len(cell_rows), len(gene_cols)), dtype=np.uint16)

@@ -28,6 +28,7 @@
 #include <condition_variable>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cuda_fp16.h>
@@ -658,20 +659,45 @@ struct PermKey {
         return iters < o.iters;
     }
 };
-// MT19937 tables depend on (seed, n, iters) only and cost ~10 ms of serial host time each:
-// keep the few a process ever needs.
-std::map<PermKey, std::vector<uint16_t>> g_perm_cache;
+// MT19937 tables depend on (seed, n, iters) only and cost ~10 ms of serial host time each: keep the most recently
+// used ones, at most PERM_CACHE_BYTES in total (a long-lived process with varying marker sets must not grow for ever).
+// Callers hold a shared_ptr, so an entry evicted by another context's call stays alive while it is in use.
+typedef std::shared_ptr<const std::vector<uint16_t>> PermTable;
+constexpr size_t PERM_CACHE_BYTES = (size_t)256 << 20;
+struct PermEntry {
+    PermTable table;
+    uint64_t last_use;
+};
+std::map<PermKey, PermEntry> g_perm_cache;
+size_t g_perm_bytes = 0;
+uint64_t g_perm_clock = 0;
 std::mutex g_perm_mutex;  // contexts are single-threaded, but two contexts may run in two threads
 
-const std::vector<uint16_t> &mt_table_cached(uint32_t seed, int n, int iters) {
+PermTable mt_table_cached(uint32_t seed, int n, int iters) {
+    const PermKey key{PP_RNG_MT19937, seed, 0, n, iters};
+    {
+        std::lock_guard<std::mutex> lock(g_perm_mutex);
+        auto it = g_perm_cache.find(key);
+        if (it != g_perm_cache.end()) {
+            it->second.last_use = ++g_perm_clock;
+            return it->second.table;
+        }
+    }
+    auto v = std::make_shared<std::vector<uint16_t>>((size_t)n * iters);
+    mt_perm_table(seed, n, iters, v->data());
+    const size_t bytes = v->size() * sizeof(uint16_t);
     std::lock_guard<std::mutex> lock(g_perm_mutex);
-    PermKey key{PP_RNG_MT19937, seed, 0, n, iters};
-    auto it = g_perm_cache.find(key);
-    if (it != g_perm_cache.end()) return it->second;
-    // entries are never evicted while in use: a std::map node is stable and the table is tiny (n * iters * 2 B)
-    std::vector<uint16_t> &v = g_perm_cache[key];
-    v.resize((size_t)n * iters);
-    mt_perm_table(seed, n, iters, v.data());
+    while (!g_perm_cache.empty() && g_perm_bytes + bytes > PERM_CACHE_BYTES) {  // evict the least recently used
+        auto lru = g_perm_cache.begin();
+        for (auto it = g_perm_cache.begin(); it != g_perm_cache.end(); ++it)
+            if (it->second.last_use < lru->second.last_use) lru = it;
+        g_perm_bytes -= lru->second.table->size() * sizeof(uint16_t);
+        g_perm_cache.erase(lru);
+    }
+    if (bytes <= PERM_CACHE_BYTES && g_perm_cache.find(key) == g_perm_cache.end()) {
+        g_perm_cache[key] = PermEntry{v, ++g_perm_clock};
+        g_perm_bytes += bytes;
+    }
     return v;
 }
 
@@ -785,8 +811,8 @@ PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t c
     if (cnt == 0) return PP_OK;
     auto body = [&]() -> int {
     if (rng_mode == PP_RNG_MT19937) {
-        const std::vector<uint16_t> &t = mt_table_cached((uint32_t)seed, n, iterations);
-        for (size_t i = 0; i < cnt; ++i) out_table[i] = t[i];
+        const PermTable t = mt_table_cached((uint32_t)seed, n, iterations);
+        for (size_t i = 0; i < cnt; ++i) out_table[i] = (*t)[i];
         return PP_OK;
     }
     if (rng_mode != PP_RNG_PHILOX) return pp_fail(ctx, PP_EINVAL, "pp_perm_table: rng_mode must be MT19937 or PHILOX");
@@ -909,6 +935,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     std::vector<DevBuf> d_T(n_classes), d_perm(n_classes), d_src(n_classes), d_mask(n_classes), d_map(n_classes);
     std::vector<ClassDesc> cds(n_classes);
     const int32_t *ext = perm_tables;
+    std::vector<PermTable> held_tables;
     const bool trace = getenv("PP_TRACE") != nullptr;  // host-side phase times on stderr
     auto now_ms = [] {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -929,8 +956,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 PP_CHECK_LAUNCH();
             }
         } else if (rng_mode == PP_RNG_MT19937) {
-            const std::vector<uint16_t> &t = mt_table_cached((uint32_t)seed, nu, iterations);
-            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, t.data(), pcnt * 2, cudaMemcpyHostToDevice, ts));
+            held_tables.push_back(mt_table_cached((uint32_t)seed, nu, iterations));  // alive until the copy is done
+            if (pcnt) PP_CUDA(cudaMemcpyAsync(d_perm[c].p, held_tables.back()->data(), pcnt * 2, cudaMemcpyHostToDevice, ts));
         } else {
             std::vector<uint16_t> t(pcnt);
             for (size_t i = 0; i < pcnt; ++i) {

@@ -441,6 +441,24 @@ __global__ void csr_densify_kernel(const int64_t *__restrict__ indptr, const int
     }
 }
 
+// device-resident CSR: bit 0 of *flag = indptr decreases somewhere, bit 1 = a column index is out of range
+__global__ void csr_validate_kernel(const void *__restrict__ indptr, int is64, int64_t n_rows,
+                                    const int32_t *__restrict__ indices, int64_t p0, int64_t nnz, int64_t n_cols,
+                                    int32_t *__restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const int64_t a = is64 ? ((const int64_t *)indptr)[r] : (int64_t)((const int32_t *)indptr)[r];
+        const int64_t b = is64 ? ((const int64_t *)indptr)[r + 1] : (int64_t)((const int32_t *)indptr)[r + 1];
+        if (b < a) bad |= 1;
+    }
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+        const int32_t c = indices[p0 + k];
+        if (c < 0 || (int64_t)c >= n_cols) bad |= 2;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 __global__ void rebase_indptr_kernel(const void *__restrict__ src, int is64, int64_t r0, int64_t n, int64_t base,
                                      int64_t *__restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,6 +482,36 @@ int pp_csr_validate(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols
         const int32_t *idx = x->indices + ip(0);
         for (int64_t k = 0; k < nnz; ++k)
             if (idx[k] < 0 || idx[k] >= n_cols) return pp_fail(ctx, PP_EINVAL, "%s: CSR column index out of range", who);
+    } else {
+        // the same checks on the device: a malformed tensor must not turn into out-of-bounds accesses of
+        // csr_col_nonzero_kernel / csr_densify_kernel
+        PP_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        const size_t isz = x->indptr_is_64 ? 8 : 4;
+        int64_t e64[2] = {0, 0};
+        int32_t e32[2] = {0, 0};
+        for (int j = 0; j < 2; ++j) {
+            const int64_t row = j == 0 ? 0 : n_rows;
+            void *dst = x->indptr_is_64 ? (void *)&e64[j] : (void *)&e32[j];
+            PP_CUDA(cudaMemcpyAsync(dst, (const uint8_t *)x->indptr + isz * row, isz, cudaMemcpyDeviceToHost, st));
+        }
+        PP_CUDA(cudaStreamSynchronize(st));
+        if (!x->indptr_is_64) { e64[0] = e32[0]; e64[1] = e32[1]; }
+        const int64_t nnz = e64[1] - e64[0];
+        if (e64[0] < 0 || nnz < 0) return pp_fail(ctx, PP_EINVAL, "%s: CSR indptr decreases", who);
+        if (nnz > 0 && (!x->indices || !x->data)) return pp_fail(ctx, PP_EINVAL, "%s: NULL CSR indices / data", who);
+        DevBuf d_flag;
+        PP_CUDA(d_flag.alloc(sizeof(int32_t), st));
+        PP_CUDA(cudaMemsetAsync(d_flag.p, 0, sizeof(int32_t), st));
+        const unsigned grid = (unsigned)std::min<int64_t>((std::max(n_rows, nnz) + 255) / 256, (int64_t)ctx->n_sm * 16);
+        csr_validate_kernel<<<std::max(grid, 1u), 256, 0, st>>>(x->indptr, x->indptr_is_64, n_rows, x->indices, e64[0], nnz,
+                                                                n_cols, d_flag.as<int32_t>());
+        PP_CHECK_LAUNCH();
+        int32_t flag = 0;
+        PP_CUDA(cudaMemcpyAsync(&flag, d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+        if (flag & 1) return pp_fail(ctx, PP_EINVAL, "%s: CSR indptr decreases", who);
+        if (flag & 2) return pp_fail(ctx, PP_EINVAL, "%s: CSR column index out of range", who);
     }
     return PP_OK;
 }

@@ -102,6 +102,22 @@ def scores_to_frame(scores, keys, sample_names):
     return df
 
 
+def _quantile_transform(raw, local_shard):
+    """sklearn QuantileTransformer().fit_transform on the host, as cyclone.py:138-139 (a pass-through, not part of
+    the CUDA path).  The transform is fitted on ALL cells, so it needs the whole matrix on the host of every rank:
+    it is refused for `local_shard` (a shard-wise fit would make the scores depend on the sharding) and for CUDA
+    tensors.  Matrices of more than 10 000 cells are sub-sampled by sklearn; the sub-sample is seeded with
+    `settings.seed` so that all ranks (and repeated calls) fit the same quantiles -- the reference's is unseeded."""
+    if local_shard:
+        raise ValueError("quantile_transform=True needs the whole matrix: not available with local_shard=True")
+    if utils.is_cuda_tensor(raw):
+        raise ValueError("quantile_transform=True runs sklearn on the host: pass a host matrix, not a CUDA tensor")
+    from sklearn.preprocessing import QuantileTransformer
+    dense = raw.toarray() if utils.issparse(raw) else raw
+    return QuantileTransformer(random_state=int(settings.seed) % (2 ** 32)).fit_transform(
+        np.asarray(dense, dtype=np.float64))
+
+
 def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterations=1000, min_iter=100,
             min_pairs=50, quantile_transform=False, *, local_shard=False):
     """Score each sample for each category of marker pairs.
@@ -137,9 +153,7 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
         raise ValueError("no genes present for marker pairs for category {}".format(empty[0]))
     logg.hint("received {} marker pairs".format(total))
     if quantile_transform:
-        from sklearn.preprocessing import QuantileTransformer
-        dense = raw.toarray() if utils.issparse(raw) else raw
-        raw = QuantileTransformer().fit_transform(np.asarray(dense, dtype=np.float64))
+        raw = _quantile_transform(raw, local_shard)
 
     keys = list(pairs.keys())
     rank, ws = _dist.world()

@@ -412,3 +412,89 @@ def test_host_pipeline_chunk_boundaries(n_cells):
     um[used] = 1
     k = min(n_cells, 40)
     assert np.array_equal(host[0][0][-k:], orc.phase_scores(x[-k:], 120, 10, 3, pairs, um), equal_nan=True)
+
+
+def test_quantile_transform_pass_through():
+    """quantile_transform=True (pypairs/tools/cyclone.py:138-139): sklearn on the host, then the same scoring; the
+    oracle scores the sklearn-transformed matrix.  <= 10 000 cells: sklearn does not sub-sample, so the fit is the
+    reference's own (unseeded) one."""
+    from sklearn.preprocessing import QuantileTransformer
+    from pypairs_b200 import pairs
+    rng = np.random.default_rng(46)
+    markers, names, x = default_setup(rng, 60, 1600, "poisson", np.float64)
+    sn = ["c{}".format(i) for i in range(60)]
+    df = pairs.cyclone(x, markers, names, sn, iterations=120, min_iter=20, min_pairs=5, quantile_transform=True)
+    xt = QuantileTransformer().fit_transform(x)
+    assert not np.array_equal(xt, x)
+    pr, us = orc.filter_marker_pairs(markers, names)
+    for k in ["G1", "S", "G2M"]:
+        assert np.array_equal(df[k].values, orc.phase_scores(xt, 120, 20, 5, pr[k], us[k]), equal_nan=True), k
+    import scipy.sparse as sp
+    df2 = pairs.cyclone(sp.csr_matrix(x), markers, names, sn, iterations=120, min_iter=20, min_pairs=5,
+                        quantile_transform=True)
+    assert df2.equals(df)
+    import torch
+    with pytest.raises(ValueError):
+        pairs.cyclone(torch.from_numpy(x).cuda(), markers, names, sn, quantile_transform=True)
+
+
+def test_device_inputs_are_ordered_after_torch_work():
+    """The library runs on its own non-blocking streams: a CUDA tensor that torch is still producing (large async
+    conversion / arithmetic enqueued right before the call) must be complete when the kernels read it."""
+    import torch
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(47)
+    markers, names, x = default_setup(rng, 4000, 6000, "poisson", np.float32)
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    want, _ = _ffi().cyclone(x, u, p, 40, 10, 5)
+    xi = torch.from_numpy(x.astype(np.int32)).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        big = torch.empty((1 << 28,), dtype=torch.float32, device="cuda")
+        big.normal_()                       # keeps torch's stream busy ...
+        big.mul_(2.0).add_(1.0)
+        xd = (xi.to(torch.float64) * 3.0 + 1.0).to(torch.float32)  # ... ahead of a monotone transform of the counts
+        got, _ = _ffi().cyclone(xd, u, p, 40, 10, 5)               # and int32 input is converted by matrix_arg itself
+        assert np.array_equal(got, want, equal_nan=True)
+        got, _ = _ffi().cyclone(xi, u, p, 40, 10, 5)
+        assert np.array_equal(got, want, equal_nan=True)
+    # sandbag through a torch sparse-CSR tensor: col_indices() are int64 and converted right before the call
+    import scipy.sparse as sp
+    n, g, c = 600, 900, 3
+    lab = rng.integers(0, c, n)
+    xs = rng.poisson(1.0, (n, g)).astype(np.float32)
+    xs[:, 0] += 1
+    order = np.argsort(lab, kind="stable")
+    sizes = np.bincount(lab, minlength=c)
+    thr = orc.calc_thresholds(sizes, 0.6)
+    k0, c0, _ = _ffi().sandbag(xs, order, sizes, np.arange(g), thr)
+    m = sp.csr_matrix(xs)
+    for _ in range(3):
+        big = torch.empty((1 << 28,), dtype=torch.float32, device="cuda").normal_()
+        t = torch.sparse_csr_tensor(torch.from_numpy(m.indptr.astype(np.int64)).cuda(),
+                                    torch.from_numpy(m.indices.astype(np.int64)).cuda(),
+                                    torch.from_numpy(m.data).cuda(), size=m.shape)
+        k1, c1, _ = _ffi().sandbag(t, order, sizes, np.arange(g), thr)
+        assert np.array_equal(k0, k1) and np.array_equal(c0, c1)
+        del big
+
+
+def test_malformed_device_csr_is_rejected():
+    import torch
+    f = _ffi()
+    n, g = 8, 12
+    crow = torch.tensor([0, 2, 4, 4, 4, 4, 4, 4, 4], dtype=torch.int64)
+    vals = torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float32)
+    bad_col = torch.tensor([1, 40, 2, 3], dtype=torch.int64)
+    t = torch.sparse_csr_tensor(crow.cuda(), bad_col.cuda(), vals.cuda(), size=(n, g))
+    with pytest.raises(f.PyPairsB200Error) as e:
+        f.sandbag(t, np.arange(n), np.array([4, 4]), np.arange(g), np.array([3, 3]))
+    assert "column index out of range" in str(e.value)
+    bad_crow = torch.tensor([0, 3, 2, 4, 4, 4, 4, 4, 4], dtype=torch.int64)
+    t = torch.sparse_csr_tensor(bad_crow.cuda(), torch.tensor([1, 5, 2, 3]).cuda(), vals.cuda(), size=(n, g))
+    with pytest.raises(f.PyPairsB200Error) as e:
+        f.sandbag(t, np.arange(n), np.array([4, 4]), np.arange(g), np.array([3, 3]))
+    assert "indptr decreases" in str(e.value)

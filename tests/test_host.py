@@ -108,12 +108,28 @@ def test_sparse_input_stays_sparse(monkeypatch, sandbag_api):
         raw, _, _ = utils.parse_data(m, gn, sn)
         assert sp.issparse(raw) and raw.format == "csr"
         assert list(pairs.sandbag(m, ann, gn, sn, fraction=0.65).items()) == list(exp.items())
-    keep, st, n_rows, n_cols = _ffi.csr_arg(sp.csc_matrix(x.astype(np.int32)))
+    keep, st, n_rows, n_cols, dev = _ffi.csr_arg(sp.csc_matrix(x.astype(np.int32)))
+    assert dev is None
     assert (n_rows, n_cols) == x.shape and st.data_dtype == _ffi.PP_F64 and st.is_device == 0
     dup = sp.csr_matrix((np.array([1.0, 2.0, 5.0]), np.array([3, 3, 1]), np.array([0, 3] + [3] * (x.shape[0] - 1))),
                         shape=x.shape)
-    keep, st, _, _ = _ffi.csr_arg(dup)  # duplicates are summed, as .toarray() would
+    keep, st, _, _, _ = _ffi.csr_arg(dup)  # duplicates are summed, as .toarray() would
     assert keep[0].tolist() == [5.0, 3.0] and keep[1].tolist() == [1, 3]
+    # torch sparse-CSR: a repeated column inside a row is coalesced (summed) too, sorted or not
+    import torch
+    for cols in ([3, 3, 1], [3, 1, 3]):
+        t = torch.sparse_csr_tensor(torch.tensor([0, 3] + [3] * (x.shape[0] - 1)), torch.tensor(cols),
+                                    torch.tensor([1.0, 2.0, 5.0]), size=x.shape)
+        keep, st, _, _, _ = _ffi.csr_arg(t)
+        got = dict(zip(keep[2].tolist(), keep[0].tolist()))
+        assert got == ({1: 5.0, 3: 3.0} if cols == [3, 3, 1] else {1: 2.0, 3: 6.0})
+    t = torch.sparse_csr_tensor(torch.tensor([0, 2, 3] + [3] * (x.shape[0] - 2)), torch.tensor([4, 2, 2]),
+                                torch.tensor([1.0, 2.0, 5.0]), size=x.shape)  # unsorted row, no duplicates: kept as is
+    keep, st, _, _, _ = _ffi.csr_arg(t)
+    assert keep[2].tolist() == [4, 2, 2] and keep[0].tolist() == [1.0, 2.0, 5.0]
+    assert _ffi._pick_device(None, None) is None and _ffi._pick_device(1, None) == 1 and _ffi._pick_device(None, 1) == 1
+    with pytest.raises(ValueError):
+        _ffi._pick_device(0, 1)  # explicit device must agree with the tensor's device
 
 
 def test_sandbag_input_errors(monkeypatch):
@@ -201,6 +217,19 @@ def test_cyclone_epilogue_random_tables(monkeypatch, keys, arrow):
             assert np.array_equal(got[col].to_numpy(), exp[col].to_numpy(), equal_nan=True)
         else:
             assert [str(v) for v in got[col]] == [str(v) for v in exp[col]], col
+
+
+def test_quantile_transform_restrictions():
+    """The sklearn pass-through is fitted on all cells: refused for rank-local shards and CUDA tensors."""
+    from pypairs_b200 import cyclone as cyc
+    x = np.random.default_rng(3).poisson(2.0, (30, 8)).astype(np.float64)
+    with pytest.raises(ValueError):
+        cyc._quantile_transform(x, True)
+    from sklearn.preprocessing import QuantileTransformer
+    import scipy.sparse as sp
+    want = QuantileTransformer().fit_transform(x)
+    assert np.array_equal(cyc._quantile_transform(x, False), want)
+    assert np.array_equal(cyc._quantile_transform(sp.csr_matrix(x), False), want)
 
 
 def test_default_marker_fixture(golden_dir):
