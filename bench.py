@@ -385,33 +385,74 @@ def run_b200(args):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+def reference_setup(seed=20262):
+    """The cyclone workload from oracle/ and tests/golden only (the reference arm must not load the product)."""
+    from oracle import oracle as orc
+    markers = orc.default_cc_marker()
+    genes = sorted({g for v in markers.values() for p in v for g in p})
+    names = genes + ["X{}".format(i) for i in range(CYC_GENES - len(genes))]
+    np.random.default_rng(seed).shuffle(names)
+    pairs, used = orc.filter_marker_pairs(markers, names)
+    return list(pairs.keys()), pairs, used
+
+
+def cpu_cyclone_runner(n_threads):
+    """(step(xs) -> [scores per class], description dict): the reference's own Numba gufunc from oracle/_ref when that
+    copy is present (kind "reference"), else the C/OpenMP restatement (kind "port"); both with `n_threads` threads."""
+    from oracle import oracle as orc, ref_numba
+    keys, pairs, used = reference_setup()
+    info = {"cores": n_threads}
+    if ref_numba.available():
+        ref_numba.configure_threads(n_threads)
+        r = ref_numba.load()
+        step = lambda xs: [ref_numba.phase_scores(xs, CYC_ITERS, CYC_MIN_ITER, CYC_MIN_PAIRS, pairs[k], used[k])  # noqa: E731
+                           for k in keys]
+        info.update(kind="reference", cores=int(r.threads), numba=r.numba.__version__,
+                    impl="pypairs.tools.cyclone.get_phase_scores (Numba gufunc, target=parallel) from oracle/_ref")
+    else:
+        orc.build()
+        step = lambda xs: [orc.phase_scores(xs, CYC_ITERS, CYC_MIN_ITER, CYC_MIN_PAIRS, pairs[k], used[k],  # noqa: E731
+                                            n_threads=n_threads) for k in keys]
+        info.update(kind="port", impl="oracle/pp_oracle.c (C + OpenMP restatement; oracle/_ref absent)")
+    port = lambda xs: [orc.phase_scores(xs, CYC_ITERS, CYC_MIN_ITER, CYC_MIN_PAIRS, pairs[k], used[k],  # noqa: E731
+                                        n_threads=n_threads) for k in keys]
+    return step, port, info
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path (oracle port, all host threads) on bounded samples of the
-    same workload: per step 512 cells of the cyclone matrix."""
+    """The reference's CPU implementation of the path on all host cores, on bounded samples of the same workload:
+    per step 512 cells of the cyclone matrix.  Loads nothing of the product (oracle/ and tests/golden only); the
+    thread count is explicit because torch.distributed.run exports OMP_NUM_THREADS=1."""
     rank, _, world = env_world()
     if rank != 0:
         return
-    from oracle import oracle as orc
-    orc.build()
-    markers, names, keys, used_idx, pair_idx, pairs_d, used_d = cyclone_setup()
+    n_threads = os.cpu_count() or 1
+    step, port, info = cpu_cyclone_runner(n_threads)
     cells = 512
     rng = np.random.default_rng(20262)
-    step = lambda xs: [orc.phase_scores(xs, CYC_ITERS, CYC_MIN_ITER, CYC_MIN_PAIRS, pairs_d[k], used_d[k]) for k in keys]  # noqa: E731
-    for _ in range(args.warmup):
-        step(rng.poisson(2.0, (16, CYC_GENES)).astype(np.float32))
+    for _ in range(max(args.warmup, 1)):  # the first call also pays Numba's lazy thread-pool start
+        step(rng.poisson(2.0, (64, CYC_GENES)).astype(np.float32))
     xs_all = [rng.poisson(2.0, (cells, CYC_GENES)).astype(np.float32) for _ in range(args.steps)]
     t0 = time.perf_counter()
     for xs in xs_all:
-        step(xs)
+        out = step(xs)
     dt = time.perf_counter() - t0
     v = cells * args.steps / dt
+    if info["kind"] == "reference":
+        from oracle import ref_numba
+        info["threading_layer"] = ref_numba.threading_layer()
+        t1 = time.perf_counter()  # the C port beside it, one step, and the two must agree bit for bit
+        chk = port(xs_all[-1])
+        info["port_value"] = cells / (time.perf_counter() - t1)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(out, chk)), "Numba reference != C port"
     sample = "{} cells per step of the 100000 x 20000 matrix, all 3 classes, 1000 iterations".format(cells)
+    base = dict(info, value=v, unit=UNIT, sample=sample)
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "value": v, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: cyclone default_cc_marker, synthetic 100000 cells x 20000 genes, "
                                    "1000 iterations (bounded sample: {})".format(sample)},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": orc.max_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))

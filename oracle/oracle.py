@@ -207,3 +207,12 @@ def cyclone_epilogue(scores, sample_names):
                 pred.append(np.nan if np.all(np.isnan(row)) else ["G1", "G2M"][int(np.nanargmax(row))])
         df["cc_prediction"] = pred
     return df
+
+
+def default_cc_marker():
+    """The reference's bundled leng15 marker set (pypairs/datasets/__init__.py:100-120), read from the compact
+    fixture tests/golden/default_cc_marker.json that make_golden.py derived from the reference's JSON."""
+    import json
+    d = json.load(open(os.path.join(os.path.dirname(_HERE), "tests", "golden", "default_cc_marker.json")))
+    genes = d["genes"]
+    return {k: [[genes[a], genes[b]] for a, b in zip(*v)] for k, v in d["classes"].items()}

@@ -100,3 +100,24 @@ def test_philox_known_answer():
     t = orc.perm_table_philox(2803, 1, 50, 20)
     assert all(sorted(r.tolist()) == list(range(50)) for r in t)
     assert len({tuple(r.tolist()) for r in t}) == 20
+
+
+def test_numba_reference_copy_matches_port():
+    """oracle/_ref (the reference's own Numba kernels, copied by oracle/build_ref.py where /root/reference exists) and
+    the C restatement agree bit for bit on both hot paths -- the two CPU arms bench.py reports side by side."""
+    from oracle import ref_numba
+    if not ref_numba.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    ref_numba.configure_threads(2)
+    rng = np.random.default_rng(11)
+    n, g, c = 90, 60, 3
+    lab = rng.integers(0, c, n)
+    x = rng.poisson(3.0 * np.exp(rng.normal(0, 1, g))[None, :] * np.where(lab[:, None] == (np.arange(g) % c)[None, :], 3, 1)
+                    ).astype(np.float64)
+    thr = orc.calc_thresholds(np.bincount(lab, minlength=c), 0.6)
+    assert np.array_equal(ref_numba.check_pairs(x, lab, thr, 2), orc.check_pairs(x, lab, thr))
+    pairs = rng.integers(0, 40, (70, 2))
+    used = np.zeros(g, dtype=bool)
+    used[rng.choice(g, 40, replace=False)] = True
+    a = ref_numba.phase_scores(x, 50, 10, 2, pairs, used)
+    assert np.array_equal(a, orc.phase_scores(x, 50, 10, 2, pairs, used), equal_nan=True)
