@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 
 /* error codes */
 #define PP_OK 0
@@ -50,6 +50,7 @@ extern "C" {
 #define PP_ENOMEM 3   /* host or device allocation failed */
 #define PP_ENAN 4     /* NaN in the expression matrix (undefined in the reference: fastmath, utils.py:185) */
 #define PP_ELIMIT 5   /* size beyond what the kernels support (message says which limit) */
+#define PP_ENCCL 6    /* NCCL could not be loaded / a collective failed / no communicator */
 
 /* element type of the expression matrix */
 #define PP_F32 0
@@ -192,6 +193,81 @@ int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols,
 int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows,
                     int64_t n_cols, int64_t ld, int32_t iterations, int32_t min_iter, int32_t min_pairs,
                     const int64_t *pairs, int64_t n_pairs, const uint8_t *used_mask, double *out_scores);
+
+/*
+ * ---- multi-GPU: one process per GPU, one communicator per pp_ctx --------------------------------
+ *
+ * The reference is single-process (Numba threads only); these entry points are what
+ * BASELINE.json's multi-GPU configurations add.  Both paths shard without a data-path exchange -- sandbag over
+ * gene-pair tiles (pypairs/tools/sandbag.py:168-169, the g1 x g2 loop nest), cyclone over cells
+ * (pypairs/tools/cyclone.py:223-224, the gufunc's loop over rows) -- and the library itself issues, on the ctx
+ * stream, the few NCCL collectives around them (see pp_sandbag_dist / pp_cyclone_dist).  NCCL is resolved at run
+ * time with dlopen (pp_nccl_load; default: the libnccl.so.2 already mapped into the process).
+ *
+ * Bootstrap: rank 0 calls pp_comm_unique_id(), the host sends the PP_COMM_ID_BYTES bytes to every rank over any
+ * channel it has, every rank calls pp_comm_init() (collective, blocking).  All ranks of a communicator must then
+ * make the same sequence of pp_*_dist calls with consistent arguments; a rank that fails validation before the
+ * first collective of a call leaves the others waiting, exactly as with NCCL itself.
+ */
+#define PP_COMM_ID_BYTES 128
+int pp_nccl_load(const char *path /* NULL or "": "libnccl.so.2" from the process / loader path */);
+int pp_nccl_version(void); /* NCCL_VERSION_CODE of the loaded library, 0 if none */
+int pp_comm_unique_id(uint8_t *out_id /* [PP_COMM_ID_BYTES] */);
+int pp_comm_init(pp_ctx *ctx, const uint8_t *id /* [PP_COMM_ID_BYTES] */, int32_t rank, int32_t world);
+int pp_comm_destroy(pp_ctx *ctx);
+int pp_comm_info(pp_ctx *ctx, int32_t *rank, int32_t *world); /* world = 0: no communicator */
+
+/*
+ * pp_sandbag_dist / pp_sandbag_csr_dist -- pp_sandbag over all ranks of the ctx's communicator.
+ *
+ * Every rank passes the SAME arguments (the whole matrix -- host, device or CSR -- and the whole cell / gene /
+ * class description, as for pp_sandbag); the work is split inside:
+ *   - the rows of x are cut into `world` contiguous blocks holding equal numbers of kept cells; a rank copies
+ *     (host input), scans for unexpressed genes and ranks ONLY its own block;
+ *   - all-reduce(max) of the expressed-gene flags and of (max rank, NaN flag, per-gene rank width);
+ *   - every rank bit-slices its cells into its region of the plane buffer, one all-gather completes it;
+ *   - gene-pair tiles t with t % world == rank are evaluated (as pp_sandbag with shard = rank);
+ *   - the compacted keys of all ranks are all-gathered and sorted on the device.
+ * gather_to < 0: every rank receives the complete, sorted marker list; gather_to = r: only rank r does (the others
+ * get *out_n = 0 and skip the device -> host copy).  out_kept_genes / probes are filled on every rank.
+ * The result is identical to pp_sandbag on one GPU.
+ */
+int pp_sandbag_dist(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                    int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
+                    int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
+                    int32_t gather_to, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
+                    const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
+                    int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept);
+int pp_sandbag_csr_dist(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const int32_t *cell_rows,
+                        int64_t n_cells, const int64_t *class_sizes, int32_t n_classes, const int32_t *gene_cols,
+                        int64_t n_genes, const int64_t *thresholds, int32_t gather_to, uint64_t **out_keys,
+                        int32_t **out_class, int64_t *out_n, const int64_t *probe_pairs, int64_t n_probe,
+                        int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed,
+                        int32_t **out_kept_genes, int64_t *out_n_kept);
+
+/*
+ * pp_cyclone_dist / pp_cyclone_csr_dist -- pp_cyclone on this rank's cell shard, then one all-gather of the score
+ * columns (pypairs/tools/cyclone.py:151-170: the per-class score vectors that become the DataFrame columns).
+ *
+ * x, row_begin, n_cells describe THIS rank's shard exactly as in pp_cyclone (x may be the whole matrix with a row
+ * range, or just the rank's own rows with row_begin = 0); marker tables, iterations, rng are the same on all ranks.
+ * shard_cells[world] = n_cells of every rank (rank order = cell order of the result).
+ * gather_to < 0: every rank receives out_* of shape [n_classes, sum(shard_cells)]; gather_to = r: only rank r does
+ * (the out_* pointers of the other ranks may be NULL).  want_observed != 0 (the same on all ranks) also gathers the
+ * observed counters.  A NaN on any rank fails the call on every rank (PP_ENAN).
+ */
+int pp_cyclone_dist(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                    int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes, const int32_t *used_idx,
+                    const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off, int32_t iterations,
+                    int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
+                    const int32_t *perm_tables, const int64_t *shard_cells, int32_t gather_to,
+                    int32_t want_observed, double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total);
+int pp_cyclone_csr_dist(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, int64_t row_begin,
+                        int64_t n_cells, int32_t n_classes, const int32_t *used_idx, const int64_t *used_off,
+                        const int32_t *pairs, const int64_t *pair_off, int32_t iterations, int32_t min_iter,
+                        int32_t min_pairs, int32_t rng_mode, uint64_t seed, const int32_t *perm_tables,
+                        const int64_t *shard_cells, int32_t gather_to, int32_t want_observed, double *out_scores,
+                        int32_t *out_obs_hits, int32_t *out_obs_total);
 
 /*
  * pp_perm_table -- the permutation stream on its own (validation / export):

@@ -1,11 +1,15 @@
-"""One process per GPU: shard bookkeeping and the single collective each path needs.
+"""One process per GPU: shard bookkeeping and the bootstrap of the library's communicator.
 
-sandbag shards gene-pair tiles (tile index mod world size, inside the library), cyclone shards
-contiguous cell ranges.  Counts/thresholds/decisions are per pair and scores are per cell, so no
-data-path collective exists; the only exchange is the final all-gather of the compacted marker
-lists / score columns (NCCL when the process group is NCCL, gloo in the CPU tests).
+sandbag shards gene-pair tiles (and the rank / bit-slice prep over cells), cyclone shards contiguous cell
+ranges.  Counts / thresholds / decisions are per pair and scores are per cell, so no data-path collective
+exists; what crosses GPUs (bit planes, compacted marker keys, score columns) is exchanged by the CUDA
+library itself with NCCL on its own stream (pp_sandbag_dist / pp_cyclone_dist, csrc/pp_comm.cu).
+torch.distributed is used for exactly two host-side things: carrying the 128-byte NCCL unique id from rank 0
+to the other ranks, and (local_shard only) exchanging sample names as fixed-width bytes.
 """
 import numpy as np
+
+_comm_ready = {}  # device index -> (rank, world) the library communicator was created for
 
 
 def world():
@@ -26,68 +30,85 @@ def cell_shard(n_cells, rank, world_size):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def _device():
-    import torch
+def shard_sizes(n_cells, world_size):
+    return np.array([cell_shard(n_cells, r, world_size)[1] - cell_shard(n_cells, r, world_size)[0]
+                     for r in range(world_size)], dtype=np.int64)
+
+
+def broadcast_object(obj, src=0):
+    """Small host object from `src` to every rank (unique id, seed)."""
     import torch.distributed as dist
-    if dist.get_backend() == "nccl":
-        return torch.device("cuda", torch.cuda.current_device())
-    return torch.device("cpu")
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
 
 
-def allgather_varlen(arrays):
-    """All-gather a tuple of equally long 1-D numpy arrays whose length differs per rank.
-    Returns, per input array, the concatenation over ranks in rank order."""
+def ensure_comm(device=None):
+    """Make sure this process's library context holds an NCCL communicator spanning the default process
+    group (collective on first use; one communicator per process for its lifetime).  -> (rank, world)."""
+    from . import _ffi
+    rank, ws = world()
+    if ws == 1:
+        return rank, ws
+    if device is None:
+        device = _ffi._current_device()
+    have = _comm_ready.get(device)
+    if have == (rank, ws):
+        return rank, ws
+    if have is not None:
+        _ffi.comm_destroy(device)
+    uid = _ffi.comm_unique_id() if rank == 0 else None
+    uid = broadcast_object(uid, 0)
+    _ffi.comm_init(uid, rank, ws, device)
+    _comm_ready[device] = (rank, ws)
+    return rank, ws
+
+
+def drop_comm(device=None):
+    """Destroy the library communicator (before the process group is torn down)."""
+    from . import _ffi
+    if device is None:
+        device = _ffi._current_device()
+    if _comm_ready.pop(device, None) is not None:
+        _ffi.comm_destroy(device)
+
+
+def allgather_counts(n):
+    """int from every rank -> int64[world]."""
     import torch
     import torch.distributed as dist
     rank, ws = world()
     if ws == 1:
-        return [np.asarray(a) for a in arrays]
-    dev = _device()
-    n = torch.tensor([len(arrays[0])], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(ws)]
-    dist.all_gather(counts, n)
-    counts = [int(c.item()) for c in counts]
-    mx = max(max(counts), 1)
-    out = []
-    for a in arrays:
-        a = np.ascontiguousarray(a)
-        view = a.view(np.int64) if a.dtype == np.uint64 else a  # torch has no uint64 collectives
-        t = torch.zeros(mx, dtype=torch.from_numpy(view[:0]).dtype, device=dev)
-        t[:len(view)] = torch.from_numpy(view).to(dev)
-        parts = [torch.empty_like(t) for _ in range(ws)]
-        dist.all_gather(parts, t)
-        cat = np.concatenate([p[:c].cpu().numpy() for p, c in zip(parts, counts)])
-        out.append(cat.view(np.uint64) if a.dtype == np.uint64 else cat)
-    return out
-
-
-def allgather_columns(local, n_total):
-    """local: float64[C, n_local] of this rank's contiguous cell shard -> float64[C, n_total]."""
-    import torch
-    import torch.distributed as dist
-    rank, ws = world()
-    if ws == 1:
-        return local
-    dev = _device()
-    base, extra = divmod(n_total, ws)
-    mx = base + (1 if extra else 0)
-    t = torch.zeros((local.shape[0], max(mx, 1)), dtype=torch.float64, device=dev)
-    t[:, :local.shape[1]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
-    parts = [torch.empty_like(t) for _ in range(ws)]
+        return np.array([n], dtype=np.int64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(n)], dtype=torch.int64, device=dev)
+    parts = [torch.zeros_like(t) for _ in range(ws)]
     dist.all_gather(parts, t)
-    cols = []
-    for r, p in enumerate(parts):
-        b, e = cell_shard(n_total, r, ws)
-        cols.append(p[:, :e - b].cpu().numpy())
-    return np.concatenate(cols, axis=1)
+    return np.array([int(p.item()) for p in parts], dtype=np.int64)
 
 
 def allgather_names(names):
-    """Concatenate every rank's list of sample names in rank order."""
+    """Concatenate every rank's sample names in rank order.  The names travel as one fixed-width byte matrix per
+    rank (UTF-8, padded to the longest name of any rank) through a single tensor all-gather -- no pickling of
+    Python lists; the result is a numpy str array."""
+    import torch
     import torch.distributed as dist
     rank, ws = world()
     if ws == 1:
-        return list(names)
-    parts = [None] * ws
-    dist.all_gather_object(parts, list(names))
-    return [n for p in parts for n in p]
+        return names
+    enc = np.char.encode(np.asarray(names, dtype=str), "utf-8") if len(names) else np.empty(0, dtype="S1")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    meta = torch.tensor([len(enc), enc.dtype.itemsize], dtype=torch.int64, device=dev)
+    metas = [torch.zeros_like(meta) for _ in range(ws)]
+    dist.all_gather(metas, meta)
+    counts = [int(m[0].item()) for m in metas]
+    width = max(max(int(m[1].item()) for m in metas), 1)
+    rows = max(max(counts), 1)
+    buf = np.zeros((rows, width), dtype=np.uint8)
+    if len(enc):
+        buf[:len(enc), :enc.dtype.itemsize] = np.ascontiguousarray(enc).view(np.uint8).reshape(len(enc), -1)
+    t = torch.from_numpy(buf).to(dev)
+    parts = [torch.empty_like(t) for _ in range(ws)]
+    dist.all_gather(parts, t)
+    cat = np.concatenate([p[:c].cpu().numpy() for p, c in zip(parts, counts)])
+    return np.char.decode(np.ascontiguousarray(cat).view("S{}".format(width)).ravel(), "utf-8")

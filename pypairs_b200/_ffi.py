@@ -14,10 +14,14 @@ LIB_PATH = os.path.join(_HERE, "libpypairs_b200.so")
 PP_F32, PP_F64 = 0, 1
 PP_RNG_MT19937, PP_RNG_PHILOX, PP_RNG_TABLE = 0, 1, 2
 PP_ENAN = 4
+PP_ENCCL = 6
+PP_COMM_ID_BYTES = 128
 
 SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "pp_last_error", "pp_free",
            "pp_get_timings", "pp_sandbag", "pp_sandbag_csr", "pp_cyclone", "pp_cyclone_csr", "pp_phase_scores",
-           "pp_perm_table", "pp_dense_rank", "pp_alu_peak"]
+           "pp_perm_table", "pp_dense_rank", "pp_alu_peak", "pp_nccl_load", "pp_nccl_version", "pp_comm_unique_id",
+           "pp_comm_init", "pp_comm_destroy", "pp_comm_info", "pp_sandbag_dist", "pp_sandbag_csr_dist",
+           "pp_cyclone_dist", "pp_cyclone_csr_dist"]
 
 
 class Csr(ctypes.Structure):
@@ -78,6 +82,23 @@ def load():
                                    c.POINTER(i64)]
     lib.pp_cyclone_csr.argtypes = [vp, c.POINTER(Csr), i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32, u64,
                                    vp, vp, vp, vp]
+    # multi-GPU (one process per GPU)
+    lib.pp_nccl_load.argtypes = [c.c_char_p]
+    lib.pp_nccl_version.restype = c.c_int
+    lib.pp_comm_unique_id.argtypes = [vp]
+    lib.pp_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.pp_comm_destroy.argtypes = [vp]
+    lib.pp_comm_info.argtypes = [vp, c.POINTER(i32), c.POINTER(i32)]
+    lib.pp_sandbag_dist.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i32, vp, i64, vp, i32,
+                                    c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp, i32, c.POINTER(vp),
+                                    c.POINTER(i64)]
+    lib.pp_sandbag_csr_dist.argtypes = [vp, c.POINTER(Csr), i64, i64, vp, i64, vp, i32, vp, i64, vp, i32,
+                                        c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp, i32,
+                                        c.POINTER(vp), c.POINTER(i64)]
+    lib.pp_cyclone_dist.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32,
+                                    i32, i32, u64, vp, vp, i32, i32, vp, vp, vp]
+    lib.pp_cyclone_csr_dist.argtypes = [vp, c.POINTER(Csr), i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32,
+                                        u64, vp, vp, i32, i32, vp, vp, vp]
     lib.pp_phase_scores.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp]
     lib.pp_perm_table.argtypes = [vp, i32, u64, i32, i32, i32, vp]
     lib.pp_dense_rank.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i64, vp, c.POINTER(i32)]
@@ -249,11 +270,15 @@ def csr_arg(x):
 
 
 def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, device=None,
-            drop_unexpressed=False):
+            drop_unexpressed=False, dist=False, gather_to=-1):
     """-> (keys uint64[n], cls int32[n], timings dict[, probe_pos, probe_neg][, kept_gene_cols])
 
     drop_unexpressed=True: `gene_cols` are candidates, genes that are zero in every row of x are dropped on
-    the device and the kept columns are returned as the last element (keys index the kept list)."""
+    the device and the kept columns are returned as the last element (keys index the kept list).
+
+    dist=True: pp_sandbag_dist over the ranks of the context's communicator (`comm_init`): every rank passes the same
+    arguments, prepares its own block of cells, evaluates its share of the gene-pair tiles; the merged, sorted list
+    arrives on every rank (gather_to < 0) or on rank `gather_to` only (n = 0 elsewhere)."""
     lib = load()
     sparse = is_sparse(x)
     if sparse:
@@ -276,13 +301,17 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
         ppos = np.zeros((n_probe, len(class_sizes)), dtype=np.int32)
         pneg = np.zeros_like(ppos)
     kg, kn = ctypes.c_void_p(), ctypes.c_int64()
+    split = (int(gather_to),) if dist else (shard, n_shards)
     tail = (_ptr(cell_rows), len(cell_rows), _ptr(class_sizes), len(class_sizes), _ptr(gene_cols), len(gene_cols),
-            _ptr(thresholds), shard, n_shards, ctypes.byref(ok), ctypes.byref(oc), ctypes.byref(on), _ptr(pp), n_probe,
-            _ptr(ppos), _ptr(pneg), 1 if drop_unexpressed else 0, ctypes.byref(kg), ctypes.byref(kn))
+            _ptr(thresholds)) + split + (ctypes.byref(ok), ctypes.byref(oc), ctypes.byref(on), _ptr(pp), n_probe,
+                                         _ptr(ppos), _ptr(pneg), 1 if drop_unexpressed else 0, ctypes.byref(kg),
+                                         ctypes.byref(kn))
     if sparse:
-        rc = lib.pp_sandbag_csr(h, ctypes.byref(csr), n_rows, n_cols, *tail)
+        fn = lib.pp_sandbag_csr_dist if dist else lib.pp_sandbag_csr
+        rc = fn(h, ctypes.byref(csr), n_rows, n_cols, *tail)
     else:
-        rc = lib.pp_sandbag(h, px, code, is_dev, n_rows, n_cols, ld, *tail)
+        fn = lib.pp_sandbag_dist if dist else lib.pp_sandbag
+        rc = fn(h, px, code, is_dev, n_rows, n_cols, ld, *tail)
     kept = None
     if kg.value:
         kept = np.ctypeslib.as_array(ctypes.cast(kg, ctypes.POINTER(ctypes.c_int32)), shape=(max(kn.value, 1),))[
@@ -310,8 +339,13 @@ _RNG = {"mt19937": PP_RNG_MT19937, "philox": PP_RNG_PHILOX, "table": PP_RNG_TABL
 
 
 def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,
-            perm_tables=None, row_begin=0, n_cells=None, want_observed=False, device=None):
-    """-> (scores float64[C, n_cells], timings[, obs_hits, obs_total])"""
+            perm_tables=None, row_begin=0, n_cells=None, want_observed=False, device=None, shard_cells=None,
+            gather_to=-1):
+    """-> (scores float64[C, n_cells], timings[, obs_hits, obs_total])
+
+    shard_cells (one entry per rank of the context's communicator, `comm_init`): pp_cyclone_dist -- this call scores
+    this rank's `n_cells` cells and the score columns of all ranks are all-gathered on the device; the returned arrays
+    are [C, sum(shard_cells)] on every rank (gather_to < 0) or on rank `gather_to` only (None elsewhere)."""
     lib = load()
     sparse = is_sparse(x)
     if sparse:
@@ -337,20 +371,89 @@ def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="
             raise ValueError("rng='table' needs perm_tables")
         tabs = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.int32).ravel() for t in perm_tables]),
                                     dtype=np.int32)
-    scores = np.empty((nc, n_cells), dtype=np.float64)
-    oh = np.empty((nc, n_cells), dtype=np.int32) if want_observed else None
-    ot = np.empty((nc, n_cells), dtype=np.int32) if want_observed else None
-    tail = (row_begin, n_cells, nc, _ptr(used), _ptr(used_off), _ptr(pairs), _ptr(pair_off), iterations, min_iter,
-            min_pairs, _RNG[rng], seed, _ptr(tabs), _ptr(scores), _ptr(oh), _ptr(ot))
+    dist = shard_cells is not None
+    receive = True
+    n_out = n_cells
+    if dist:
+        shard_cells = np.ascontiguousarray(shard_cells, dtype=np.int64)
+        me, world = comm_info(h)
+        if len(shard_cells) != world:
+            raise ValueError("shard_cells has {} entries for {} ranks".format(len(shard_cells), world))
+        receive = gather_to < 0 or gather_to == me
+        n_out = int(shard_cells.sum())
+    scores = np.empty((nc, n_out), dtype=np.float64) if receive else None
+    oh = np.empty((nc, n_out), dtype=np.int32) if want_observed and receive else None
+    ot = np.empty((nc, n_out), dtype=np.int32) if want_observed and receive else None
+    head = (row_begin, n_cells, nc, _ptr(used), _ptr(used_off), _ptr(pairs), _ptr(pair_off), iterations, min_iter,
+            min_pairs, _RNG[rng], seed, _ptr(tabs))
+    outs = (_ptr(scores), _ptr(oh), _ptr(ot))
+    if dist:
+        head = head + (_ptr(shard_cells), int(gather_to), 1 if want_observed else 0)
     if sparse:
-        rc = lib.pp_cyclone_csr(h, ctypes.byref(csr), n_rows, n_cols, *tail)
+        fn = lib.pp_cyclone_csr_dist if dist else lib.pp_cyclone_csr
+        rc = fn(h, ctypes.byref(csr), n_rows, n_cols, *(head + outs))
     else:
-        rc = lib.pp_cyclone(h, px, code, is_dev, n_rows, n_cols, ld, *tail)
+        fn = lib.pp_cyclone_dist if dist else lib.pp_cyclone
+        rc = fn(h, px, code, is_dev, n_rows, n_cols, ld, *(head + outs))
     check(rc, h)
     del keep
     if want_observed:
         return scores, timings(h), oh, ot
     return scores, timings(h)
+
+
+# ---- multi-GPU: one communicator per context -------------------------------------------------------------------
+def nccl_library_path():
+    """The libnccl.so.2 torch itself uses (nvidia/nccl/lib of the venv), or None: the library then falls back to
+    the copy already mapped into the process / the loader path."""
+    try:
+        import nvidia.nccl as pkg
+        for d in list(pkg.__path__):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except ImportError:
+        pass
+    return None
+
+
+def comm_unique_id():
+    """128 opaque bytes made by rank 0 (ncclGetUniqueId); every rank passes them to comm_init."""
+    lib = load()
+    p = nccl_library_path()
+    rc = lib.pp_nccl_load(p.encode() if p else None)
+    if rc != 0:
+        raise PyPairsB200Error(rc, lib.pp_last_error(None).decode())
+    buf = ctypes.create_string_buffer(PP_COMM_ID_BYTES)
+    rc = lib.pp_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+    if rc != 0:
+        raise PyPairsB200Error(rc, lib.pp_last_error(None).decode())
+    return bytes(buf.raw)
+
+
+def comm_init(unique_id, rank, world, device=None):
+    """Join the communicator of `unique_id` with this process's context (collective over all `world` ranks)."""
+    lib, h = load(), ctx(device)
+    p = nccl_library_path()
+    rc = lib.pp_nccl_load(p.encode() if p else None)
+    if rc != 0:
+        raise PyPairsB200Error(rc, lib.pp_last_error(None).decode())
+    buf = ctypes.create_string_buffer(bytes(unique_id), PP_COMM_ID_BYTES)
+    check(lib.pp_comm_init(h, ctypes.cast(buf, ctypes.c_void_p), int(rank), int(world)), h)
+
+
+def comm_destroy(device=None):
+    lib, h = load(), ctx(device)
+    check(lib.pp_comm_destroy(h), h)
+
+
+def comm_info(h_or_device=None):
+    """(rank, world) of the context's communicator; world = 0 without one."""
+    lib = load()
+    h = h_or_device if isinstance(h_or_device, ctypes.c_void_p) else ctx(h_or_device)
+    r, w = ctypes.c_int32(), ctypes.c_int32()
+    check(lib.pp_comm_info(h, ctypes.byref(r), ctypes.byref(w)), h)
+    return r.value, w.value
 
 
 def phase_scores(matrix, iterations, min_iter, min_pairs, pairs, used, device=None):

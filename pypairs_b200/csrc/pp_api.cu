@@ -94,6 +94,7 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) pp_comm_destroy(ctx);
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int b = 0; b < 2; ++b)

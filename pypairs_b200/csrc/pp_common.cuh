@@ -16,6 +16,16 @@
 
 #define PP_API extern "C" __attribute__((visibility("default")))
 
+// The handful of NCCL declarations the library needs (values fixed by NCCL's ABI since 2.0); the entry points are
+// resolved at run time (pp_comm.cu), so neither nccl.h nor libnccl is needed to build.
+namespace ppn {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2 };
+}  // namespace ppn
+
 struct pp_ctx {
     int device = 0;
     int n_sm = 0;
@@ -35,6 +45,8 @@ struct pp_ctx {
     std::string err;
     pp_timings tm = {};
     int launches = 0;
+    void *comm = nullptr;  // ncclComm_t of pp_comm_init (one rank per ctx), NULL = single GPU
+    int comm_rank = 0, comm_world = 0;
 };
 
 extern thread_local std::string g_pp_err;  // errors raised without a ctx
@@ -169,6 +181,10 @@ int pp_csr_col_nonzero(pp_ctx *ctx, const DevCsr &m, uint8_t *d_nz);
 // rows[i] < 0 leaves row i zero.
 int pp_csr_densify(pp_ctx *ctx, const DevCsr &m, const int32_t *d_rows, int64_t n_out, const int32_t *d_colmap,
                    void *d_out, int64_t out_ld);
+
+// ---- collectives on the ctx stream (pp_comm.cu); a ctx without communicator fails with PP_ENCCL
+int pp_allreduce_max(pp_ctx *ctx, void *d_buf, size_t count, int nccl_dtype);  // in place
+int pp_allgather_bytes(pp_ctx *ctx, const void *d_send, void *d_recv, size_t bytes_per_rank);  // in place allowed
 
 // ---- internal entry points (one per .cu) --------------------------------------------------------
 // Rank transform: for each slot s < n_slots (cell_rows[s] < 0 marks a padding slot: all ranks 0),

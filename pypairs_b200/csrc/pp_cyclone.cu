@@ -831,14 +831,123 @@ PP_API int pp_perm_table(pp_ctx *ctx, int32_t rng_mode, uint64_t seed, int32_t c
     PP_GUARD(ctx, body());
 }
 
-// Shared body of pp_cyclone (dense x, csr == NULL) and pp_cyclone_csr (csr != NULL, x / ld unused).
+// pp_cyclone_dist: the score columns of all ranks (cyclone.py:151-170) through ONE all-gather on the ctx stream.
+// Every rank contributes a block [n_classes][max shard] of doubles (+ the two observed-counter arrays when asked
+// for); receiving ranks copy the gathered blocks to the host and lay them out as [n_classes][all cells], shards in
+// rank order.  The NaN flag is max-reduced first so that a NaN on one rank fails the call on every rank.
+static int cyclone_gather(pp_ctx *ctx, const double *d_scores, const int32_t *d_oh, const int32_t *d_ot, int32_t *d_flags,
+                          int64_t n_cells, int32_t n_classes, const int64_t *shard_cells, int32_t gather_to,
+                          double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total, bool want_oh, bool want_ot) {
+    cudaStream_t st = ctx->stream;
+    const int wd = ctx->comm_world, me = ctx->comm_rank;
+    const bool receive = gather_to < 0 || gather_to == me;
+    int rc = pp_allreduce_max(ctx, d_flags, 4, ppn::ncclInt32);
+    if (rc) return rc;
+    int64_t maxn = 0, n_total = 0;
+    for (int q = 0; q < wd; ++q) {
+        maxn = std::max(maxn, shard_cells[q]);
+        n_total += shard_cells[q];
+    }
+    const size_t sc_blk = sizeof(double) * (size_t)n_classes * maxn, ob_blk = sizeof(int32_t) * (size_t)n_classes * maxn;
+    const size_t blk = sc_blk + (want_oh ? ob_blk : 0) + (want_ot ? ob_blk : 0);
+    int32_t flags[4] = {0, 0, 0, 0};
+    uint8_t *gbuf = nullptr;
+    if (blk) {
+        if (!(gbuf = (uint8_t *)pp_slab(ctx, SLAB_OUT, blk * wd))) return PP_ENOMEM;
+        uint8_t *mine = gbuf + blk * me;
+        if (n_cells > 0) {
+            PP_CUDA(cudaMemcpy2DAsync(mine, maxn * sizeof(double), d_scores, n_cells * sizeof(double), n_cells * sizeof(double),
+                                      n_classes, cudaMemcpyDeviceToDevice, st));
+            if (want_oh)
+                PP_CUDA(cudaMemcpy2DAsync(mine + sc_blk, maxn * sizeof(int32_t), d_oh, n_cells * sizeof(int32_t),
+                                          n_cells * sizeof(int32_t), n_classes, cudaMemcpyDeviceToDevice, st));
+            if (want_ot)
+                PP_CUDA(cudaMemcpy2DAsync(mine + sc_blk + (want_oh ? ob_blk : 0), maxn * sizeof(int32_t), d_ot,
+                                          n_cells * sizeof(int32_t), n_cells * sizeof(int32_t), n_classes,
+                                          cudaMemcpyDeviceToDevice, st));
+        }
+        rc = pp_allgather_bytes(ctx, mine, gbuf, blk);
+        if (rc) return rc;
+    }
+    // receiving ranks: shards laid side by side on the device ([n_classes][all cells] per array), one copy to pinned
+    // staging, then into the caller's arrays
+    uint8_t *stage = nullptr;
+    const size_t sc_all = sizeof(double) * (size_t)n_classes * n_total, ob_all = sizeof(int32_t) * (size_t)n_classes * n_total;
+    const size_t all_bytes = sc_all + (want_oh ? ob_all : 0) + (want_ot ? ob_all : 0);
+    if (receive && all_bytes) {
+        uint8_t *d_full = (uint8_t *)pp_slab(ctx, SLAB_OUT2, all_bytes);
+        if (!d_full) return PP_ENOMEM;
+        int64_t off = 0;
+        for (int q = 0; q < wd; ++q) {
+            const uint8_t *b = gbuf + blk * q;
+            const int64_t nq = shard_cells[q];
+            if (nq > 0) {
+                PP_CUDA(cudaMemcpy2DAsync(d_full + sizeof(double) * off, n_total * sizeof(double), b, maxn * sizeof(double),
+                                          nq * sizeof(double), n_classes, cudaMemcpyDeviceToDevice, st));
+                if (want_oh)
+                    PP_CUDA(cudaMemcpy2DAsync(d_full + sc_all + sizeof(int32_t) * off, n_total * sizeof(int32_t), b + sc_blk,
+                                              maxn * sizeof(int32_t), nq * sizeof(int32_t), n_classes, cudaMemcpyDeviceToDevice, st));
+                if (want_ot)
+                    PP_CUDA(cudaMemcpy2DAsync(d_full + sc_all + (want_oh ? ob_all : 0) + sizeof(int32_t) * off,
+                                              n_total * sizeof(int32_t), b + sc_blk + (want_oh ? ob_blk : 0), maxn * sizeof(int32_t),
+                                              nq * sizeof(int32_t), n_classes, cudaMemcpyDeviceToDevice, st));
+            }
+            off += nq;
+        }
+        if (ctx->pin_out_bytes < all_bytes) {
+            if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+            ctx->pin_out = nullptr;
+            ctx->pin_out_bytes = 0;
+            const size_t want = std::max<size_t>(all_bytes * 2, (size_t)8 << 20);
+            PP_CUDA(cudaHostAlloc(&ctx->pin_out, want, cudaHostAllocDefault));
+            ctx->pin_out_bytes = want;
+        }
+        stage = (uint8_t *)ctx->pin_out;
+        PP_CUDA(cudaMemcpyAsync(stage, d_full, all_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    PP_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    PP_CUDA(cudaEventRecord(ctx->ev[5], st));
+    PP_CUDA(cudaStreamSynchronize(st));
+    if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_cyclone: NaN in the expression matrix");
+    if (stage) {
+        if (!out_scores) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: out_scores is NULL on a receiving rank");
+        // fresh pages of a large result: a few threads take the page faults in parallel
+        struct Part { void *dst; const uint8_t *src; size_t n; };
+        const Part parts[3] = {{out_scores, stage, sc_all},
+                               {want_oh ? out_obs_hits : nullptr, stage + sc_all, ob_all},
+                               {want_ot ? out_obs_total : nullptr, stage + sc_all + (want_oh ? ob_all : 0), ob_all}};
+        for (const Part &pt : parts) {
+            if (!pt.dst) continue;
+            const int n_thr = pt.n >= ((size_t)4 << 20) ? 4 : 1;
+            std::vector<std::thread> pool;
+            for (int t = 1; t < n_thr; ++t)
+                pool.emplace_back([=] { memcpy((uint8_t *)pt.dst + pt.n * t / n_thr, pt.src + pt.n * t / n_thr, pt.n * (t + 1) / n_thr - pt.n * t / n_thr); });
+            memcpy(pt.dst, pt.src, pt.n / n_thr);
+            for (auto &th : pool) th.join();
+        }
+    }
+    return PP_OK;
+}
+
+// Shared body of pp_cyclone (dense x, csr == NULL), pp_cyclone_csr (csr != NULL, x / ld unused) and their _dist forms
+// (shard_cells != NULL: the scores of all ranks are all-gathered, see cyclone_gather).
 static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, const pp_csr *csr, int64_t n_rows,
                         int64_t n_cols, int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes,
                         const int32_t *used_idx, const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off,
                         int32_t iterations, int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
-                        const int32_t *perm_tables, double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
+                        const int32_t *perm_tables, const int64_t *shard_cells, int32_t gather_to, bool want_oh,
+                        bool want_ot, double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
-    if ((!x && !csr) || !used_idx || !used_off || !pairs || !pair_off || !out_scores)
+    const bool dist = shard_cells != nullptr;
+    if (dist) {
+        if (!ctx->comm) return pp_fail(ctx, PP_ENCCL, "pp_cyclone_dist: the context has no communicator (pp_comm_init)");
+        if (gather_to >= ctx->comm_world) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: gather_to %d of %d ranks", gather_to, ctx->comm_world);
+        if (shard_cells[ctx->comm_rank] != n_cells) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: shard_cells[rank] != n_cells");
+        for (int q = 0; q < ctx->comm_world; ++q)
+            if (shard_cells[q] < 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: negative shard size");
+    }
+    const bool receive = !dist || gather_to < 0 || gather_to == ctx->comm_rank;
+    if ((!x && !csr) || !used_idx || !used_off || !pairs || !pair_off || (receive && !out_scores))
         return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: x_dtype must be PP_F32/PP_F64");
     if (n_rows <= 0 || n_cols <= 0 || (!csr && ld < n_cols)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad matrix shape");
@@ -854,7 +963,15 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     ctx->tm = pp_timings();
     ctx->launches = 0;
     ctx->tm.n_units = n_cells;
-    if (n_cells == 0) return PP_OK;
+    if (n_cells == 0 && !dist) return PP_OK;
+    if (n_cells == 0) {  // an empty shard still takes part in the collectives
+        PP_CUDA(cudaSetDevice(ctx->device));
+        DevBuf d_f;
+        PP_CUDA(d_f.alloc(sizeof(int32_t) * 4, ctx->stream));
+        PP_CUDA(cudaMemsetAsync(d_f.p, 0, sizeof(int32_t) * 4, ctx->stream));
+        return cyclone_gather(ctx, nullptr, nullptr, nullptr, d_f.as<int32_t>(), 0, n_classes, shard_cells, gather_to,
+                              out_scores, out_obs_hits, out_obs_total, want_oh, want_ot);
+    }
 
     // ---- union of used genes, per-class maps
     std::vector<int32_t> uni;
@@ -1028,8 +1145,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaMemcpyAsync(d_cd.p, cds.data(), sizeof(ClassDesc) * n_classes, cudaMemcpyHostToDevice, ts));
     const size_t out_cnt = (size_t)n_classes * n_cells;
     PP_CUDA(d_scores.alloc(sizeof(double) * out_cnt, st));
-    if (out_obs_hits) PP_CUDA(d_oh.alloc(sizeof(int32_t) * out_cnt, st));
-    if (out_obs_total) PP_CUDA(d_ot.alloc(sizeof(int32_t) * out_cnt, st));
+    if (want_oh) PP_CUDA(d_oh.alloc(sizeof(int32_t) * out_cnt, st));
+    if (want_ot) PP_CUDA(d_ot.alloc(sizeof(int32_t) * out_cnt, st));
     PP_CUDA(cudaEventRecord(ctx->ev[1], ts));  // tables enqueued
     bool tables_awaited = false;
 
@@ -1043,8 +1160,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     P.min_pairs = min_pairs;
     P.classes = d_cd.as<ClassDesc>();
     P.scores = d_scores.as<double>();
-    P.obs_hits = out_obs_hits ? d_oh.as<int32_t>() : nullptr;
-    P.obs_total = out_obs_total ? d_ot.as<int32_t>() : nullptr;
+    P.obs_hits = want_oh ? d_oh.as<int32_t>() : nullptr;
+    P.obs_total = want_ot ? d_ot.as<int32_t>() : nullptr;
     PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     PP_CUDA(cudaFuncSetAttribute(score_kernel<MODE_B8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     P.max_rank = d_flags.as<int32_t>();
@@ -1317,10 +1434,15 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             score_ms += ms;
         }
     }
+    if (dist) {
+        rc = cyclone_gather(ctx, d_scores.as<double>(), d_oh.as<int32_t>(), d_ot.as<int32_t>(), d_flags.as<int32_t>(), n_cells,
+                            n_classes, shard_cells, gather_to, out_scores, out_obs_hits, out_obs_total, want_oh, want_ot);
+        if (rc) return rc;
+    } else {
     // results: device -> pinned staging -> the caller's (pageable) arrays; a direct copy would be staged by the driver
     // at a fraction of the rate
     const size_t sc_bytes = sizeof(double) * out_cnt, ob_bytes = sizeof(int32_t) * out_cnt;
-    const size_t stage_bytes = sc_bytes + (out_obs_hits ? ob_bytes : 0) + (out_obs_total ? ob_bytes : 0) + 16;
+    const size_t stage_bytes = sc_bytes + (want_oh ? ob_bytes : 0) + (want_ot ? ob_bytes : 0) + 16;
     if (ctx->pin_out_bytes < stage_bytes) {
         if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
         ctx->pin_out = nullptr;
@@ -1331,17 +1453,18 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     uint8_t *stage_p = (uint8_t *)ctx->pin_out;
     int32_t *flags = (int32_t *)stage_p;
-    uint8_t *st_sc = stage_p + 16, *st_oh = st_sc + sc_bytes, *st_ot = st_oh + (out_obs_hits ? ob_bytes : 0);
+    uint8_t *st_sc = stage_p + 16, *st_oh = st_sc + sc_bytes, *st_ot = st_oh + (want_oh ? ob_bytes : 0);
     PP_CUDA(cudaMemcpyAsync(st_sc, d_scores.p, sc_bytes, cudaMemcpyDeviceToHost, st));
-    if (out_obs_hits) PP_CUDA(cudaMemcpyAsync(st_oh, d_oh.p, ob_bytes, cudaMemcpyDeviceToHost, st));
-    if (out_obs_total) PP_CUDA(cudaMemcpyAsync(st_ot, d_ot.p, ob_bytes, cudaMemcpyDeviceToHost, st));
+    if (want_oh) PP_CUDA(cudaMemcpyAsync(st_oh, d_oh.p, ob_bytes, cudaMemcpyDeviceToHost, st));
+    if (want_ot) PP_CUDA(cudaMemcpyAsync(st_ot, d_ot.p, ob_bytes, cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaEventRecord(ctx->ev[5], st));
     PP_CUDA(cudaStreamSynchronize(st));
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_cyclone: NaN in the expression matrix");
     memcpy(out_scores, st_sc, sc_bytes);
-    if (out_obs_hits) memcpy(out_obs_hits, st_oh, ob_bytes);
-    if (out_obs_total) memcpy(out_obs_total, st_ot, ob_bytes);
+    if (want_oh) memcpy(out_obs_hits, st_oh, ob_bytes);
+    if (want_ot) memcpy(out_obs_total, st_ot, ob_bytes);
+    }
     if (pipelined) {  // copies overlap compute: h2d = copy-stream span, main = sum of the score launches
         ctx->tm.h2d_ms = copy_ms;
         ctx->tm.main_ms = score_ms;
@@ -1368,7 +1491,8 @@ PP_API int pp_cyclone(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
     PP_GUARD(ctx, cyclone_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, row_begin, n_cells, n_classes,
                                used_idx, used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode, seed,
-                               perm_tables, out_scores, out_obs_hits, out_obs_total));
+                               perm_tables, nullptr, -1, out_obs_hits != nullptr, out_obs_total != nullptr, out_scores,
+                               out_obs_hits, out_obs_total));
 }
 
 PP_API int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, int64_t row_begin,
@@ -1379,7 +1503,36 @@ PP_API int pp_cyclone_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t 
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_csr: NULL argument");
     PP_GUARD(ctx, cyclone_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
                                row_begin, n_cells, n_classes, used_idx, used_off, pairs, pair_off, iterations, min_iter,
-                               min_pairs, rng_mode, seed, perm_tables, out_scores, out_obs_hits, out_obs_total));
+                               min_pairs, rng_mode, seed, perm_tables, nullptr, -1, out_obs_hits != nullptr,
+                               out_obs_total != nullptr, out_scores, out_obs_hits, out_obs_total));
+}
+
+// want_observed: the observed-counter arrays must be requested by ALL ranks or by none (they change the size of the
+// all-gathered block); a non-receiving rank passes NULL outputs, so the wish travels separately.
+PP_API int pp_cyclone_dist(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                           int64_t ld, int64_t row_begin, int64_t n_cells, int32_t n_classes, const int32_t *used_idx,
+                           const int64_t *used_off, const int32_t *pairs, const int64_t *pair_off, int32_t iterations,
+                           int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
+                           const int32_t *perm_tables, const int64_t *shard_cells, int32_t gather_to,
+                           int32_t want_observed, double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
+    if (ctx && (!x || !shard_cells)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: NULL argument");
+    PP_GUARD(ctx, cyclone_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, row_begin, n_cells, n_classes,
+                               used_idx, used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode, seed,
+                               perm_tables, shard_cells, gather_to, want_observed != 0, want_observed != 0, out_scores,
+                               out_obs_hits, out_obs_total));
+}
+
+PP_API int pp_cyclone_csr_dist(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, int64_t row_begin,
+                               int64_t n_cells, int32_t n_classes, const int32_t *used_idx, const int64_t *used_off,
+                               const int32_t *pairs, const int64_t *pair_off, int32_t iterations, int32_t min_iter,
+                               int32_t min_pairs, int32_t rng_mode, uint64_t seed, const int32_t *perm_tables,
+                               const int64_t *shard_cells, int32_t gather_to, int32_t want_observed, double *out_scores,
+                               int32_t *out_obs_hits, int32_t *out_obs_total) {
+    if (ctx && (!x || !shard_cells)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_csr_dist: NULL argument");
+    PP_GUARD(ctx, cyclone_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
+                               row_begin, n_cells, n_classes, used_idx, used_off, pairs, pair_off, iterations, min_iter,
+                               min_pairs, rng_mode, seed, perm_tables, shard_cells, gather_to, want_observed != 0,
+                               want_observed != 0, out_scores, out_obs_hits, out_obs_total));
 }
 
 PP_API int pp_phase_scores(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows,

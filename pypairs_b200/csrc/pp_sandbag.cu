@@ -9,7 +9,9 @@
 //                            (bit p of the rank) and the suffix planes "rank >= 2^j"; bit c of
 //                            cell word w belongs to cell 32*w + c (cells of ONE class).  A
 //                            (block, plane, run of words) is one contiguous byte range -> one
-//                            1-D TMA bulk copy.
+//                            1-D TMA bulk copy.  With several ranks (pp_sandbag_dist) every rank owns one such
+//                            region holding ITS cells (class-sorted and padded per rank), regions are exchanged
+//                            with one all-gather, and a chunk names (owner rank, first word, words).
 // Pair kernel (pair_kernel): CTA tile = 128 a-positions x 64 b-positions, every thread owns a
 // 4x4 register tile of gene pairs and walks all cell words.  For one word the predicate
 // x[a] > x[b] (x[a] < x[b] in the second sweep) of sandbag.py:179-182 is evaluated for 32
@@ -62,8 +64,10 @@ col_or_kernel(const uint16_t *__restrict__ rank, int64_t n_slots, int n_genes, u
 //     q <  Bn            low plane q   (bit q of the rank)
 //     q >= Bn            suffix plane S_j, j = q - Bn + 1 (1 <= j < Bn): OR of the planes >= j, i.e. "rank >= 2^j"
 // ------------------------------------------------------------------------------------------
+// n_words = cell words of THIS rank's cells (rows of `rank`), stride_words = words per plane of a rank's region (the
+// same on every rank, >= n_words; the words beyond n_words stay zero = all-tie cells).
 __global__ void __launch_bounds__(256)
-bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes, int n_words,
+bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes, int n_words, int stride_words,
                 const int32_t *__restrict__ pos_gene, const int64_t *__restrict__ blk_off,
                 const int32_t *__restrict__ blk_bits, uint32_t *__restrict__ planes) {
     const int lane = threadIdx.x & 31;
@@ -71,7 +75,7 @@ bitslice_kernel(const uint16_t *__restrict__ rank, int64_t rank_ld, int n_genes,
     if (pos - lane >= n_genes) return;
     const int g = pos < n_genes ? __ldg(pos_gene + pos) : 0;
     const int nb = pos >> 6, bn = __ldg(blk_bits + nb);
-    const int64_t ps = (int64_t)n_words * 64;  // words per plane
+    const int64_t ps = (int64_t)stride_words * 64;  // words per plane
     for (int w = blockIdx.y; w < n_words; w += gridDim.y) {
         uint32_t r[32];
         const uint16_t *src = rank + (int64_t)w * 32 * rank_ld + g;
@@ -116,11 +120,11 @@ template <int N> __device__ __forceinline__ void load_words(const uint32_t *p, u
     }
 }
 
-struct Chunk {  // a run of cell words of one class
-    int32_t w_begin;
+struct Chunk {  // a run of cell words of one class inside one rank's plane region
+    int32_t w_begin;    // first word, local to the owner's region
     int32_t n_words;
     int32_t class_end;  // class index if this chunk closes the class, else -1
-    int32_t pad;
+    int32_t owner;      // rank whose region holds the words (0 on a single GPU)
 };
 
 struct TileDesc {
@@ -142,7 +146,8 @@ struct PairParams {
     unsigned long long *out;    // compacted (key << 16 | class)
     unsigned long long *out_count;
     unsigned long long out_cap;
-    int n_genes, n_words, n_classes;
+    int64_t rank_stride;  // u32 words between the plane regions of two ranks
+    int n_genes, n_words, n_classes;  // n_words = words per plane of one region
     int32_t chunk_off[MAX_PLANES + 1], chunk_cnt[MAX_PLANES + 1];  // table of plane count bp
 };
 
@@ -243,7 +248,9 @@ __device__ __forceinline__ void tile_body(const PairParams &P, const TileDesc td
                 for (int j = 0; j < PER_LANE; ++j) {
                     const int i = lane + 32 * j;
                     if (i < N_COPIES)
-                        bulk_g2s(dst + i * PLANE, src[j] + (real[j] ? (int64_t)ch.w_begin * 64 : 0), bytes, &pk_full_bar[s]);
+                        bulk_g2s(dst + i * PLANE,
+                                 src[j] + (real[j] ? (int64_t)ch.owner * P.rank_stride + (int64_t)ch.w_begin * 64 : 0), bytes,
+                                 &pk_full_bar[s]);
                 }
             }
         };
@@ -452,8 +459,8 @@ __global__ void __launch_bounds__(PAIR_THREADS + 32, 1) pair_kernel(const PairPa
 // per-class counters of selected pairs straight from the planes (one warp per probe pair)
 __global__ void probe_kernel(const uint32_t *__restrict__ planes, const int64_t *__restrict__ blk_off,
                              const int32_t *__restrict__ blk_bits, const int32_t *__restrict__ gene_pos,
-                             const Chunk *__restrict__ chunks, int n_chunks, int n_words, int n_classes,
-                             const int64_t *__restrict__ pairs, int64_t n_probe, int32_t *__restrict__ pos_out,
+                             const Chunk *__restrict__ chunks, int n_chunks, int n_words, int64_t rank_stride,
+                             int n_classes, const int64_t *__restrict__ pairs, int64_t n_probe, int32_t *__restrict__ pos_out,
                              int32_t *__restrict__ neg_out) {
     const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -466,10 +473,12 @@ __global__ void probe_kernel(const uint32_t *__restrict__ planes, const int64_t 
     int pos = 0, neg = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const Chunk ch = chunks[c];
+        const int64_t reg = (int64_t)ch.owner * rank_stride;
         for (int w = ch.w_begin + lane; w < ch.w_begin + ch.n_words; w += 32) {
             uint32_t gt = 0, lt = 0;
             for (int p = 0; p < max(b1, b2); ++p) {
-                const uint32_t a = p < b1 ? pa[p * ps + (int64_t)w * 64] : 0u, b = p < b2 ? pb[p * ps + (int64_t)w * 64] : 0u;
+                const uint32_t a = p < b1 ? pa[reg + p * ps + (int64_t)w * 64] : 0u;
+                const uint32_t b = p < b2 ? pb[reg + p * ps + (int64_t)w * 64] : 0u;
                 gt = lop3_gt(a, b, gt);
                 lt = lop3_lt(a, b, lt);
             }
@@ -621,18 +630,31 @@ int bit_length64(uint64_t v) {
 
 }  // namespace
 
-// Shared body of pp_sandbag (dense x, csr == NULL) and pp_sandbag_csr (csr != NULL, x / ld unused).
+// Shared body of pp_sandbag / pp_sandbag_csr (csr != NULL: x / ld unused) and their _dist forms.
+//
+// Cells are laid out in PIECES: piece (q, k) = the cells of class k owned by data rank q, padded to whole 32-cell
+// words; the planes of rank q's pieces form region q of the plane buffer.  On one GPU there is one data rank that
+// owns everything (and `shard / n_shards` only deals the gene-pair tiles, every shard preparing all cells itself);
+// with dist = true the data ranks are the ranks of the ctx's communicator, every rank prepares only its own region,
+// one all-gather completes the buffer, and rank r evaluates the tiles t % world == r.
 static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, const pp_csr *csr, int64_t n_rows,
                         int64_t n_cols, int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
                         int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
-                        int32_t shard, int32_t n_shards, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
-                        const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
-                        int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
+                        int32_t shard, int32_t n_shards, bool dist, int32_t gather_to, uint64_t **out_keys,
+                        int32_t **out_class, int64_t *out_n, const int64_t *probe_pairs, int64_t n_probe,
+                        int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed, int32_t **out_kept_genes,
+                        int64_t *out_n_kept) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
     if ((!x && !csr) || !cell_rows || !class_sizes || !gene_cols || !thresholds || !out_keys || !out_class || !out_n)
         return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: x_dtype must be PP_F32/PP_F64");
     if (n_rows <= 0 || n_cols <= 0 || (!csr && ld < n_cols)) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: bad matrix shape");
+    if (dist) {
+        if (!ctx->comm) return pp_fail(ctx, PP_ENCCL, "pp_sandbag_dist: the context has no communicator (pp_comm_init)");
+        if (gather_to >= ctx->comm_world) return pp_fail(ctx, PP_EINVAL, "pp_sandbag_dist: gather_to %d of %d ranks", gather_to, ctx->comm_world);
+        shard = ctx->comm_rank;
+        n_shards = ctx->comm_world;
+    }
     if (csr) {
         const int vrc = pp_csr_validate(ctx, csr, n_rows, n_cols, "pp_sandbag_csr");
         if (vrc) return vrc;
@@ -661,42 +683,93 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     if (out_kept_genes) *out_kept_genes = nullptr;
     if (out_n_kept) *out_n_kept = 0;
 
+    // ---- data ranks: contiguous row blocks [rb[q], rb[q+1]) holding equal numbers of kept cells
+    const int wd = dist ? ctx->comm_world : 1, me = dist ? ctx->comm_rank : 0;
+    const bool receive = !dist || gather_to < 0 || gather_to == me;
+    std::vector<int64_t> rb((size_t)wd + 1, 0);
+    rb[wd] = n_rows;
+    if (wd > 1 && n_cells > 0) {
+        std::vector<int32_t> sorted(cell_rows, cell_rows + n_cells);
+        std::sort(sorted.begin(), sorted.end());
+        for (int q = 1; q < wd; ++q) rb[q] = sorted[(size_t)(n_cells * q / wd)];
+    }
+    auto owner_of = [&](int64_t row) { return (int)(std::upper_bound(rb.begin() + 1, rb.begin() + wd, row) - (rb.begin() + 1)); };
+    // pieces: cells of (owner q, class k), class-sorted order kept
+    std::vector<int64_t> piece_cnt((size_t)wd * n_classes, 0);
+    std::vector<std::vector<int32_t>> my_cells((size_t)n_classes);
+    {
+        int64_t src = 0;
+        for (int k = 0; k < n_classes; ++k) {
+            for (int64_t i = 0; i < class_sizes[k]; ++i) {
+                const int32_t row = cell_rows[src + i];
+                const int q = wd > 1 ? owner_of(row) : 0;
+                ++piece_cnt[(size_t)q * n_classes + k];
+                if (q == me) my_cells[k].push_back(row);
+            }
+            src += class_sizes[k];
+        }
+    }
+    std::vector<int32_t> piece_w((size_t)wd * n_classes), piece_w0((size_t)wd * n_classes);
+    int W_me = 0, Wl = 1;  // words of my region in use; words per plane of every region
+    for (int q = 0; q < wd; ++q) {
+        int64_t w = 0;
+        for (int k = 0; k < n_classes; ++k) {
+            piece_w0[(size_t)q * n_classes + k] = (int32_t)w;
+            piece_w[(size_t)q * n_classes + k] = (int32_t)((piece_cnt[(size_t)q * n_classes + k] + 31) / 32);
+            w += piece_w[(size_t)q * n_classes + k];
+        }
+        if (w > (1 << 26)) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 2^31 cells");
+        if (q == me) W_me = (int)w;
+        Wl = std::max(Wl, (int)w);
+    }
+    const int64_t r0 = rb[me], nr_local = rb[me + 1] - rb[me];  // my row block
+
     PP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
-    DevBuf d_slots, d_gene, d_flags, d_chunks, d_tiles, d_thr, d_cnt;
+    DevBuf d_slots, d_gene, d_red, d_chunks, d_tiles, d_thr, d_cnt;
     void *s_x = nullptr, *s_rank = nullptr, *s_planes = nullptr, *s_out = nullptr, *s_out2 = nullptr;  // ctx slabs
     const size_t esz = x_dtype == PP_F64 ? 8 : 4;
-    const void *dx = x;
-    DevCsr dcsr;
+    const uint8_t *dx_local = nullptr;  // row r0 of the matrix on the device (dense input)
+    DevCsr dcsr;                        // rows [r0, r0 + nr_local), rebased to 0 (CSR input)
     int rc = PP_OK;
     if (csr) {
-        rc = pp_csr_to_device(ctx, csr, 0, n_rows, &dcsr);
+        rc = pp_csr_to_device(ctx, csr, r0, nr_local, &dcsr);
         if (rc) return rc;
     } else if (!x_is_device) {
-        if (!(s_x = pp_slab(ctx, SLAB_X, (size_t)n_rows * ld * esz))) return PP_ENOMEM;
-        PP_CUDA(cudaMemcpyAsync(s_x, x, (size_t)n_rows * ld * esz, cudaMemcpyHostToDevice, st));
-        ctx->tm.h2d_bytes = (int64_t)((size_t)n_rows * ld * esz);
-        dx = s_x;
+        if (!(s_x = pp_slab(ctx, SLAB_X, (size_t)std::max<int64_t>(nr_local, 1) * ld * esz))) return PP_ENOMEM;
+        if (nr_local > 0) {
+            const size_t bytes = ((size_t)(nr_local - 1) * ld + (size_t)n_cols) * esz;  // the last row may end at n_cols
+            PP_CUDA(cudaMemcpyAsync(s_x, (const uint8_t *)x + (size_t)r0 * ld * esz, bytes, cudaMemcpyHostToDevice, st));
+            ctx->tm.h2d_bytes = (int64_t)bytes;
+        }
+        dx_local = (const uint8_t *)s_x;
+    } else {
+        dx_local = (const uint8_t *)x + (size_t)r0 * ld * esz;
     }
     PP_CUDA(cudaEventRecord(ctx->ev[1], st));
 
-    // ---- optional: drop genes that are zero in ALL rows of x (utils.py:368, before sample filtering)
+    // ---- optional: drop genes that are zero in ALL rows of x (utils.py:368, before sample filtering); every data
+    //      rank scans its own row block, the flags are max-reduced
     std::vector<int32_t> kept;
     if (drop_unexpressed) {
         DevBuf d_nz;
         PP_CUDA(d_nz.alloc((size_t)n_cols, st));
         PP_CUDA(cudaMemsetAsync(d_nz.p, 0, (size_t)n_cols, st));
-        dim3 grid((unsigned)((n_cols + 255) / 256), (unsigned)std::min<int64_t>((n_rows + 63) / 64, 65535));
         if (csr) {
             rc = pp_csr_col_nonzero(ctx, dcsr, d_nz.as<uint8_t>());
             if (rc) return rc;
-        } else if (x_dtype == PP_F64) {
-            col_nonzero_kernel<double><<<grid, 256, 0, st>>>((const double *)dx, ld, n_rows, n_cols, d_nz.as<uint8_t>());
+        } else if (nr_local > 0) {
+            dim3 grid((unsigned)((n_cols + 255) / 256), (unsigned)std::min<int64_t>((nr_local + 63) / 64, 65535));
+            if (x_dtype == PP_F64)
+                col_nonzero_kernel<double><<<grid, 256, 0, st>>>((const double *)dx_local, ld, nr_local, n_cols, d_nz.as<uint8_t>());
+            else
+                col_nonzero_kernel<float><<<grid, 256, 0, st>>>((const float *)dx_local, ld, nr_local, n_cols, d_nz.as<uint8_t>());
             PP_CHECK_LAUNCH();
-        } else {
-            col_nonzero_kernel<float><<<grid, 256, 0, st>>>((const float *)dx, ld, n_rows, n_cols, d_nz.as<uint8_t>());
-            PP_CHECK_LAUNCH();
+        }
+        if (wd > 1) {
+            rc = pp_allreduce_max(ctx, d_nz.p, (size_t)n_cols, ppn::ncclUint8);
+            if (rc) return rc;
         }
         std::vector<uint8_t> nz((size_t)n_cols);
         PP_CUDA(cudaMemcpyAsync(nz.data(), d_nz.p, (size_t)n_cols, cudaMemcpyDeviceToHost, st));
@@ -711,35 +784,31 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         *out_kept_genes = hk;
         *out_n_kept = n_genes;
     }
-    if (n_genes < 2 || n_cells == 0) return PP_OK;  // no pairs
+    if (n_genes < 2 || n_cells == 0) return PP_OK;  // no pairs (the same decision on every rank)
     if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65535 kept genes");
 
-    // ---- host-side layout tables: padded slots, chunks, tiles
-    std::vector<int32_t> slots;
-    std::vector<int32_t> class_w0(n_classes + 1, 0);
-    {
-        int64_t src = 0;
-        for (int k = 0; k < n_classes; ++k) {
-            const int64_t nk = class_sizes[k], wk = (nk + 31) / 32;
-            class_w0[k + 1] = class_w0[k] + (int32_t)wk;
-            for (int64_t i = 0; i < wk * 32; ++i) slots.push_back(i < nk ? cell_rows[src + i] : -1);
-            src += nk;
-        }
+    // ---- my slots: row (relative to my block) of every cell of my pieces, -1 = padding cell
+    const int64_t n_slots = (int64_t)W_me * 32;
+    std::vector<int32_t> slots((size_t)std::max<int64_t>(n_slots, 1), -1);
+    for (int k = 0; k < n_classes; ++k) {  // dx_local / dcsr start at row r0 in every input form
+        const int64_t base = (int64_t)piece_w0[(size_t)me * n_classes + k] * 32;
+        for (size_t i = 0; i < my_cells[k].size(); ++i) slots[(size_t)base + i] = (int32_t)(my_cells[k][i] - r0);
     }
-    const int W = class_w0[n_classes];
-    const int64_t n_slots = (int64_t)W * 32;
     const int NB = (int)((n_genes + 63) / 64);
     const int NB_alloc = (NB + 1) & ~1;
 
-    PP_CUDA(d_slots.alloc(sizeof(int32_t) * n_slots, st));
-    PP_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(int32_t) * n_slots, cudaMemcpyHostToDevice, st));
+    PP_CUDA(d_slots.alloc(sizeof(int32_t) * slots.size(), st));
+    PP_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(int32_t) * slots.size(), cudaMemcpyHostToDevice, st));
     PP_CUDA(d_gene.alloc(sizeof(int32_t) * n_genes, st));
     PP_CUDA(cudaMemcpyAsync(d_gene.p, gene_cols, sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
-    if (!(s_rank = pp_slab(ctx, SLAB_RANK, sizeof(uint16_t) * n_slots * n_genes))) return PP_ENOMEM;
-    PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
-    PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
+    if (!(s_rank = pp_slab(ctx, SLAB_RANK, sizeof(uint16_t) * std::max<int64_t>(n_slots, 1) * n_genes))) return PP_ENOMEM;
+    // one buffer for everything that is max-reduced after ranking: [0] largest rank, [1] NaN seen, [4 + g] OR of gene g's ranks
+    PP_CUDA(d_red.alloc(sizeof(uint32_t) * (4 + (size_t)n_genes), st));
+    PP_CUDA(cudaMemsetAsync(d_red.p, 0, sizeof(uint32_t) * (4 + (size_t)n_genes), st));
+    int32_t *d_flags = d_red.as<int32_t>();
+    uint32_t *d_orbits = d_red.as<uint32_t>() + 4;
 
-    if (csr) {
+    if (csr && n_slots > 0) {
         // densify the kept genes of a run of slots, rank them, next run (<= 256 MB of dense values at a time)
         std::vector<int32_t> colmap((size_t)n_cols, -1), ident((size_t)n_genes);
         for (int64_t g = 0; g < n_genes; ++g) {
@@ -764,34 +833,35 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             rc = pp_csr_densify(ctx, dcsr, d_slots.as<int32_t>() + s0, nl, d_colmap.as<int32_t>(), d_dense.p, n_genes);
             if (rc) return rc;
             rc = pp_rank_launch(ctx, d_dense.p, x_dtype, n_genes, d_loc.as<int32_t>() + s0, nl, d_ident.as<int32_t>(),
-                                n_genes, (uint16_t *)s_rank + s0 * n_genes, n_genes, d_flags.as<int32_t>());
+                                n_genes, (uint16_t *)s_rank + s0 * n_genes, n_genes, d_flags);
             if (rc) return rc;
         }
         PP_CUDA(cudaStreamSynchronize(st));  // colmap / ident / loc are locals
-    } else {
-        rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
-                            (uint16_t *)s_rank, n_genes, d_flags.as<int32_t>());
+    } else if (n_slots > 0) {
+        rc = pp_rank_launch(ctx, dx_local, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
+                            (uint16_t *)s_rank, n_genes, d_flags);
         if (rc) return rc;
     }
-    int32_t flags[4];
-    PP_CUDA(cudaMemcpyAsync(flags, d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
-    PP_CUDA(cudaStreamSynchronize(st));
-    if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
-    const int B = std::max(1, bit_length64((uint64_t)flags[0]));
-    ctx->tm.n_planes = B;
-
-    // ---- planes every gene needs; gene positions sorted by it (widest first, so the expensive tiles start first)
-    DevBuf d_orbits;
-    PP_CUDA(d_orbits.alloc(sizeof(uint32_t) * n_genes, st));
-    PP_CUDA(cudaMemsetAsync(d_orbits.p, 0, sizeof(uint32_t) * n_genes, st));
-    {
+    // ---- planes every gene needs: bit_length(OR of its ranks) -- the max over the data ranks of their ORs has the same
+    //      bit length as the OR over all cells
+    if (n_slots > 0) {
         dim3 grid((unsigned)((n_genes + 255) / 256), (unsigned)std::min<int64_t>(std::max<int64_t>(n_slots / 128, 1), 128));
-        col_or_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_slots, (int)n_genes, d_orbits.as<uint32_t>());
+        col_or_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_slots, (int)n_genes, d_orbits);
         PP_CHECK_LAUNCH();
     }
-    std::vector<uint32_t> orbits((size_t)n_genes);
-    PP_CUDA(cudaMemcpyAsync(orbits.data(), d_orbits.p, sizeof(uint32_t) * n_genes, cudaMemcpyDeviceToHost, st));
+    if (wd > 1) {
+        rc = pp_allreduce_max(ctx, d_red.p, 4 + (size_t)n_genes, ppn::ncclUint32);
+        if (rc) return rc;
+    }
+    std::vector<uint32_t> red(4 + (size_t)n_genes);
+    PP_CUDA(cudaMemcpyAsync(red.data(), d_red.p, sizeof(uint32_t) * red.size(), cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaStreamSynchronize(st));
+    if (red[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
+    const int B = std::max(1, bit_length64((uint64_t)red[0]));
+    ctx->tm.n_planes = B;
+    const uint32_t *orbits = red.data() + 4;
+
+    // gene positions sorted by the planes they need (widest first, so the expensive tiles start first)
     std::vector<int32_t> pos_gene((size_t)n_genes), gene_pos((size_t)n_genes);
     {
         std::vector<int32_t> start(MAX_PLANES + 2, 0);  // counting sort by descending plane count, stable
@@ -805,18 +875,21 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     std::vector<int32_t> blk_bits((size_t)NB_alloc, 1);
     std::vector<int64_t> blk_off((size_t)NB_alloc, 0);
-    size_t plane_words = 0;
+    size_t plane_words = 0;  // words of ONE region
     for (int nb = 0; nb < NB_alloc; ++nb) {
         int bn = 1;
         for (int64_t p = (int64_t)nb * 64; p < std::min<int64_t>((int64_t)nb * 64 + 64, n_genes); ++p)
             bn = std::max(bn, bit_length64(orbits[pos_gene[p]]));
         blk_bits[nb] = bn;
         blk_off[nb] = (int64_t)plane_words;
-        plane_words += (size_t)(2 * bn - 1) * W * 64;  // bn low planes + suffix planes S_1 .. S_{bn-1}
+        plane_words += (size_t)(2 * bn - 1) * Wl * 64;  // bn low planes + suffix planes S_1 .. S_{bn-1}
     }
     const size_t zero_words = (size_t)words_per_chunk(1) * 64;
-    if (!(s_planes = pp_slab(ctx, SLAB_PLANES, (plane_words + zero_words) * 4))) return PP_ENOMEM;
-    PP_CUDA(cudaMemsetAsync(s_planes, 0, (plane_words + zero_words) * 4, st));
+    if (!(s_planes = pp_slab(ctx, SLAB_PLANES, ((size_t)wd * plane_words + zero_words) * 4))) return PP_ENOMEM;
+    uint32_t *my_region = (uint32_t *)s_planes + (size_t)me * plane_words;
+    uint32_t *zeros = (uint32_t *)s_planes + (size_t)wd * plane_words;
+    PP_CUDA(cudaMemsetAsync(my_region, 0, plane_words * 4, st));  // padding words of my region stay all-tie
+    PP_CUDA(cudaMemsetAsync(zeros, 0, zero_words * 4, st));
     DevBuf d_pos_gene, d_gene_pos, d_blk_bits, d_blk_off;
     PP_CUDA(d_pos_gene.alloc(sizeof(int32_t) * n_genes, st));
     PP_CUDA(cudaMemcpyAsync(d_pos_gene.p, pos_gene.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
@@ -825,12 +898,16 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(d_blk_off.alloc(sizeof(int64_t) * NB_alloc, st));
     PP_CUDA(cudaMemcpyAsync(d_blk_off.p, blk_off.data(), sizeof(int64_t) * NB_alloc, cudaMemcpyHostToDevice, st));
 
-    // ---- bit-slice
-    {
-        dim3 grid((unsigned)((n_genes + 255) / 256), (unsigned)std::min(W, 32768));
-        bitslice_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_genes, (int)n_genes, W, d_pos_gene.as<int32_t>(),
-                                              d_blk_off.as<int64_t>(), d_blk_bits.as<int32_t>(), (uint32_t *)s_planes);
+    // ---- bit-slice my cells into my region; the other regions arrive with one all-gather over NVLink
+    if (W_me > 0) {
+        dim3 grid((unsigned)((n_genes + 255) / 256), (unsigned)std::min(W_me, 32768));
+        bitslice_kernel<<<grid, 256, 0, st>>>((uint16_t *)s_rank, n_genes, (int)n_genes, W_me, Wl, d_pos_gene.as<int32_t>(),
+                                              d_blk_off.as<int64_t>(), d_blk_bits.as<int32_t>(), my_region);
         PP_CHECK_LAUNCH();
+    }
+    if (wd > 1) {
+        rc = pp_allgather_bytes(ctx, my_region, s_planes, plane_words * 4);
+        if (rc) return rc;
     }
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
 
@@ -870,24 +947,29 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     ctx->tm.n_units = n_pairs_shard;
     ctx->tm.avg_planes = n_pairs_shard > 0 ? (float)(plane_pairs / (double)n_pairs_shard) : 0.f;
 
-    // ---- chunks (runs of <= words_per_chunk(bp) words inside one class), one table per plane count in use;
-    //      table 0 (one chunk per class) serves the probe kernel
+    // ---- chunks: for every class, region after region, runs of <= words_per_chunk(bp) words of that class; one
+    //      table per plane count in use; table 0 (one chunk per piece) serves the probe kernel
     std::vector<Chunk> chunks;
     PairParams P;
     for (int bp = 0; bp <= MAX_PLANES; ++bp) {
         P.chunk_off[bp] = (int32_t)chunks.size();
         P.chunk_cnt[bp] = 0;
         if (bp > 0 && !bp_used[bp]) continue;
-        const int wc = bp == 0 ? W : words_per_chunk(bp);
-        for (int k = 0; k < n_classes; ++k)
-            for (int w = class_w0[k]; w < class_w0[k + 1]; w += wc) {
-                Chunk c;
-                c.w_begin = w;
-                c.n_words = std::min(wc, class_w0[k + 1] - w);
-                c.class_end = (w + c.n_words == class_w0[k + 1]) ? k : -1;
-                c.pad = 0;
-                chunks.push_back(c);
+        const int wc = bp == 0 ? Wl : words_per_chunk(bp);
+        for (int k = 0; k < n_classes; ++k) {
+            for (int q = 0; q < wd; ++q) {
+                const int w0 = piece_w0[(size_t)q * n_classes + k], w1 = w0 + piece_w[(size_t)q * n_classes + k];
+                for (int w = w0; w < w1; w += wc) {
+                    Chunk c;
+                    c.w_begin = w;
+                    c.n_words = std::min(wc, w1 - w);
+                    c.class_end = -1;
+                    c.owner = q;
+                    chunks.push_back(c);
+                }
             }
+            chunks.back().class_end = k;  // classes are non-empty: the last chunk pushed belongs to class k
+        }
         P.chunk_cnt[bp] = (int32_t)chunks.size() - P.chunk_off[bp];
     }
     const size_t dyn_smem = (size_t)STAGES * (A_BLOCKS + 1) * STAGE_PLANE_WORDS * 64 * 4;
@@ -906,7 +988,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     DevBuf d_mpd;
     PP_CUDA(d_mpd.alloc(sizeof(int32_t) * n_classes, st));
     PP_CUDA(cudaMemcpyAsync(d_mpd.p, mpd32.data(), sizeof(int32_t) * n_classes, cudaMemcpyHostToDevice, st));
-    PP_CUDA(d_cnt.alloc(sizeof(unsigned long long), st));
+    PP_CUDA(d_cnt.alloc(sizeof(unsigned long long) * ((size_t)wd + 1), st));  // [0] my count, [1 ..] all ranks' counts
 
     unsigned long long cap = (unsigned long long)std::min<int64_t>(std::max<int64_t>(n_pairs_shard, 1),
                                                                      std::max<int64_t>(1 << 22, n_pairs_shard / 16));
@@ -917,7 +999,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(cudaMemsetAsync(d_cnt.p, 0, sizeof(unsigned long long), st));
         if (!tiles.empty()) {
             P.planes = (uint32_t *)s_planes;
-            P.zeros = (uint32_t *)s_planes + plane_words;
+            P.zeros = zeros;
             P.blk_off = d_blk_off.as<int64_t>();
             P.blk_bits = d_blk_bits.as<int32_t>();
             P.pos_gene = d_pos_gene.as<int32_t>();
@@ -928,8 +1010,9 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             P.out = (unsigned long long *)s_out;
             P.out_count = d_cnt.as<unsigned long long>();
             P.out_cap = cap;
+            P.rank_stride = (int64_t)plane_words;
             P.n_genes = (int)n_genes;
-            P.n_words = W;
+            P.n_words = Wl;
             P.n_classes = n_classes;
             pair_kernel<<<(unsigned)tiles.size(), PAIR_THREADS + 32, dyn_smem, st>>>(P);
             PP_CHECK_LAUNCH();
@@ -943,7 +1026,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         cap = count;  // exact size known now; evaluate once more
     }
 
-    // ---- optional probe counters
+    // ---- optional probe counters (the planes are complete on every rank)
     if (n_probe > 0 && probe_pairs && probe_pos && probe_neg) {
         for (int64_t q = 0; q < n_probe; ++q)
             if (probe_pairs[2 * q] < 0 || probe_pairs[2 * q + 1] >= n_genes || probe_pairs[2 * q] >= probe_pairs[2 * q + 1])
@@ -958,12 +1041,50 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(cudaMemcpyAsync(d_gene_pos.p, gene_pos.data(), sizeof(int32_t) * n_genes, cudaMemcpyHostToDevice, st));
         probe_kernel<<<(unsigned)((n_probe + 3) / 4), 128, 0, st>>>(
             (uint32_t *)s_planes, d_blk_off.as<int64_t>(), d_blk_bits.as<int32_t>(), d_gene_pos.as<int32_t>(),
-            d_chunks.as<Chunk>() + P.chunk_off[0], P.chunk_cnt[0], W, n_classes, d_pp.as<int64_t>(), n_probe,
-            d_pos.as<int32_t>(), d_neg.as<int32_t>());
+            d_chunks.as<Chunk>() + P.chunk_off[0], P.chunk_cnt[0], Wl, (int64_t)plane_words, n_classes, d_pp.as<int64_t>(),
+            n_probe, d_pos.as<int32_t>(), d_neg.as<int32_t>());
         PP_CHECK_LAUNCH();
         PP_CUDA(cudaMemcpyAsync(probe_pos, d_pos.p, cb, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaMemcpyAsync(probe_neg, d_neg.p, cb, cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // ---- several ranks: all-gather the compacted keys (counts first, then the lists padded to the longest)
+    unsigned long long *d_keys = (unsigned long long *)s_out;  // unsorted keys to sort, `count` of them
+    if (wd > 1) {
+        unsigned long long *d_counts = d_cnt.as<unsigned long long>() + 1;
+        rc = pp_allgather_bytes(ctx, d_cnt.p, d_counts, sizeof(unsigned long long));
+        if (rc) return rc;
+        std::vector<unsigned long long> counts((size_t)wd);
+        PP_CUDA(cudaMemcpyAsync(counts.data(), d_counts, sizeof(unsigned long long) * wd, cudaMemcpyDeviceToHost, st));
+        PP_CUDA(cudaStreamSynchronize(st));
+        unsigned long long maxc = 0, all = 0;
+        for (int q = 0; q < wd; ++q) {
+            maxc = std::max(maxc, counts[q]);
+            all += counts[q];
+        }
+        if (all > 0) {
+            if (!(s_out2 = pp_slab(ctx, SLAB_OUT2, sizeof(unsigned long long) * std::max<unsigned long long>(maxc * wd, all))))
+                return PP_ENOMEM;
+            unsigned long long *gbuf = (unsigned long long *)s_out2;
+            if (count) PP_CUDA(cudaMemcpyAsync(gbuf + (size_t)me * maxc, s_out, sizeof(unsigned long long) * count, cudaMemcpyDeviceToDevice, st));
+            rc = pp_allgather_bytes(ctx, gbuf + (size_t)me * maxc, gbuf, sizeof(unsigned long long) * maxc);
+            if (rc) return rc;
+            // pack the lists back to back in the compaction slab (grown if the merged list is longer than `cap`;
+            // pp_slab drains the stream before it re-allocates, and my keys already sit in gbuf)
+            if (receive) {
+                if (!(s_out = pp_slab(ctx, SLAB_OUT, sizeof(unsigned long long) * all))) return PP_ENOMEM;
+                unsigned long long off = 0;
+                for (int q = 0; q < wd; ++q) {
+                    if (counts[q])
+                        PP_CUDA(cudaMemcpyAsync((unsigned long long *)s_out + off, gbuf + (size_t)q * maxc,
+                                                sizeof(unsigned long long) * counts[q], cudaMemcpyDeviceToDevice, st));
+                    off += counts[q];
+                }
+            }
+        }
+        d_keys = (unsigned long long *)s_out;
+        count = receive ? all : 0;
     }
 
     // ---- sort into np.where order and return
@@ -973,8 +1094,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         if (!(s_out2 = pp_slab(ctx, SLAB_OUT2, sizeof(unsigned long long) * count))) return PP_ENOMEM;
         unsigned long long *sorted = nullptr;
         const int hi_bit = 16 + bit_length64((uint64_t)n_genes * (uint64_t)n_genes);
-        rc = radix_sort_u64(ctx, (unsigned long long *)s_out, (unsigned long long *)s_out2, (int64_t)count, 16,
-                            hi_bit, &sorted);
+        rc = radix_sort_u64(ctx, d_keys, (unsigned long long *)s_out2, (int64_t)count, 16, hi_bit, &sorted);
         if (rc) return rc;
         hk = (uint64_t *)malloc(sizeof(uint64_t) * count);
         hc = (int32_t *)malloc(sizeof(int32_t) * count);
@@ -1036,7 +1156,7 @@ PP_API int pp_sandbag(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, 
                       int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
     PP_GUARD(ctx, sandbag_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, cell_rows, n_cells, class_sizes,
-                               n_classes, gene_cols, n_genes, thresholds, shard, n_shards, out_keys, out_class, out_n,
+                               n_classes, gene_cols, n_genes, thresholds, shard, n_shards, false, -1, out_keys, out_class, out_n,
                                probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed, out_kept_genes, out_n_kept));
 }
 
@@ -1049,6 +1169,31 @@ PP_API int pp_sandbag_csr(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t 
     if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag_csr: NULL argument");
     PP_GUARD(ctx, sandbag_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
                                cell_rows, n_cells, class_sizes, n_classes, gene_cols, n_genes, thresholds, shard,
-                               n_shards, out_keys, out_class, out_n, probe_pairs, n_probe, probe_pos, probe_neg,
+                               n_shards, false, -1, out_keys, out_class, out_n, probe_pairs, n_probe, probe_pos, probe_neg,
+                               drop_unexpressed, out_kept_genes, out_n_kept));
+}
+
+PP_API int pp_sandbag_dist(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int64_t n_rows, int64_t n_cols,
+                           int64_t ld, const int32_t *cell_rows, int64_t n_cells, const int64_t *class_sizes,
+                           int32_t n_classes, const int32_t *gene_cols, int64_t n_genes, const int64_t *thresholds,
+                           int32_t gather_to, uint64_t **out_keys, int32_t **out_class, int64_t *out_n,
+                           const int64_t *probe_pairs, int64_t n_probe, int32_t *probe_pos, int32_t *probe_neg,
+                           int32_t drop_unexpressed, int32_t **out_kept_genes, int64_t *out_n_kept) {
+    if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag_dist: NULL argument");
+    PP_GUARD(ctx, sandbag_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, cell_rows, n_cells, class_sizes,
+                               n_classes, gene_cols, n_genes, thresholds, 0, 1, true, gather_to, out_keys, out_class, out_n,
+                               probe_pairs, n_probe, probe_pos, probe_neg, drop_unexpressed, out_kept_genes, out_n_kept));
+}
+
+PP_API int pp_sandbag_csr_dist(pp_ctx *ctx, const pp_csr *x, int64_t n_rows, int64_t n_cols, const int32_t *cell_rows,
+                               int64_t n_cells, const int64_t *class_sizes, int32_t n_classes, const int32_t *gene_cols,
+                               int64_t n_genes, const int64_t *thresholds, int32_t gather_to, uint64_t **out_keys,
+                               int32_t **out_class, int64_t *out_n, const int64_t *probe_pairs, int64_t n_probe,
+                               int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed,
+                               int32_t **out_kept_genes, int64_t *out_n_kept) {
+    if (ctx && !x) return pp_fail(ctx, PP_EINVAL, "pp_sandbag_csr_dist: NULL argument");
+    PP_GUARD(ctx, sandbag_impl(ctx, nullptr, x ? x->data_dtype : PP_F32, x ? x->is_device : 0, x, n_rows, n_cols, n_cols,
+                               cell_rows, n_cells, class_sizes, n_classes, gene_cols, n_genes, thresholds, 0, 1, true,
+                               gather_to, out_keys, out_class, out_n, probe_pairs, n_probe, probe_pos, probe_neg,
                                drop_unexpressed, out_kept_genes, out_n_kept));
 }

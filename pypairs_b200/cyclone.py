@@ -119,7 +119,7 @@ def _quantile_transform(raw, local_shard):
 
 
 def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterations=1000, min_iter=100,
-            min_pairs=50, quantile_transform=False, *, local_shard=False):
+            min_pairs=50, quantile_transform=False, *, local_shard=False, gather_to=None):
     """Score each sample for each category of marker pairs.
 
     Same signature, defaults and return value as pypairs.pairs.cyclone
@@ -129,16 +129,22 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
 
     `local_shard=True` (keyword-only extension, torch.distributed only): `data` holds just this
     rank's cells -- for matrices that do not fit one host -- and the frame covers all ranks' cells
-    in rank order.
+    in rank order (`sample_names` may name this rank's cells or, to skip the exchange of names, all cells).
+    `gather_to=r` (keyword-only extension): only rank r receives the scores and builds the frame, the
+    other ranks return None.
 
     `settings.rng` selects the permutation stream ('mt19937' = bit-exact with the reference,
-    'philox' = device-generated).  Under torch.distributed the cells are sharded over the ranks
-    and every rank returns the complete frame.
+    'philox' = device-generated).  Under torch.distributed the cells are sharded over the ranks, the score
+    columns are all-gathered on the device by the library (pp_cyclone_dist) and every rank returns the
+    complete frame.
     """
     logg.info("predicting category scores with cyclone", r=True)
     if marker_pairs is None:
         logg.hint("no marker pairs passed, using default cell cycle prediction marker")
         marker_pairs = datasets.default_cc_marker()
+    all_names = None
+    if local_shard and sample_names is not None and hasattr(data, "shape") and len(sample_names) != data.shape[0]:
+        all_names, sample_names = sample_names, range(data.shape[0])  # names of ALL ranks' cells: checked below
     raw, gene_names, sample_names = utils.parse_data(data, gene_names, sample_names)
     pairs, used = filter_marker_pairs(marker_pairs, gene_names)
     total = sum(len(p) for p in pairs.values())
@@ -157,20 +163,37 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
 
     keys = list(pairs.keys())
     rank, ws = _dist.world()
-    begin, end = (0, raw.shape[0]) if local_shard else _dist.cell_shard(raw.shape[0], rank, ws)
     rng = settings.rng if settings.fix_seed else "philox"
     seed = settings.seed if settings.fix_seed else int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
-    if ws > 1 and not settings.fix_seed:  # all shards must share one stream
-        seed = int(_dist.allgather_varlen((np.array([seed], dtype=np.uint64),))[0][0])
-    local, tm = _ffi.cyclone(raw, [np.where(used[k])[0] for k in keys], [pairs[k] for k in keys], iterations, min_iter,
-                             min_pairs, rng=rng, seed=seed, row_begin=begin, n_cells=end - begin)
-    if ws > 1 and local_shard:
-        scores = np.stack(_dist.allgather_varlen(tuple(local[c] for c in range(len(keys)))))
-        sample_names = _dist.allgather_names(sample_names)
-    elif ws > 1:
-        scores = _dist.allgather_columns(local, raw.shape[0])
+    used_idx, pair_idx = [np.where(used[k])[0] for k in keys], [pairs[k] for k in keys]
+    if ws > 1:
+        _dist.ensure_comm()
+        if not settings.fix_seed:  # all shards must share one stream
+            seed = int(_dist.broadcast_object(seed, 0))
+        if local_shard:
+            begin, end = 0, raw.shape[0]
+            shard_cells = _dist.allgather_counts(raw.shape[0])
+        else:
+            begin, end = _dist.cell_shard(raw.shape[0], rank, ws)
+            shard_cells = _dist.shard_sizes(raw.shape[0], ws)
+        scores, tm = _ffi.cyclone(raw, used_idx, pair_idx, iterations, min_iter, min_pairs, rng=rng, seed=seed,
+                                  row_begin=begin, n_cells=end - begin, shard_cells=shard_cells,
+                                  gather_to=-1 if gather_to is None else int(gather_to))
+        if all_names is not None:
+            if len(all_names) != int(shard_cells.sum()):
+                raise ValueError("{} sample names for {} local / {} total cells".format(
+                    len(all_names), raw.shape[0], int(shard_cells.sum())))
+            sample_names = all_names
+        elif local_shard:
+            sample_names = _dist.allgather_names(sample_names)
+        if scores is None:  # not the receiving rank
+            logg.info("finished", time_=True)
+            cyclone.last_timings = tm
+            return None
     else:
-        scores = local
+        if all_names is not None:
+            raise ValueError("{} sample names for {} cells".format(len(all_names), raw.shape[0]))
+        scores, tm = _ffi.cyclone(raw, used_idx, pair_idx, iterations, min_iter, min_pairs, rng=rng, seed=seed)
     df = scores_to_frame(scores, keys, sample_names)
     if utils.is_anndata(data):
         logg.hint('adding scores with key "pypairs_{category}" to `data.obs`"')

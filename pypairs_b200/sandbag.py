@@ -72,7 +72,7 @@ def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
 
 
 def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=0.65, filter_genes=None,
-            filter_samples=None, *, as_table=False):
+            filter_samples=None, *, as_table=False, gather_to=None):
     """Calculate the pairs of genes serving as marker pairs for each category.
 
     Same signature, defaults and return value as pypairs.pairs.sandbag
@@ -84,20 +84,27 @@ def sandbag(data, annotation=None, gene_names=None, sample_names=None, fraction=
     `as_table=True` (keyword-only extension) returns a `utils.MarkerTable` -- the same markers as index arrays,
     without building Python tuples (`.to_dict()` gives the dict); pairs.cyclone accepts it directly.
 
-    Under torch.distributed (one process per GPU) the gene-pair tiles are sharded over the ranks
-    and every rank returns the complete dict.
+    Under torch.distributed (one process per GPU) every rank passes the same arguments; the library splits the
+    prep over the cells and the gene-pair tiles over the ranks and merges the marker lists with NCCL
+    (pp_sandbag_dist).  Every rank returns the complete dict, or -- `gather_to=r` (keyword-only extension) -- only
+    rank r does and the others return None without building the Python result.
     """
     logg.info("identifying marker pairs with sandbag", r=True)
     logg.hint("sandbag running with fraction of {}".format(fraction))
     p = prepare(data, annotation, gene_names, sample_names, fraction, filter_genes, filter_samples)
     rank, ws = _dist.world()
-    keys, cls, tm, kept = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
-                                       shard=rank, n_shards=ws, drop_unexpressed=True)
     if ws > 1:
-        keys, cls = _dist.allgather_varlen((keys, cls))
-        order = np.argsort(keys, kind="stable")
-        keys, cls = keys[order], cls[order]
+        _dist.ensure_comm()
+        keys, cls, tm, kept = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
+                                           drop_unexpressed=True, dist=True,
+                                           gather_to=-1 if gather_to is None else int(gather_to))
+    else:
+        keys, cls, tm, kept = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
+                                           drop_unexpressed=True)
     sandbag.last_timings = tm
+    if ws > 1 and gather_to is not None and rank != int(gather_to):
+        logg.info("finished", time_=True)
+        return None
     if as_table:
         k64 = np.ascontiguousarray(keys).view(np.int64)
         n = max(len(kept), 1)
