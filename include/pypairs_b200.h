@@ -287,6 +287,18 @@ int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device, int6
                   int64_t n_genes, uint16_t *out_rank, int32_t *out_max_rank);
 
 /*
+ * pp_score_labels -- the label columns of the result frame (pypairs/tools/cyclone.py:172-181) from the score
+ * columns, one host pass (no device work, no ctx):
+ *   out_max_class[i] = first class with the largest score of cell i, NaN skipped (DataFrame.idxmax), or n_classes
+ *                      ("N/A") unless the NaN-skipping sum of the cell's scores is > 0 (cyclone.py:172-173);
+ *   out_cc[i]        (only when idx_g1 >= 0 and idx_g2m >= 0; cyclone.py:176-181) = 2 ("S") if max(G1, G2M) < 0.5,
+ *                      else 0 ("G1") / 1 ("G2M") = first maximum of the two; -1 if both are NaN.
+ * scores: double[n_classes, n_cells] as returned by pp_cyclone.
+ */
+int pp_score_labels(const double *scores, int32_t n_classes, int64_t n_cells, int32_t idx_g1, int32_t idx_g2m,
+                    int32_t *out_max_class, int32_t *out_cc);
+
+/*
  * pp_alu_peak -- roofline denominator for the bit-sliced / packed-integer kernels: measured
  * throughput of independent 32-bit LOP3 instructions on this device, in lane-operations per
  * second (threads x instructions / time), best of `repeats` launches.  Also returns the SM

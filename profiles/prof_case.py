@@ -1,7 +1,8 @@
 """Small, fixed workloads for ncu (launch list and --set full captures).
 
     python profiles/prof_case.py cyclone [cells]     default 9472 cells = one wave of 64-cell tiles on 148 SMs
-    python profiles/prof_case.py sandbag [genes] [cells]   default 6000 genes x 10000 cells
+    python profiles/prof_case.py sandbag [genes] [cells] [workload]   default 6000 genes x 10000 cells of bench.py's
+                                                                      "sandbag" workload (or sandbag_lognormal / sandbag_atlas)
 Each runs the hot path twice (first call = warm-up) with the matrix generated on the device.
 """
 import os
@@ -34,13 +35,15 @@ def main():
     else:
         g = int(sys.argv[2]) if len(sys.argv) > 2 else 6000
         n = int(sys.argv[3]) if len(sys.argv) > 3 else 10000
-        x, lab = bench.sandbag_matrix_device()
+        wl = sys.argv[4] if len(sys.argv) > 4 else "sandbag"
+        G, N, c, kind, seed = bench.SB_SHAPES[wl]
+        x, lab = bench.sandbag_matrix_device(G, N, c, kind, seed)
         x = x[:n, :g].contiguous()
         lab = lab[:n]
-        sizes = np.bincount(lab, minlength=3)
+        sizes = np.bincount(lab, minlength=c)
         thr = np.ceil(sizes * 0.65).astype(np.int64)
         order = np.argsort(lab, kind="stable")
-        for _ in range(2):
+        for _ in range(3):
             keys, cls, tm = _ffi.sandbag(x, order, sizes, np.arange(g), thr)
         print("sandbag", g, "genes x", n, "cells:", len(keys), "markers", tm)
 

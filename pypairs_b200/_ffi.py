@@ -21,7 +21,7 @@ SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "
            "pp_get_timings", "pp_sandbag", "pp_sandbag_csr", "pp_cyclone", "pp_cyclone_csr", "pp_phase_scores",
            "pp_perm_table", "pp_dense_rank", "pp_alu_peak", "pp_nccl_load", "pp_nccl_version", "pp_comm_unique_id",
            "pp_comm_init", "pp_comm_destroy", "pp_comm_info", "pp_sandbag_dist", "pp_sandbag_csr_dist",
-           "pp_cyclone_dist", "pp_cyclone_csr_dist"]
+           "pp_cyclone_dist", "pp_cyclone_csr_dist", "pp_score_labels"]
 
 
 class Csr(ctypes.Structure):
@@ -99,6 +99,7 @@ def load():
                                     i32, i32, u64, vp, vp, i32, i32, vp, vp, vp]
     lib.pp_cyclone_csr_dist.argtypes = [vp, c.POINTER(Csr), i64, i64, i64, i64, i32, vp, vp, vp, vp, i32, i32, i32, i32,
                                         u64, vp, vp, i32, i32, vp, vp, vp]
+    lib.pp_score_labels.argtypes = [vp, i32, i64, i32, i32, vp, vp]
     lib.pp_phase_scores.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, i32, i32, i32, vp, i64, vp, vp]
     lib.pp_perm_table.argtypes = [vp, i32, u64, i32, i32, i32, vp]
     lib.pp_dense_rank.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i64, vp, c.POINTER(i32)]
@@ -320,12 +321,11 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
     check(rc, h)
     n = on.value
     if n:
-        keys = np.ctypeslib.as_array(ctypes.cast(ok, ctypes.POINTER(ctypes.c_uint64)), shape=(n,)).copy()
-        cls = np.ctypeslib.as_array(ctypes.cast(oc, ctypes.POINTER(ctypes.c_int32)), shape=(n,)).copy()
+        keys, cls = _adopt(ok, np.uint64, n), _adopt(oc, np.int32, n)
     else:
         keys, cls = np.empty(0, dtype=np.uint64), np.empty(0, dtype=np.int32)
-    lib.pp_free(ok)
-    lib.pp_free(oc)
+        lib.pp_free(ok)
+        lib.pp_free(oc)
     del keep
     out = (keys, cls, timings(h))
     if probe_pairs is not None:
@@ -333,6 +333,28 @@ def sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=
     if drop_unexpressed:
         out = out + (kept if kept is not None else np.empty(0, dtype=np.int32),)
     return out
+
+
+def _adopt(ptr, dtype, n):
+    """ndarray over a result buffer the library malloc'ed for the caller, without copying it; pp_free runs when the
+    last array viewing the buffer goes away."""
+    import weakref
+    buf = (ctypes.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(ptr.value)
+    weakref.finalize(buf, load().pp_free, ctypes.c_void_p(ptr.value))
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+def score_labels(scores, idx_g1=-1, idx_g2m=-1):
+    """(max_class codes, cc codes or None) of pp_score_labels for float64[C, N] scores."""
+    lib = load()
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    nc, n = scores.shape
+    mc = np.empty(n, dtype=np.int32)
+    cc = np.empty(n, dtype=np.int32) if idx_g1 >= 0 and idx_g2m >= 0 else None
+    rc = lib.pp_score_labels(_ptr(scores), nc, n, idx_g1, idx_g2m, _ptr(mc), _ptr(cc))
+    if rc != 0:
+        raise PyPairsB200Error(rc, lib.pp_last_error(None).decode())
+    return mc, cc
 
 
 _RNG = {"mt19937": PP_RNG_MT19937, "philox": PP_RNG_PHILOX, "table": PP_RNG_TABLE}

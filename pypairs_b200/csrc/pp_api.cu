@@ -3,6 +3,8 @@
 
 #include <algorithm>
 
+#include <math.h>
+
 #include "pp_common.cuh"
 
 thread_local std::string g_pp_err;
@@ -104,6 +106,7 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
         if (ctx->slab[i]) cudaFree(ctx->slab[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->zc_stream) cudaStreamDestroy(ctx->zc_stream);
     delete ctx;
 }
 
@@ -150,7 +153,7 @@ PP_API int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_devic
     PP_CUDA(d_flags.alloc(sizeof(int32_t) * 4, st));
     PP_CUDA(cudaMemsetAsync(d_flags.p, 0, sizeof(int32_t) * 4, st));
     int rc = pp_rank_launch(ctx, dx, x_dtype, ld, d_rows.as<int32_t>(), n_cells, d_cols.as<int32_t>(), n_genes,
-                            d_rank.as<uint16_t>(), n_genes, d_flags.as<int32_t>());
+                            d_rank.as<uint16_t>(), n_genes, d_flags.as<int32_t>(), gene_cols);
     if (rc) return rc;
     int32_t flags[4];
     PP_CUDA(cudaMemcpyAsync(out_rank, d_rank.p, sizeof(uint16_t) * n_cells * n_genes, cudaMemcpyDeviceToHost, st));
@@ -158,6 +161,35 @@ PP_API int pp_dense_rank(pp_ctx *ctx, const void *x, int x_dtype, int x_is_devic
     PP_CUDA(cudaStreamSynchronize(st));
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_dense_rank: NaN in the expression matrix");
     if (out_max_rank) *out_max_rank = flags[0];
+    return PP_OK;
+}
+
+// ---- label columns of the result frame (host only) -----------------------------------------------
+PP_API int pp_score_labels(const double *scores, int32_t n_classes, int64_t n_cells, int32_t idx_g1, int32_t idx_g2m,
+                           int32_t *out_max_class, int32_t *out_cc) {
+    if (!scores || !out_max_class || n_classes < 0 || n_cells < 0) return pp_fail(nullptr, PP_EINVAL, "pp_score_labels: bad argument");
+    const bool cc = idx_g1 >= 0 && idx_g2m >= 0 && out_cc;
+    if (cc && (idx_g1 >= n_classes || idx_g2m >= n_classes)) return pp_fail(nullptr, PP_EINVAL, "pp_score_labels: class index out of range");
+    for (int64_t i = 0; i < n_cells; ++i) {
+        int arg = 0;
+        double best = -INFINITY, sum = 0.0;
+        for (int k = 0; k < n_classes; ++k) {
+            const double v = scores[(int64_t)k * n_cells + i];
+            if (v != v) continue;  // NaN is skipped by idxmax and by sum
+            sum += v;
+            if (v > best) {
+                best = v;
+                arg = k;
+            }
+        }
+        out_max_class[i] = sum > 0.0 ? arg : n_classes;
+        if (cc) {
+            const double a = scores[(int64_t)idx_g1 * n_cells + i], b = scores[(int64_t)idx_g2m * n_cells + i];
+            const double sa = a != a ? -INFINITY : a, sb = b != b ? -INFINITY : b;
+            const double mx = sa > sb ? sa : sb;
+            out_cc[i] = (mx == -INFINITY && (a != a) && (b != b)) ? -1 : mx < 0.5 ? 2 : (sb > sa ? 1 : 0);
+        }
+    }
     return PP_OK;
 }
 

@@ -32,6 +32,7 @@ struct pp_ctx {
     int smem_optin = 0;
     cudaStream_t stream = nullptr;   // compute stream
     cudaStream_t copy_stream = nullptr;  // H2D prefetch stream
+    cudaStream_t zc_stream = nullptr;    // zero-copy gather lane of pp_cyclone (created on first use)
     cudaEvent_t ev[8] = {};
     void *pin[2] = {nullptr, nullptr};  // pinned staging buffers of the host-gather path (grown on demand)
     size_t pin_bytes = 0;
@@ -39,7 +40,7 @@ struct pp_ctx {
     size_t pin_out_bytes = 0;
     // grow-only device slabs for the few large buffers of a call (matrix copy, rank matrix, bit planes, ...): calls
     // are synchronous, so the same slab is safely re-used by the next call and the allocator is out of the timed path
-    static constexpr int N_SLABS = 10;
+    static constexpr int N_SLABS = 12;
     void *slab[N_SLABS] = {};
     size_t slab_bytes[N_SLABS] = {};
     std::string err;
@@ -54,7 +55,7 @@ extern thread_local std::string g_pp_err;  // errors raised without a ctx
 int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...);
 // pointer to at least `bytes` of device memory in slab `slot` (contents undefined); nullptr + error on failure
 void *pp_slab(pp_ctx *ctx, int slot, size_t bytes);
-enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, SLAB_CHUNK0 = 5, SLAB_CHUNK1 = 6, SLAB_MISC = 7, SLAB_SORT = 8 };
+enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, SLAB_CHUNK0 = 5, SLAB_CHUNK1 = 6, SLAB_MISC = 7, SLAB_SORT = 8, SLAB_ZC0 = 9, SLAB_ZC1 = 10 };
 
 #define PP_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -191,4 +192,6 @@ int pp_allgather_bytes(pp_ctx *ctx, const void *d_send, void *d_recv, size_t byt
 // rank[s * rank_ld + g] = dense rank of x[cell_rows[s], gene_cols[g]] among that cell's kept genes.
 int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const int32_t *d_cell_rows,
                    int64_t n_slots, const int32_t *d_gene_cols, int64_t n_genes, uint16_t *d_rank,
-                   int64_t rank_ld, int32_t *d_flags /* [0]=max rank (atomicMax), [1]=NaN seen */);
+                   int64_t rank_ld, int32_t *d_flags /* [0]=max rank (atomicMax), [1]=NaN seen */,
+                   const int32_t *h_gene_cols = nullptr /* host copy of gene_cols: lets the launcher pick the streaming
+                                                           kernel when the columns are ascending and dense */);

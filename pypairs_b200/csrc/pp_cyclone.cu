@@ -792,6 +792,35 @@ void gather_rows(const T *x, int64_t ld, int64_t r0, int64_t nr, const int32_t *
     crew.run(work);
 }
 
+// Zero-copy lane: the marker columns of rows [r0, r0 + nr) of a MAPPED host matrix -> dense [nr, n_kept] device buffer.
+// One warp per row, eight loads in flight per lane; every load is a 32-byte sector read over PCIe, so the kernel is
+// bound by the link's small-read rate, not by the SMs (it runs beside the score kernel's persistent CTAs).
+constexpr int ZC_WARPS = 8;
+template <typename T>
+__global__ void __launch_bounds__(ZC_WARPS * 32)
+zc_gather_kernel(const T *__restrict__ x, int64_t ld, int64_t r0, int64_t nr, const int32_t *__restrict__ cols, int n_kept,
+                 T *__restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * ZC_WARPS + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * ZC_WARPS;
+    for (int64_t r = warp; r < nr; r += n_warps) {
+        const T *s = x + (r0 + r) * ld;
+        T *d = dst + r * n_kept;
+        for (int j0 = 0; j0 < n_kept; j0 += 32 * 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 32 + lane;
+                v[u] = j < n_kept ? __ldcs(s + __ldg(cols + j)) : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 32 + lane;
+                if (j < n_kept) d[j] = v[u];
+            }
+        }
+    }
+}
+
 int host_threads() {
     if (const char *e = getenv("PP_HOST_THREADS")) return std::max(1, atoi(e));
     unsigned hc = std::thread::hardware_concurrency();
@@ -947,11 +976,13 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             if (shard_cells[q] < 0) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: negative shard size");
     }
     const bool receive = !dist || gather_to < 0 || gather_to == ctx->comm_rank;
-    if ((!x && !csr) || !used_idx || !used_off || !pairs || !pair_off || (receive && !out_scores))
+    const bool empty_shard = dist && n_cells == 0 && n_rows == 0;  // a rank without cells still joins the collectives
+    if ((!x && !csr && !empty_shard) || !used_idx || !used_off || !pairs || !pair_off || (receive && !out_scores))
         return pp_fail(ctx, PP_EINVAL, "pp_cyclone: NULL argument");
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: x_dtype must be PP_F32/PP_F64");
-    if (n_rows <= 0 || n_cols <= 0 || (!csr && ld < n_cols)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad matrix shape");
-    if (csr) {
+    if (!empty_shard && (n_rows <= 0 || n_cols <= 0 || (!csr && ld < n_cols)))
+        return pp_fail(ctx, PP_EINVAL, "pp_cyclone: bad matrix shape");
+    if (csr && !empty_shard) {
         const int vrc = pp_csr_validate(ctx, csr, n_rows, n_cols, "pp_cyclone_csr");
         if (vrc) return vrc;
     }
@@ -1012,8 +1043,31 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
     // (measured: with 16 host threads the gather beats full-row copies 161 vs 195 ms on cfg2; with 8 threads per
     // rank, 4 ranks sharing the host, it loses 402 vs 349 ms -- so it needs >= 12 threads for this process)
-    const bool host_gather = !csr && !x_is_device && (int64_t)U * 4 <= n_cols && host_threads() >= 12;
-    const bool pipelined = !csr && !x_is_device && (n_cells > wave_cells || host_gather);
+    // A second way in for PINNED / registered host matrices: a gather kernel reads the marker columns straight from the
+    // mapped host memory (32-byte sectors over the GPU's own PCIe link: 1 133 sectors = 36 KB instead of 80 KB per cfg2
+    // row, no host core involved).  Alone it moves 0.9 cells/us (profiles/hostbench/zerocopy_probe.cu: 56 ms per 50k
+    // cells against 72 ms for the full rows by DMA); it runs BESIDE the host gather, chunks going to whichever lane has
+    // a free buffer.  With the zero-copy lane present the host gather is worth having from 4 threads on.
+    // PP_FEED = gather | zerocopy | copy forces one way (tests, experiments).
+    const bool narrow = !csr && !x_is_device && (int64_t)U * 4 <= n_cols;
+    const char *feed_env = getenv("PP_FEED");
+    const std::string feed = feed_env ? feed_env : "auto";
+    const uint8_t *xz = nullptr;  // device-side address of x0 when the matrix is mapped host memory
+    if (narrow && (feed == "auto" || feed == "zerocopy") && n_cells > 0) {
+        cudaPointerAttributes a0, a1;
+        const uint8_t *last = x0 + ((size_t)(n_cells - 1) * ld + (size_t)n_cols) * esz - 1;
+        if (cudaPointerGetAttributes(&a0, x0) == cudaSuccess && cudaPointerGetAttributes(&a1, last) == cudaSuccess &&
+            a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost && a0.devicePointer && a1.devicePointer &&
+            (const uint8_t *)a1.devicePointer - (const uint8_t *)a0.devicePointer == last - x0)
+            xz = (const uint8_t *)a0.devicePointer;
+        else
+            cudaGetLastError();
+    }
+    const bool zc_lane = xz != nullptr;
+    const bool host_gather = narrow && feed != "copy" && feed != "zerocopy" &&
+                             (feed == "gather" || host_threads() >= (zc_lane ? 4 : 12));
+    const bool compact = host_gather || zc_lane;  // the device chunk buffers hold [cells, U]
+    const bool pipelined = !csr && !x_is_device && (n_cells > wave_cells || compact);
     const int64_t chunk_cells = (pipelined || csr) ? std::min(wave_cells, n_cells) : n_cells;
     {
         std::vector<int32_t> rows(chunk_cells);
@@ -1329,13 +1383,14 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 for (cudaEvent_t e : ev) cudaEventDestroy(e);
             }
         } events;
-        void *buf[2] = {nullptr, nullptr};  // device chunk buffers (ctx slabs)
-        cudaEvent_t copied[2], freed[2], ev_c0, ev_c1;
+        void *buf[2] = {nullptr, nullptr}, *zbuf[2] = {nullptr, nullptr};  // device chunk buffers of the two lanes (ctx slabs)
+        cudaEvent_t copied[2], freed[2], zready[2], zfreed[2], ev_c0, ev_c1;
         std::vector<cudaEvent_t> ev_s;
         DevBuf d_ident;
         const int n_thr = host_threads();
         HostCrew crew(host_gather ? n_thr : 1);
-        const int64_t dev_ld = host_gather ? U : ld;  // row length of the device chunk buffers
+        const bool dma_lane = host_gather || !zc_lane;  // staged / direct copies by the DMA engine
+        const int64_t dev_ld = compact ? U : ld;        // row length of the device chunk buffers
         const int32_t *dev_cols = d_uni.as<int32_t>();
         cudaStream_t cs = ctx->copy_stream;
         if (host_gather) {
@@ -1349,6 +1404,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 for (int b = 0; b < 2; ++b) PP_CUDA(cudaHostAlloc(&ctx->pin[b], need, cudaHostAllocDefault));
                 ctx->pin_bytes = need;
             }
+        }
+        if (compact) {
             std::vector<int32_t> ident(U);
             for (int j = 0; j < U; ++j) ident[j] = j;
             PP_CUDA(d_ident.alloc(sizeof(int32_t) * U, st));
@@ -1357,45 +1414,81 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             dev_cols = d_ident.as<int32_t>();
         }
         for (int b = 0; b < 2; ++b) {
-            if (!(buf[b] = pp_slab(ctx, b == 0 ? SLAB_CHUNK0 : SLAB_CHUNK1, (size_t)chunk_cells * dev_ld * esz)))
-                return PP_ENOMEM;
-            PP_CUDA(events.make(&copied[b], cudaEventDisableTiming));
-            PP_CUDA(events.make(&freed[b], cudaEventDisableTiming));
+            if (dma_lane) {
+                if (!(buf[b] = pp_slab(ctx, b == 0 ? SLAB_CHUNK0 : SLAB_CHUNK1, (size_t)chunk_cells * dev_ld * esz)))
+                    return PP_ENOMEM;
+                PP_CUDA(events.make(&copied[b], cudaEventDisableTiming));
+                PP_CUDA(events.make(&freed[b], cudaEventDisableTiming));
+            }
+            if (zc_lane) {
+                if (!(zbuf[b] = pp_slab(ctx, b == 0 ? SLAB_ZC0 : SLAB_ZC1, (size_t)chunk_cells * U * esz))) return PP_ENOMEM;
+                PP_CUDA(events.make(&zready[b], cudaEventDisableTiming));
+                PP_CUDA(events.make(&zfreed[b], cudaEventDisableTiming));
+            }
         }
+        if (zc_lane && !ctx->zc_stream) PP_CUDA(cudaStreamCreateWithFlags(&ctx->zc_stream, cudaStreamNonBlocking));
+        cudaStream_t zs = ctx->zc_stream;
         PP_CUDA(events.make(&ev_c0, cudaEventDefault));
         PP_CUDA(events.make(&ev_c1, cudaEventDefault));
         PP_CUDA(cudaEventRecord(ctx->ev[3], st));
         PP_CUDA(cudaStreamWaitEvent(cs, ctx->ev[3], 0));  // buffers exist before the first copy
+        if (zc_lane) PP_CUDA(cudaStreamWaitEvent(zs, ctx->ev[3], 0));
         PP_CUDA(cudaEventRecord(ev_c0, cs));
-        int i = 0;
+        int i = 0, n_dma = 0, n_zc = 0;  // chunks so far: all, per lane
         double gather_host_ms = 0.0, wait_host_ms = 0.0;
+        int64_t zc_bytes = 0;  // useful bytes the zero-copy lane fetched (the sectors on the bus are ~6x that)
         // the first chunks are an eighth, a quarter and a half wave: the device starts after ~1 ms of host work, not ~5
         for (int64_t c0 = 0, nc = 0; c0 < n_cells; c0 += nc, ++i) {
-            const int b = i & 1;
             nc = i < 3 ? chunk_cells >> (3 - i) : chunk_cells;
             nc = std::min({(std::max<int64_t>(nc, 1) + 127) / 128 * 128, chunk_cells, n_cells - c0});
-            const void *src = x0 + (size_t)c0 * ld * esz;
-            if (host_gather) {
-                const double t_g0 = now_ms();
-                if (i >= 2) PP_CUDA(cudaEventSynchronize(copied[b]));  // H2D two chunks ago has drained pin[b]
-                const double t_g1 = now_ms();
+            // lane of this chunk: the zero-copy lane whenever one of its two buffers is free (the rank kernel that read it
+            // has finished) -- it costs the host nothing --, else the DMA lane, whose gather keeps this thread busy
+            bool use_zc = zc_lane && !dma_lane;
+            if (zc_lane && dma_lane && i > 0)
+                use_zc = n_zc < 2 || cudaEventQuery(zfreed[n_zc & 1]) == cudaSuccess;
+            const void *chunk_dev = nullptr;
+            if (use_zc) {
+                const int b = n_zc & 1;
+                if (n_zc >= 2) PP_CUDA(cudaStreamWaitEvent(zs, zfreed[b], 0));
+                const unsigned grid = (unsigned)std::min<int64_t>((nc + ZC_WARPS - 1) / ZC_WARPS, ctx->n_sm);
                 if (x_dtype == PP_F64)
-                    gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], crew);
+                    zc_gather_kernel<double><<<grid, ZC_WARPS * 32, 0, zs>>>((const double *)xz, ld, c0, nc, d_uni.as<int32_t>(), U, (double *)zbuf[b]);
                 else
-                    gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], crew);
-                src = ctx->pin[b];
-                wait_host_ms += t_g1 - t_g0;
-                gather_host_ms += now_ms() - t_g1;
+                    zc_gather_kernel<float><<<grid, ZC_WARPS * 32, 0, zs>>>((const float *)xz, ld, c0, nc, d_uni.as<int32_t>(), U, (float *)zbuf[b]);
+                PP_CHECK_LAUNCH();
+                PP_CUDA(cudaEventRecord(zready[b], zs));
+                PP_CUDA(cudaStreamWaitEvent(st, zready[b], 0));
+                chunk_dev = zbuf[b];
+                zc_bytes += (int64_t)((size_t)nc * U * esz);
+            } else {
+                const int b = n_dma & 1;
+                const void *src = x0 + (size_t)c0 * ld * esz;
+                if (host_gather) {
+                    const double t_g0 = now_ms();
+                    if (n_dma >= 2) PP_CUDA(cudaEventSynchronize(copied[b]));  // H2D two chunks ago has drained pin[b]
+                    const double t_g1 = now_ms();
+                    if (x_dtype == PP_F64)
+                        gather_rows<double>((const double *)x0, ld, c0, nc, uni.data(), U, (double *)ctx->pin[b], crew);
+                    else
+                        gather_rows<float>((const float *)x0, ld, c0, nc, uni.data(), U, (float *)ctx->pin[b], crew);
+                    src = ctx->pin[b];
+                    wait_host_ms += t_g1 - t_g0;
+                    gather_host_ms += now_ms() - t_g1;
+                }
+                if (n_dma >= 2) PP_CUDA(cudaStreamWaitEvent(cs, freed[b], 0));  // the rank kernel two chunks ago is done
+                PP_CUDA(cudaMemcpyAsync(buf[b], src, (size_t)nc * dev_ld * esz, cudaMemcpyHostToDevice, cs));
+                ctx->tm.h2d_bytes += (int64_t)((size_t)nc * dev_ld * esz);
+                PP_CUDA(cudaEventRecord(copied[b], cs));
+                PP_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
+                chunk_dev = buf[b];
             }
-            if (i >= 2) PP_CUDA(cudaStreamWaitEvent(cs, freed[b], 0));  // the rank kernel two chunks ago is done
-            PP_CUDA(cudaMemcpyAsync(buf[b], src, (size_t)nc * dev_ld * esz, cudaMemcpyHostToDevice, cs));
-            ctx->tm.h2d_bytes += (int64_t)((size_t)nc * dev_ld * esz);
-            PP_CUDA(cudaEventRecord(copied[b], cs));
-            PP_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
-            rc = pp_rank_launch(ctx, buf[b], x_dtype, dev_ld, d_rows.as<int32_t>(), nc, dev_cols, U,
+            rc = pp_rank_launch(ctx, chunk_dev, x_dtype, dev_ld, d_rows.as<int32_t>(), nc, dev_cols, U,
                                 (uint16_t *)s_rank + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
             if (rc) return rc;
-            PP_CUDA(cudaEventRecord(freed[b], st));
+            if (use_zc)
+                PP_CUDA(cudaEventRecord(zfreed[n_zc++ & 1], st));
+            else
+                PP_CUDA(cudaEventRecord(freed[n_dma++ & 1], st));
             cudaEvent_t e0, e1;
             PP_CUDA(events.make(&e0, cudaEventDefault));
             PP_CUDA(events.make(&e1, cudaEventDefault));
@@ -1409,10 +1502,12 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             PP_CHECK_LAUNCH();
             PP_CUDA(cudaEventRecord(e1, st));
         }
+        ctx->tm.h2d_bytes += zc_bytes;
         PP_CUDA(cudaEventRecord(ev_c1, cs));
         if (trace)
-            fprintf(stderr, "[pp_cyclone] %d chunks of %lld cells, %d host threads: gather %.1f ms, waiting for staging buffers %.1f ms\n",
-                    i, (long long)chunk_cells, n_thr, gather_host_ms, wait_host_ms);
+            fprintf(stderr, "[pp_cyclone] %d chunks of %lld cells (%d by DMA%s, %d by the zero-copy gather), %d host threads: gather %.1f ms, "
+                    "waiting for staging buffers %.1f ms\n", i, (long long)chunk_cells, n_dma, host_gather ? " after the host gather" : "",
+                    n_zc, n_thr, gather_host_ms, wait_host_ms);
         {
             cudaEvent_t e0, e1;
             PP_CUDA(events.make(&e0, cudaEventDefault));
@@ -1426,6 +1521,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         }
         PP_CUDA(cudaEventRecord(ctx->ev[4], st));
         PP_CUDA(cudaStreamSynchronize(cs));
+        if (zc_lane) PP_CUDA(cudaStreamSynchronize(zs));
         PP_CUDA(cudaStreamSynchronize(st));
         cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
         for (size_t j = 0; j + 1 < ev_s.size(); j += 2) {
@@ -1515,7 +1611,7 @@ PP_API int pp_cyclone_dist(pp_ctx *ctx, const void *x, int x_dtype, int x_is_dev
                            int32_t min_iter, int32_t min_pairs, int32_t rng_mode, uint64_t seed,
                            const int32_t *perm_tables, const int64_t *shard_cells, int32_t gather_to,
                            int32_t want_observed, double *out_scores, int32_t *out_obs_hits, int32_t *out_obs_total) {
-    if (ctx && (!x || !shard_cells)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: NULL argument");
+    if (ctx && ((!x && n_rows > 0) || !shard_cells)) return pp_fail(ctx, PP_EINVAL, "pp_cyclone_dist: NULL argument");
     PP_GUARD(ctx, cyclone_impl(ctx, x, x_dtype, x_is_device, nullptr, n_rows, n_cols, ld, row_begin, n_cells, n_classes,
                                used_idx, used_off, pairs, pair_off, iterations, min_iter, min_pairs, rng_mode, seed,
                                perm_tables, shard_cells, gather_to, want_observed != 0, want_observed != 0, out_scores,

@@ -78,7 +78,8 @@ template <typename T>
 __global__ void __launch_bounds__(RANK_THREADS)
 rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cell_rows, int64_t n_slots,
             const int32_t *__restrict__ gene_cols, int n, uint16_t *__restrict__ rank_out, int64_t rank_ld,
-            uint8_t *__restrict__ scratch, size_t scratch_per_cta, int32_t *__restrict__ flags) {
+            uint8_t *__restrict__ scratch, size_t scratch_per_cta, int32_t *__restrict__ flags,
+            const int32_t *__restrict__ todo, const int32_t *__restrict__ ctl) {
     typedef typename KeyOf<T>::type K;
     __shared__ RankSmem sm;
     extern __shared__ __align__(16) uint16_t vals[];  // [n] staged counts of the fast path
@@ -94,7 +95,12 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
     uint16_t *idxA = reinterpret_cast<uint16_t *>(keyB + n_al);
     uint16_t *idxB = idxA + n_al;
 
-    for (int64_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+    // ctl == NULL or ctl[0] == 0: every slot; else only the ctl[1] slots listed in `todo` (the cells the streaming
+    // kernel below could not rank on its count fast path)
+    const bool listed = ctl != nullptr && ctl[0] != 0;
+    const int64_t n_work = listed ? (int64_t)ctl[1] : n_slots;
+    for (int64_t wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int64_t slot = listed ? (int64_t)todo[wi] : wi;
         uint16_t *out = rank_out + slot * rank_ld;
         const int row = cell_rows[slot];
         if (row < 0) {  // padding cell: ties in every gene
@@ -377,39 +383,293 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Streaming form of the count fast path for DENSE column spans (sandbag: all / almost all genes of a row; the
+// compact [cells, U] matrices of the cyclone host pipeline; densified CSR chunks).
+//
+// The kernel above loads a row, then runs its shared-memory phases, then loads the next row: with ~3 CTAs per SM
+// only about a third of the bytes HBM needs in flight are in flight (1.66 TB/s on cfg3).  Here a producer warp streams
+// the rows of ALL cells of the CTA through a ring of 16 KB chunks with 1-D TMA bulk copies (cp.async.bulk +
+// mbarrier complete_tx), running ahead of the consumers by the depth of the ring -- across cell boundaries -- so the
+// loads of cell i+1 overlap the prefix / look-up / store phases of cell i.  Consumers: pass 1 per chunk (count test,
+// u16 staging, presence bitmap), then prefix popcount, then look-up with 16-byte stores of eight ranks.
+// Cells that are not small counts (any real value, NaN) are appended to a to-do list and ranked by rank_kernel
+// afterwards; a probe of a few cells decides up front whether the matrix is count-like at all.
+// ------------------------------------------------------------------------------------------------
+constexpr int STREAM_CHUNK = 16384;  // bytes per ring stage
+constexpr int STREAM_MAX_STAGES = 8;
+
+struct alignas(16) StreamSmem {
+    uint32_t bitmap[BM_WORDS];
+    uint32_t bm_prefix[BM_WORDS];
+    uint32_t wtot[32];
+    uint64_t full[STREAM_MAX_STAGES], empty[STREAM_MAX_STAGES];
+    int bad[2];
+};
+
+__device__ __forceinline__ void cons_sync(int n_cons) { asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory"); }
+
+template <typename T>
+__global__ void probe_counts_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cell_rows,
+                                    int64_t n_slots, const int32_t *__restrict__ gene_cols, int n, int32_t *__restrict__ ctl) {
+    const int64_t slot = (int64_t)blockIdx.x * n_slots / gridDim.x;
+    const int row = cell_rows[slot];
+    if (row < 0) return;
+    bool ok = true;
+    for (int g = threadIdx.x; g < min(n, 2048); g += blockDim.x) ok = ok && is_small_count(x[(int64_t)row * ld + gene_cols[g]]);
+    if (!ok) ctl[0] = 0;
+}
+
+__global__ void build_inv_kernel(const int32_t *__restrict__ gene_cols, int n, int c_min, int32_t *__restrict__ inv) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) inv[gene_cols[g] - c_min] = g;
+}
+
+template <typename T, int NCONS>
+__global__ void __launch_bounds__(NCONS + 32, NCONS == 512 ? 2 : 1)
+rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cell_rows, int64_t n_slots, int n,
+                   int c_min, int span, const int32_t *__restrict__ inv, int n_stages, uint16_t *__restrict__ rank_out,
+                   int64_t rank_ld, int32_t *__restrict__ flags, int32_t *__restrict__ todo, int32_t *__restrict__ ctl) {
+    constexpr int CHE = STREAM_CHUNK / (int)sizeof(T);  // elements per chunk
+    constexpr int PFX = 512, WPT = BM_WORDS / PFX;      // the prefix pass runs on the first 512 consumers, 4 words each
+    static_assert(NCONS % 32 == 0 && NCONS >= PFX && NCONS + 32 <= 1024, "consumer warps + one producer warp");
+    __shared__ StreamSmem sm;
+    extern __shared__ __align__(128) uint8_t dyn[];
+    uint8_t *ring = dyn;                                                           // [n_stages][STREAM_CHUNK]
+    uint16_t *vals = reinterpret_cast<uint16_t *>(dyn + (size_t)n_stages * STREAM_CHUNK);  // [n] staged counts
+    if (ctl[0] == 0) return;  // the probe found real-valued cells: rank_kernel takes everything
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], NCONS / 32);
+        }
+        sm.bad[0] = sm.bad[1] = 0;
+        fence_mbar_init();
+    }
+    for (int i = tid; i < BM_WORDS; i += NCONS + 32) sm.bitmap[i] = 0;
+    __syncthreads();
+    const uintptr_t xb = reinterpret_cast<uintptr_t>(x);
+
+    if (warp == NCONS / 32) {  // ---- producer warp: one lane issues the bulk copies of every chunk of every cell
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int64_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+                const int row = cell_rows[slot];
+                if (row < 0) continue;
+                const uintptr_t a = xb + ((uintptr_t)row * (uintptr_t)ld + (uintptr_t)c_min) * sizeof(T);
+                const uintptr_t a0 = a & ~(uintptr_t)15, e1 = (a + (uintptr_t)span * sizeof(T) + 15) & ~(uintptr_t)15;
+                for (uintptr_t off = 0; a0 + off < e1; off += STREAM_CHUNK, ++q) {
+                    const int s = (int)(q % (uint32_t)n_stages);
+                    const uint32_t use = q / (uint32_t)n_stages;
+                    if (use > 0) mbar_wait(&sm.empty[s], (use - 1) & 1);
+                    const uint32_t bytes = (uint32_t)min((uintptr_t)STREAM_CHUNK, e1 - a0 - off);
+                    mbar_arrive_expect_tx(&sm.full[s], bytes);
+                    bulk_g2s(ring + (size_t)s * STREAM_CHUNK, reinterpret_cast<const void *>(a0 + off), bytes, &sm.full[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers
+    uint32_t q = 0;
+    int par = 0;
+    for (int64_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
+        uint16_t *out = rank_out + slot * rank_ld;
+        const int row = cell_rows[slot];
+        if (row < 0) {  // padding cell: ties in every gene
+            for (int g = tid; g < n; g += NCONS) out[g] = 0;
+            continue;
+        }
+        const uintptr_t a = xb + ((uintptr_t)row * (uintptr_t)ld + (uintptr_t)c_min) * sizeof(T);
+        const uintptr_t a0 = a & ~(uintptr_t)15, e1 = (a + (uintptr_t)span * sizeof(T) + 15) & ~(uintptr_t)15;
+        const int shift = (int)((a - a0) / sizeof(T));  // elements of the first chunk before column c_min
+        bool small = true;
+        int col0 = -shift;  // column (relative to c_min) of element 0 of the chunk
+        for (uintptr_t off = 0; a0 + off < e1; off += STREAM_CHUNK, ++q, col0 += CHE) {
+            const int s = (int)(q % (uint32_t)n_stages);
+            mbar_wait(&sm.full[s], (q / (uint32_t)n_stages) & 1);
+            const T *src = reinterpret_cast<const T *>(ring + (size_t)s * STREAM_CHUNK);
+#pragma unroll 4
+            for (int e = tid; e < CHE; e += NCONS) {
+                const int col = col0 + e;
+                if (col >= 0 && col < span) {
+                    const int g = inv ? __ldg(inv + col) : col;
+                    if (g >= 0) {
+                        const T v = src[e];
+                        const bool ok = is_small_count(v);
+                        small = small && ok;
+                        const uint32_t u = ok ? (uint32_t)v : 0u;
+                        vals[g] = (uint16_t)u;
+                        const uint32_t bit = 1u << (u & 31);
+                        if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+        }
+        if (!small) sm.bad[par] = 1;
+        cons_sync(NCONS);  // bitmap, vals, bad complete
+        const bool bad = sm.bad[par] != 0;
+        if (tid == 0) sm.bad[par ^ 1] = 0;  // next cell's flag (nobody reads it before the next cons_sync)
+        par ^= 1;
+        if (!bad) {
+            // exclusive prefix popcount over the bitmap words: WPT words per thread, warp scan, warp totals
+            uint32_t c[WPT], t4 = 0, incl = 0;
+            if (tid < PFX) {
+#pragma unroll
+                for (int j = 0; j < WPT; ++j) { c[j] = __popc(sm.bitmap[tid * WPT + j]); t4 += c[j]; }
+                incl = t4;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (lane == 31) sm.wtot[warp] = incl;
+            }
+            cons_sync(NCONS);
+            if (tid < PFX) {
+                uint32_t base = 0;
+                for (int w = 0; w < warp; ++w) base += sm.wtot[w];
+                uint32_t run = base + incl - t4;
+#pragma unroll
+                for (int j = 0; j < WPT; ++j) { sm.bm_prefix[tid * WPT + j] = run; run += c[j]; }
+                if (tid == PFX - 1) atomicMax(&flags[0], (int)run - 1);  // distinct values - 1
+            }
+            cons_sync(NCONS);
+            // look-up: scalar head up to a 16-byte boundary of the output row, then eight ranks per 16-byte store
+            auto rank_of = [&](int g) -> uint32_t {
+                const uint32_t u = vals[g];
+                return sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & ((1u << (u & 31)) - 1u));
+            };
+            const int head = min(n, (int)(((16 - (reinterpret_cast<uintptr_t>(out) & 15)) & 15) >> 1));
+            if (tid < head) out[tid] = (uint16_t)rank_of(tid);
+            const int n_vec = (n - head) >> 3;
+            for (int v8 = tid; v8 < n_vec; v8 += NCONS) {
+                const int g = head + v8 * 8;
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[j] = rank_of(g + 2 * j) | (rank_of(g + 2 * j + 1) << 16);
+                *reinterpret_cast<uint4 *>(out + g) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            for (int g = head + n_vec * 8 + tid; g < n; g += NCONS) out[g] = (uint16_t)rank_of(g);
+        } else if (tid == 0) {
+            todo[atomicAdd(&ctl[1], 1)] = (int32_t)slot;
+        }
+        cons_sync(NCONS);  // everybody is done with bitmap / prefix / vals
+        for (int i = tid; i < BM_WORDS; i += NCONS) sm.bitmap[i] = 0;
+        cons_sync(NCONS);
+    }
+}
 }  // namespace
 
-int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const int32_t *d_cell_rows,
-                   int64_t n_slots, const int32_t *d_gene_cols, int64_t n_genes, uint16_t *d_rank,
-                   int64_t rank_ld, int32_t *d_flags) {
-    if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "more than 65535 kept genes per cell (%lld)", (long long)n_genes);
-    if (n_slots == 0 || n_genes == 0) return PP_OK;
-    const size_t ksz = (x_dtype == PP_F64) ? 8 : 4;
+// Launch configuration of the streaming kernel for rows of `span` columns holding n kept genes: consumers per CTA
+// (512 with two CTAs per SM when they fit, else 1024 with one), ring stages, dynamic shared memory.  ok = false: no fit.
+struct StreamCfg { bool ok; int n_cons, n_stages, grid_per_sm; size_t dyn; };
+static StreamCfg stream_config(pp_ctx *ctx, int64_t n) {
+    StreamCfg c = {false, 0, 0, 0, 0};
+    const size_t vals = ((size_t)n * 2 + 127) & ~(size_t)127;
+    const size_t stat = sizeof(StreamSmem);
+    const size_t sm_total = 228 * 1024, reserve = 1024;  // per SM; every resident CTA also reserves 1 KB
+    const size_t dyn_max1 = (size_t)ctx->smem_optin - stat, dyn_max2 = sm_total / 2 - reserve - stat;
+    if (vals + 3 * STREAM_CHUNK <= dyn_max2) {  // two CTAs of 512 consumers per SM, >= 3 stages each
+        c.n_cons = 512;
+        c.grid_per_sm = 2;
+        c.n_stages = (int)std::min<size_t>(STREAM_MAX_STAGES, (dyn_max2 - vals) / STREAM_CHUNK);
+    } else if (vals + 2 * STREAM_CHUNK <= dyn_max1) {  // one CTA of 960 consumers, as many stages as fit
+        c.n_cons = 960;
+        c.grid_per_sm = 1;
+        c.n_stages = (int)std::min<size_t>(STREAM_MAX_STAGES, (dyn_max1 - vals) / STREAM_CHUNK);
+    } else {
+        return c;
+    }
+    c.dyn = (size_t)c.n_stages * STREAM_CHUNK + vals;
+    c.ok = true;
+    return c;
+}
+
+template <typename T>
+static int rank_launch_typed(pp_ctx *ctx, const T *d_x, int64_t ld, const int32_t *d_cell_rows, int64_t n_slots,
+                             const int32_t *d_gene_cols, int64_t n_genes, uint16_t *d_rank, int64_t rank_ld,
+                             int32_t *d_flags, const int32_t *h_gene_cols) {
+    cudaStream_t st = ctx->stream;
+    // ---- streaming count path: ascending columns covering at least half of their span, rows of >= 8 KB, 16-byte
+    //      aligned matrix base (the bulk copies start at the 16-byte boundary below a row's first kept column)
+    DevBuf d_inv, d_todo, d_ctl;
+    const int32_t *todo = nullptr, *ctl = nullptr;
+    bool stream = h_gene_cols != nullptr && n_genes * (int64_t)sizeof(T) >= 8192 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
+    int c_min = 0, span = 0;
+    if (stream) {
+        for (int64_t g = 1; g < n_genes && stream; ++g) stream = h_gene_cols[g] > h_gene_cols[g - 1];
+        c_min = h_gene_cols[0];
+        span = h_gene_cols[n_genes - 1] - c_min + 1;
+        stream = stream && (int64_t)span <= 2 * n_genes;
+    }
+    const StreamCfg cfg = stream ? stream_config(ctx, n_genes) : StreamCfg{false, 0, 0, 0, 0};
+    if (stream && cfg.ok) {
+        PP_CUDA(d_ctl.alloc(sizeof(int32_t) * 2, st));
+        PP_CUDA(d_todo.alloc(sizeof(int32_t) * n_slots, st));
+        const int32_t init[2] = {1, 0};
+        PP_CUDA(cudaMemcpyAsync(d_ctl.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        probe_counts_kernel<T><<<(unsigned)std::min<int64_t>(n_slots, 64), 256, 0, st>>>(
+            d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_ctl.as<int32_t>());
+        PP_CHECK_LAUNCH();
+        const int32_t *inv = nullptr;
+        if ((int64_t)span != n_genes) {
+            PP_CUDA(d_inv.alloc(sizeof(int32_t) * (size_t)span, st));
+            PP_CUDA(cudaMemsetAsync(d_inv.p, 0xff, sizeof(int32_t) * (size_t)span, st));
+            build_inv_kernel<<<(unsigned)((n_genes + 255) / 256), 256, 0, st>>>(d_gene_cols, (int)n_genes, c_min, d_inv.as<int32_t>());
+            PP_CHECK_LAUNCH();
+            inv = d_inv.as<int32_t>();
+        }
+        const int grid = (int)std::min<int64_t>(n_slots, (int64_t)ctx->n_sm * cfg.grid_per_sm);
+        if (cfg.n_cons == 512) {
+            PP_CUDA(cudaFuncSetAttribute(rank_stream_kernel<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dyn));
+            rank_stream_kernel<T, 512><<<grid, 512 + 32, cfg.dyn, st>>>(d_x, ld, d_cell_rows, n_slots, (int)n_genes, c_min, span, inv,
+                                                                       cfg.n_stages, d_rank, rank_ld, d_flags,
+                                                                       d_todo.as<int32_t>(), d_ctl.as<int32_t>());
+        } else {
+            PP_CUDA(cudaFuncSetAttribute(rank_stream_kernel<T, 960>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dyn));
+            rank_stream_kernel<T, 960><<<grid, 960 + 32, cfg.dyn, st>>>(d_x, ld, d_cell_rows, n_slots, (int)n_genes, c_min, span,
+                                                                         inv, cfg.n_stages, d_rank, rank_ld, d_flags,
+                                                                         d_todo.as<int32_t>(), d_ctl.as<int32_t>());
+        }
+        PP_CHECK_LAUNCH();
+        todo = d_todo.as<int32_t>();
+        ctl = d_ctl.as<int32_t>();
+    }
+    // ---- general kernel: everything (no streaming pass), or the cells the streaming pass handed over
+    const size_t ksz = sizeof(T);
     const size_t n_al = ((size_t)n_genes + 15) & ~(size_t)15;
     const size_t per_cta = 2 * n_al * ksz + 2 * n_al * 2;
     const size_t dyn = ((size_t)n_genes * 2 + 15) & ~(size_t)15;
-    PP_CUDA(cudaFuncSetAttribute(rank_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    PP_CUDA(cudaFuncSetAttribute(rank_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    PP_CUDA(cudaFuncSetAttribute(rank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     // persistent CTAs: exactly as many as are resident at once (a partial second wave would idle half the SMs)
     int per_sm = 1;
-    if (x_dtype == PP_F64)
-        PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_kernel<double>, RANK_THREADS, dyn));
-    else
-        PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_kernel<float>, RANK_THREADS, dyn));
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_kernel<T>, RANK_THREADS, dyn));
     const int64_t resident = (int64_t)ctx->n_sm * std::max(per_sm, 1);
-    int grid = (int)std::min<int64_t>(n_slots, resident);
+    const int grid = (int)std::min<int64_t>(n_slots, resident);
     uint8_t *scratch = (uint8_t *)pp_slab(ctx, SLAB_SORT, per_cta * (size_t)grid);  // sort path only; stream-ordered reuse
     if (!scratch) return PP_ENOMEM;
-    if (x_dtype == PP_F64)
-        rank_kernel<double><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
-            (const double *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
-            scratch, per_cta, d_flags);
-    else
-        rank_kernel<float><<<grid, RANK_THREADS, dyn, ctx->stream>>>(
-            (const float *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
-            scratch, per_cta, d_flags);
+    rank_kernel<T><<<grid, RANK_THREADS, dyn, st>>>(d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
+                                                    scratch, per_cta, d_flags, todo, ctl);
     PP_CHECK_LAUNCH();
     return PP_OK;
+}
+
+int pp_rank_launch(pp_ctx *ctx, const void *d_x, int x_dtype, int64_t ld, const int32_t *d_cell_rows,
+                   int64_t n_slots, const int32_t *d_gene_cols, int64_t n_genes, uint16_t *d_rank,
+                   int64_t rank_ld, int32_t *d_flags, const int32_t *h_gene_cols) {
+    if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "more than 65535 kept genes per cell (%lld)", (long long)n_genes);
+    if (n_slots == 0 || n_genes == 0) return PP_OK;
+    if (x_dtype == PP_F64)
+        return rank_launch_typed<double>(ctx, (const double *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, n_genes, d_rank,
+                                         rank_ld, d_flags, h_gene_cols);
+    return rank_launch_typed<float>(ctx, (const float *)d_x, ld, d_cell_rows, n_slots, d_gene_cols, n_genes, d_rank, rank_ld,
+                                    d_flags, h_gene_cols);
 }
 
 // ------------------------------------------------------------------------------------------------

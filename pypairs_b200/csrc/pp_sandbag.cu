@@ -22,7 +22,10 @@
 // Thresholds (sandbag.py:184-190) are applied in-register at every class boundary and the
 // if/elif decision (:192-197) at the end; survivors are compacted with warp-aggregated
 // atomics and radix-sorted into the row-major order np.where would produce.
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -645,6 +648,16 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                         int32_t *probe_pos, int32_t *probe_neg, int32_t drop_unexpressed, int32_t **out_kept_genes,
                         int64_t *out_n_kept) {
     if (!ctx) return pp_fail(nullptr, PP_EINVAL, "ctx is NULL");
+    // PP_TRACE=1: host-side time line of the call on stderr (ms since entry at every mark)
+    const bool trace = getenv("PP_TRACE") != nullptr;
+    const auto t_entry = std::chrono::steady_clock::now();
+    std::string trace_line;
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s=%.3f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count());
+        trace_line += buf;
+    };
     if ((!x && !csr) || !cell_rows || !class_sizes || !gene_cols || !thresholds || !out_keys || !out_class || !out_n)
         return pp_fail(ctx, PP_EINVAL, "pp_sandbag: NULL argument");
     if (x_dtype != PP_F32 && x_dtype != PP_F64) return pp_fail(ctx, PP_EINVAL, "pp_sandbag: x_dtype must be PP_F32/PP_F64");
@@ -688,10 +701,17 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const bool receive = !dist || gather_to < 0 || gather_to == me;
     std::vector<int64_t> rb((size_t)wd + 1, 0);
     rb[wd] = n_rows;
-    if (wd > 1 && n_cells > 0) {
-        std::vector<int32_t> sorted(cell_rows, cell_rows + n_cells);
-        std::sort(sorted.begin(), sorted.end());
-        for (int q = 1; q < wd; ++q) rb[q] = sorted[(size_t)(n_cells * q / wd)];
+    if (wd > 1 && n_cells > 0) {  // rb[q] = row of the (n_cells * q / wd)-th kept cell in row order (counting, no sort)
+        std::vector<uint8_t> is_kept((size_t)n_rows, 0);
+        for (int64_t i = 0; i < n_cells; ++i) is_kept[(size_t)cell_rows[i]] = 1;
+        int64_t seen = 0;
+        int q = 1;
+        for (int64_t r = 0; r < n_rows && q < wd; ++r) {
+            if (!is_kept[(size_t)r]) continue;
+            while (q < wd && seen == n_cells * q / wd) rb[q++] = r;
+            ++seen;
+        }
+        for (; q < wd; ++q) rb[q] = n_rows;
     }
     auto owner_of = [&](int64_t row) { return (int)(std::upper_bound(rb.begin() + 1, rb.begin() + wd, row) - (rb.begin() + 1)); };
     // pieces: cells of (owner q, class k), class-sorted order kept
@@ -724,6 +744,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     const int64_t r0 = rb[me], nr_local = rb[me + 1] - rb[me];  // my row block
 
+    mark("layout");
     PP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     PP_CUDA(cudaEventRecord(ctx->ev[0], st));
@@ -833,13 +854,13 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             rc = pp_csr_densify(ctx, dcsr, d_slots.as<int32_t>() + s0, nl, d_colmap.as<int32_t>(), d_dense.p, n_genes);
             if (rc) return rc;
             rc = pp_rank_launch(ctx, d_dense.p, x_dtype, n_genes, d_loc.as<int32_t>() + s0, nl, d_ident.as<int32_t>(),
-                                n_genes, (uint16_t *)s_rank + s0 * n_genes, n_genes, d_flags);
+                                n_genes, (uint16_t *)s_rank + s0 * n_genes, n_genes, d_flags, ident.data());
             if (rc) return rc;
         }
         PP_CUDA(cudaStreamSynchronize(st));  // colmap / ident / loc are locals
     } else if (n_slots > 0) {
         rc = pp_rank_launch(ctx, dx_local, x_dtype, ld, d_slots.as<int32_t>(), n_slots, d_gene.as<int32_t>(), n_genes,
-                            (uint16_t *)s_rank, n_genes, d_flags);
+                            (uint16_t *)s_rank, n_genes, d_flags, gene_cols);
         if (rc) return rc;
     }
     // ---- planes every gene needs: bit_length(OR of its ranks) -- the max over the data ranks of their ORs has the same
@@ -856,6 +877,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     std::vector<uint32_t> red(4 + (size_t)n_genes);
     PP_CUDA(cudaMemcpyAsync(red.data(), d_red.p, sizeof(uint32_t) * red.size(), cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaStreamSynchronize(st));
+    mark("ranked");
     if (red[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
     const int B = std::max(1, bit_length64((uint64_t)red[0]));
     ctx->tm.n_planes = B;
@@ -910,6 +932,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         if (rc) return rc;
     }
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
+    mark("bitslice_enqueued");
 
     // ---- tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain position pairs a < b)
     const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB;
@@ -993,6 +1016,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     unsigned long long cap = (unsigned long long)std::min<int64_t>(std::max<int64_t>(n_pairs_shard, 1),
                                                                      std::max<int64_t>(1 << 22, n_pairs_shard / 16));
     unsigned long long count = 0;
+    mark("tables_enqueued");
     PP_CUDA(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (!(s_out = pp_slab(ctx, SLAB_OUT, sizeof(unsigned long long) * cap))) return PP_ENOMEM;
@@ -1021,6 +1045,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(cudaMemcpyAsync(&count, d_cnt.p, sizeof(count), cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
 
+        mark("pairs_done");
         if (count <= cap) break;
         if (attempt == 1) return pp_fail(ctx, PP_ECUDA, "pp_sandbag: compaction buffer overflow after resize");
         cap = count;  // exact size known now; evaluate once more
@@ -1087,6 +1112,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         count = receive ? all : 0;
     }
 
+    mark("gathered");
     // ---- sort into np.where order and return
     uint64_t *hk = nullptr;
     int32_t *hc = nullptr;
@@ -1120,6 +1146,7 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             free(hc);
             return pp_fail(ctx, PP_ECUDA, "pp_sandbag: result copy failed: %s", cudaGetErrorString(e));
         }
+        mark("sorted_copied");
         // unpack into the caller-owned arrays; fresh pages: a few threads take the page faults in parallel
         const uint64_t *packed = (const uint64_t *)ctx->pin_out;
         auto unpack = [=](unsigned long long a, unsigned long long b) {
@@ -1142,6 +1169,8 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     cudaEventElapsedTime(&ctx->tm.post_ms, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&ctx->tm.total_ms, ctx->ev[0], ctx->ev[4]);
     ctx->tm.n_launches = ctx->launches;
+    mark("done");
+    if (trace) fprintf(stderr, "pp_sandbag[%d/%d]:%s\n", me, wd, trace_line.c_str());
     *out_keys = hk;
     *out_class = hc;
     *out_n = (int64_t)count;

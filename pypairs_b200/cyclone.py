@@ -64,14 +64,22 @@ def _label_column(codes, labels):
     return col.tolist()
 
 
-def _first_argmax(cols):
-    """np.argmax over a handful of columns (first maximum wins), as column-wise passes: argmax along a short axis is slow."""
-    best = cols[0]
-    arg = np.zeros(len(best), dtype=np.int64)
-    for j in range(1, len(cols)):
-        arg = np.where(cols[j] > best, j, arg)
-        best = np.maximum(best, cols[j])
-    return arg, best
+def _names_index(sample_names):
+    """Index of the result frame.  A list of str goes through an Arrow array when pandas' inferred string dtype is
+    Arrow-backed: same Index as `pd.Index(list)`, built in a third of the time."""
+    import pandas as pd
+    if isinstance(sample_names, pd.Index):
+        return sample_names
+    if isinstance(sample_names, (list, tuple)) and len(sample_names) > 1000 and all(
+            type(sample_names[i]) is str for i in (0, len(sample_names) // 2, -1)):
+        dtype = pd.Series(["a"]).dtype
+        if isinstance(dtype, pd.StringDtype) and getattr(dtype, "storage", None) == "pyarrow":
+            try:
+                import pyarrow as pa
+                return pd.Index(pd.array(pa.array(sample_names, type=pa.large_string()), dtype=dtype))
+            except Exception:  # a non-str element somewhere: the generic conversion decides
+                pass
+    return pd.Index(sample_names)
 
 
 def scores_to_frame(scores, keys, sample_names):
@@ -79,26 +87,20 @@ def scores_to_frame(scores, keys, sample_names):
 
     max_class = first class with the largest score, 'N/A' unless the row sum is > 0;
     cc_prediction (only for exactly {G1, S, G2M}) = 'S' if max(G1, G2M) < 0.5 else argmax(G1, G2M).
+    The label codes come from one pass in the library (pp_score_labels).
     """
     keys = list(keys)
-    df = DataFrame({k: scores[i] for i, k in enumerate(keys)}, columns=keys)
-    df.index = sample_names
-    vals = np.asarray(scores, dtype=np.float64).reshape(len(keys), len(sample_names))  # [class, cell]
-    nan = np.isnan(vals)
-    safe = np.where(nan, -np.inf, vals)
+    vals = np.ascontiguousarray(scores, dtype=np.float64).reshape(len(keys), len(sample_names))  # [class, cell]
+    df = DataFrame({k: vals[i] for i, k in enumerate(keys)}, columns=keys)
+    df.index = _names_index(sample_names)
+    cc3 = len(keys) == 3 and all(e in keys for e in ["G1", "S", "G2M"])
     if len(keys):
-        arg, _ = _first_argmax(safe)  # first maximum, NaN skipped (DataFrame.idxmax)
-        row_sum = np.where(nan, 0.0, vals).sum(axis=0)  # DataFrame.sum skips NaN
-        df["max_class"] = _label_column(np.where(row_sum > 0, arg, len(keys)), keys + ["N/A"])
+        mc, cc = _ffi.score_labels(vals, keys.index("G1") if cc3 else -1, keys.index("G2M") if cc3 else -1)
+        df["max_class"] = _label_column(mc, keys + ["N/A"])
     else:
         df["max_class"] = []
-    if len(keys) == 3 and all(e in keys for e in ["G1", "S", "G2M"]):
-        sub = safe[[keys.index("G1"), keys.index("G2M")]]
-        pick, mx = _first_argmax(sub)
-        sub_nan = np.isneginf(mx)
-        codes = np.where(mx < 0.5, 2, pick)
-        codes[sub_nan] = -1  # NaN < 0.5 is False and idxmax of an all-NaN row is NaN
-        df["cc_prediction"] = _label_column(codes, ["G1", "G2M", "S"])
+    if cc3:
+        df["cc_prediction"] = _label_column(cc, ["G1", "G2M", "S"])
     return df
 
 

@@ -279,6 +279,33 @@ def test_host_gather_path(dtype):
         assert np.array_equal(s_host[i, rows], orc.phase_scores(x[rows], 30, 10, 5, pairs[k], used[k]))
 
 
+@pytest.mark.parametrize("dtype,feed", [(np.float32, "auto"), (np.float32, "zerocopy"), (np.float64, "zerocopy"),
+                                        (np.float32, "gather"), (np.float32, "copy"), (np.float64, "auto")])
+def test_pinned_input_zero_copy_lane(monkeypatch, dtype, feed):
+    """A pinned host matrix is also read in place by the zero-copy gather kernel (mapped memory, marker columns
+    only), beside the host gather: every way of feeding the chunks (PP_FEED) gives the scores of the device path."""
+    import torch
+    from pypairs_b200.cyclone import filter_marker_pairs
+    rng = np.random.default_rng(50)
+    markers, names, _ = default_setup(rng, 1, 6400)
+    n = 3 * 148 * 64 + 777  # several full chunks per lane
+    xt = torch.from_numpy(rng.poisson(2.0, (n, 6400)).astype(dtype)).pin_memory()
+    x = xt.numpy()
+    pairs, used = filter_marker_pairs(markers, names)
+    ks = list(pairs.keys())
+    u = [np.where(used[k])[0] for k in ks]
+    p = [pairs[k] for k in ks]
+    s_dev, _ = _ffi().cyclone(xt.cuda(), u, p, 20, 10, 5)
+    monkeypatch.setenv("PP_FEED", feed)
+    s_pin, tm = _ffi().cyclone(x, u, p, 20, 10, 5)
+    assert np.array_equal(s_pin, s_dev, equal_nan=True)
+    s_part, _ = _ffi().cyclone(x, u, p, 20, 10, 5, row_begin=100, n_cells=n - 150)  # a row range of the pinned matrix
+    assert np.array_equal(s_part, s_dev[:, 100:n - 50], equal_nan=True)
+    s_page, _ = _ffi().cyclone(np.array(x), u, p, 20, 10, 5)  # pageable copy: no zero-copy lane, same answer
+    assert np.array_equal(s_page, s_dev, equal_nan=True)
+    assert np.array_equal(s_dev[0, :16], orc.phase_scores(x[:16], 20, 10, 5, pairs[ks[0]], used[ks[0]]), equal_nan=True)
+
+
 def _score_vs_oracle(x, pairs, used, iterations, min_iter, min_pairs):
     got = _ffi().phase_scores(x, iterations, min_iter, min_pairs, pairs, used)
     exp = orc.phase_scores(x, iterations, min_iter, min_pairs, pairs, used)

@@ -44,22 +44,33 @@ def test_one_rank_communicator():
     assert e.value.code == _ffi.PP_ENCCL
 
 
-def _spawn(ws):
+def _spawn(ws, timeout=420):
+    """ws worker processes; the first failing rank ends the test at once (its peers would wait in a collective)."""
+    import tempfile
+    import time
     port = 29500 + os.getpid() % 2000
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(ws))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(ws), PYTHONFAULTHANDLER="1")
+    logs = [tempfile.TemporaryFile() for _ in range(ws)]
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_nccl_worker.py")],
-                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                              cwd=ROOT) for r in range(ws)]
+                              env=dict(env, RANK=str(r), LOCAL_RANK=str(r)), stdout=logs[r], stderr=subprocess.STDOUT, cwd=ROOT)
+             for r in range(ws)]
+    t0 = time.time()
+    while any(p.poll() is None for p in procs):
+        if any(p.poll() not in (None, 0) for p in procs) or time.time() - t0 > timeout:
+            time.sleep(2)
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            break
+        time.sleep(0.2)
     outs = []
-    for p in procs:
-        try:
-            outs.append(p.communicate(timeout=900)[0].decode())
-        except subprocess.TimeoutExpired:
-            for q in procs:
-                q.kill()
-            raise
-    assert all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
-    assert all("NCCL_OK" in o for o in outs)
+    for p, f in zip(procs, logs):
+        p.wait()
+        f.seek(0)
+        outs.append(f.read().decode(errors="replace"))
+    msg = "\n".join("---- rank {} (rc {}) ----\n{}".format(r, p.returncode, o[-4000:]) for r, (p, o) in enumerate(zip(procs, outs)))
+    assert all(p.returncode == 0 for p in procs), msg
+    assert all("NCCL_OK" in o for o in outs), msg
 
 
 def test_two_ranks_nccl():

@@ -52,6 +52,36 @@ def test_dense_rank_matches_numpy():
         assert mx == exp.max()
 
 
+@pytest.mark.parametrize("dtype,n_cols,n_keep", [(np.float32, 5003, 5003), (np.float32, 6001, 4500), (np.float64, 3001, 2900),
+                                                 (np.float32, 40000, 40000), (np.float64, 20000, 19000)])
+def test_streaming_rank_path(dtype, n_cols, n_keep):
+    """Rows of >= 8 KB with ascending, dense columns take the TMA-streamed count path (rank_stream_kernel): odd row
+    lengths (rows start at every 16-byte phase), dropped columns, cells that are not counts (handed to the general
+    kernel through the to-do list), more cells than resident CTAs."""
+    rng = np.random.default_rng(n_cols)
+    n_rows = 700
+    x = rng.poisson(rng.gamma(0.5, 6.0, n_cols)[None, :] + 0.05, (n_rows, n_cols)).astype(dtype)
+    x[3] = rng.lognormal(0, 1, n_cols).astype(dtype)         # real values: general kernel
+    x[4, 100:110] = 0.5                                      # a few non-integers
+    x[5] = 70000.0 + np.arange(n_cols) % 3                   # integers beyond 16 bits
+    x[6] = 0
+    x[7, -1] = 65535.0
+    x[8, 0] = -1.0
+    cols = np.sort(rng.choice(n_cols, n_keep, replace=False)).astype(np.int32)
+    rows = rng.permutation(n_rows)[:650].astype(np.int32)
+    rows[0] = 11
+    got, mx = _ffi().dense_rank(x, rows, cols)
+    sub = x[rows][:, cols]
+    exp = np.stack([np.unique(r, return_inverse=True)[1] for r in sub])
+    assert np.array_equal(got, exp.astype(np.uint16))
+    assert mx == exp.max()
+    xn = x.copy()
+    xn[11, cols[5]] = np.nan
+    with pytest.raises(_ffi().PyPairsB200Error) as e:
+        _ffi().dense_rank(xn, rows, cols)
+    assert e.value.code == _ffi().PP_ENAN
+
+
 @pytest.mark.parametrize("name", SANDBAG_CASE_NAMES)
 def test_golden_cases(sandbag_cases, name):
     c = sandbag_cases
