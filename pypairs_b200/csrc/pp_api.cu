@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include <math.h>
 
@@ -112,7 +113,77 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
 
 PP_API const char *pp_last_error(pp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_pp_err.c_str(); }
 
-PP_API void pp_free(void *p) { free(p); }
+// ---- result buffers handed to the caller --------------------------------------------------------------------------
+// Large variable-size results (the marker lists of pp_sandbag) are returned in PINNED host blocks from a small
+// process-wide pool: the device -> host copy lands directly in the buffer the caller receives (no staging copy, no
+// page faults of a fresh malloc), and pp_free() puts the block back.  Small results and failures fall back to malloc.
+namespace {
+struct ResultBlock {
+    void *p;
+    size_t bytes;
+    bool used;
+    uint64_t last_use;
+};
+std::vector<ResultBlock> g_blocks;
+std::mutex g_blocks_mutex;
+uint64_t g_blocks_clock = 0;
+constexpr size_t RESULT_POOL_MAX = (size_t)2 << 30, RESULT_SMALL = 64 << 10;
+constexpr size_t RESULT_MAX_BLOCKS = 16;
+}  // namespace
+
+void *pp_result_alloc(size_t bytes, bool *pinned) {
+    if (pinned) *pinned = false;
+    if (bytes == 0) bytes = 1;
+    if (bytes >= RESULT_SMALL && bytes <= RESULT_POOL_MAX / 2) {
+        std::lock_guard<std::mutex> lock(g_blocks_mutex);
+        ResultBlock *best = nullptr;
+        for (auto &b : g_blocks)  // best fit among the free blocks that are not absurdly large for this result
+            if (!b.used && b.bytes >= bytes && b.bytes <= 4 * bytes && (!best || b.bytes < best->bytes)) best = &b;
+        if (!best) {
+            size_t total = 0;
+            for (auto &b : g_blocks) total += b.bytes;
+            const size_t want = (bytes + bytes / 4 + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+            // make room: drop the least recently used free blocks
+            while (!g_blocks.empty() && (total + want > RESULT_POOL_MAX || g_blocks.size() >= RESULT_MAX_BLOCKS)) {
+                int lru = -1;
+                for (int i = 0; i < (int)g_blocks.size(); ++i)
+                    if (!g_blocks[i].used && (lru < 0 || g_blocks[i].last_use < g_blocks[lru].last_use)) lru = i;
+                if (lru < 0) break;
+                cudaFreeHost(g_blocks[lru].p);
+                total -= g_blocks[lru].bytes;
+                g_blocks.erase(g_blocks.begin() + lru);
+            }
+            void *p = nullptr;
+            if (total + want <= RESULT_POOL_MAX && g_blocks.size() < RESULT_MAX_BLOCKS &&
+                cudaHostAlloc(&p, want, cudaHostAllocPortable) == cudaSuccess) {
+                g_blocks.push_back(ResultBlock{p, want, false, 0});
+                best = &g_blocks.back();
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (best) {
+            best->used = true;
+            best->last_use = ++g_blocks_clock;
+            if (pinned) *pinned = true;
+            return best->p;
+        }
+    }
+    return malloc(bytes);
+}
+
+PP_API void pp_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_blocks_mutex);
+        for (auto &b : g_blocks)
+            if (b.p == p) {
+                b.used = false;
+                return;
+            }
+    }
+    free(p);
+}
 
 PP_API int pp_get_timings(pp_ctx *ctx, pp_timings *out) {
     if (!ctx || !out) return pp_fail(ctx, PP_EINVAL, "pp_get_timings: NULL argument");

@@ -55,6 +55,8 @@ extern thread_local std::string g_pp_err;  // errors raised without a ctx
 int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...);
 // pointer to at least `bytes` of device memory in slab `slot` (contents undefined); nullptr + error on failure
 void *pp_slab(pp_ctx *ctx, int slot, size_t bytes);
+// host buffer for a variable-size result the caller releases with pp_free(): pinned (pool) when large, else malloc
+void *pp_result_alloc(size_t bytes, bool *pinned);
 enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, SLAB_CHUNK0 = 5, SLAB_CHUNK1 = 6, SLAB_MISC = 7, SLAB_SORT = 8, SLAB_ZC0 = 9, SLAB_ZC1 = 10 };
 
 #define PP_CUDA(call)                                                                              \

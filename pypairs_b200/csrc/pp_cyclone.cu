@@ -1437,19 +1437,58 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         int i = 0, n_dma = 0, n_zc = 0;  // chunks so far: all, per lane
         double gather_host_ms = 0.0, wait_host_ms = 0.0;
         int64_t zc_bytes = 0;  // useful bytes the zero-copy lane fetched (the sectors on the bus are ~6x that)
+        // rank + score of one chunk on the compute stream (which must already wait for the chunk's data)
+        auto enqueue_compute = [&](const void *chunk_dev, int64_t c0, int64_t nc, cudaEvent_t done) -> int {
+            int r = pp_rank_launch(ctx, chunk_dev, x_dtype, dev_ld, d_rows.as<int32_t>(), nc, dev_cols, U,
+                                   (uint16_t *)s_rank + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
+            if (r) return r;
+            PP_CUDA(cudaEventRecord(done, st));  // the chunk buffer may be refilled
+            cudaEvent_t e0, e1;
+            PP_CUDA(events.make(&e0, cudaEventDefault));
+            PP_CUDA(events.make(&e1, cudaEventDefault));
+            ev_s.push_back(e0);
+            ev_s.push_back(e1);
+            P.rank = (uint16_t *)s_rank + c0 * rank_ld;
+            P.n_cells = nc;
+            P.out_off = c0;
+            PP_CUDA(cudaEventRecord(e0, st));
+            launch_score(nc);
+            PP_CHECK_LAUNCH();
+            PP_CUDA(cudaEventRecord(e1, st));
+            return PP_OK;
+        };
+        // Zero-copy chunks whose gather kernel is in flight.  With both lanes active their rank + score are enqueued only
+        // once the gather has finished (polled between the host gathers): the compute stream is in-order, and a chunk
+        // enqueued early would hold back every DMA chunk that becomes ready before it.
+        struct ZcPending { int64_t c0, nc; int b; };
+        std::vector<ZcPending> zc_pending;
+        auto drain_zc = [&](bool wait_all) -> int {
+            while (!zc_pending.empty()) {
+                const ZcPending z = zc_pending.front();
+                if (wait_all)
+                    PP_CUDA(cudaStreamWaitEvent(st, zready[z.b], 0));
+                else if (cudaEventQuery(zready[z.b]) != cudaSuccess)
+                    break;
+                zc_pending.erase(zc_pending.begin());
+                const int r = enqueue_compute(zbuf[z.b], z.c0, z.nc, zfreed[z.b]);
+                if (r) return r;
+            }
+            return PP_OK;
+        };
         // the first chunks are an eighth, a quarter and a half wave: the device starts after ~1 ms of host work, not ~5
         for (int64_t c0 = 0, nc = 0; c0 < n_cells; c0 += nc, ++i) {
             nc = i < 3 ? chunk_cells >> (3 - i) : chunk_cells;
             nc = std::min({(std::max<int64_t>(nc, 1) + 127) / 128 * 128, chunk_cells, n_cells - c0});
-            // lane of this chunk: the zero-copy lane whenever one of its two buffers is free (the rank kernel that read it
-            // has finished) -- it costs the host nothing --, else the DMA lane, whose gather keeps this thread busy
-            bool use_zc = zc_lane && !dma_lane;
-            if (zc_lane && dma_lane && i > 0)
-                use_zc = n_zc < 2 || cudaEventQuery(zfreed[n_zc & 1]) == cudaSuccess;
-            const void *chunk_dev = nullptr;
+            if (zc_lane && dma_lane) {
+                rc = drain_zc(false);
+                if (rc) return rc;
+            }
+            // lane of this chunk: the zero-copy lane whenever one of its two buffers is not being filled -- it costs the
+            // host nothing --, else the DMA lane, whose gather keeps this thread busy for the length of a chunk
+            const bool use_zc = zc_lane && (!dma_lane || (i > 0 && zc_pending.size() < 2));
             if (use_zc) {
                 const int b = n_zc & 1;
-                if (n_zc >= 2) PP_CUDA(cudaStreamWaitEvent(zs, zfreed[b], 0));
+                if (n_zc >= 2) PP_CUDA(cudaStreamWaitEvent(zs, zfreed[b], 0));  // the rank kernel that read zbuf[b] is done
                 const unsigned grid = (unsigned)std::min<int64_t>((nc + ZC_WARPS - 1) / ZC_WARPS, ctx->n_sm);
                 if (x_dtype == PP_F64)
                     zc_gather_kernel<double><<<grid, ZC_WARPS * 32, 0, zs>>>((const double *)xz, ld, c0, nc, d_uni.as<int32_t>(), U, (double *)zbuf[b]);
@@ -1457,9 +1496,13 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                     zc_gather_kernel<float><<<grid, ZC_WARPS * 32, 0, zs>>>((const float *)xz, ld, c0, nc, d_uni.as<int32_t>(), U, (float *)zbuf[b]);
                 PP_CHECK_LAUNCH();
                 PP_CUDA(cudaEventRecord(zready[b], zs));
-                PP_CUDA(cudaStreamWaitEvent(st, zready[b], 0));
-                chunk_dev = zbuf[b];
                 zc_bytes += (int64_t)((size_t)nc * U * esz);
+                ++n_zc;
+                zc_pending.push_back(ZcPending{c0, nc, b});
+                if (!dma_lane) {  // only lane: plain stream order
+                    rc = drain_zc(true);
+                    if (rc) return rc;
+                }
             } else {
                 const int b = n_dma & 1;
                 const void *src = x0 + (size_t)c0 * ld * esz;
@@ -1480,28 +1523,13 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                 ctx->tm.h2d_bytes += (int64_t)((size_t)nc * dev_ld * esz);
                 PP_CUDA(cudaEventRecord(copied[b], cs));
                 PP_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
-                chunk_dev = buf[b];
+                ++n_dma;
+                rc = enqueue_compute(buf[b], c0, nc, freed[b]);
+                if (rc) return rc;
             }
-            rc = pp_rank_launch(ctx, chunk_dev, x_dtype, dev_ld, d_rows.as<int32_t>(), nc, dev_cols, U,
-                                (uint16_t *)s_rank + c0 * rank_ld, rank_ld, d_flags.as<int32_t>());
-            if (rc) return rc;
-            if (use_zc)
-                PP_CUDA(cudaEventRecord(zfreed[n_zc++ & 1], st));
-            else
-                PP_CUDA(cudaEventRecord(freed[n_dma++ & 1], st));
-            cudaEvent_t e0, e1;
-            PP_CUDA(events.make(&e0, cudaEventDefault));
-            PP_CUDA(events.make(&e1, cudaEventDefault));
-            ev_s.push_back(e0);
-            ev_s.push_back(e1);
-            P.rank = (uint16_t *)s_rank + c0 * rank_ld;
-            P.n_cells = nc;
-            P.out_off = c0;
-            PP_CUDA(cudaEventRecord(e0, st));
-            launch_score(nc);
-            PP_CHECK_LAUNCH();
-            PP_CUDA(cudaEventRecord(e1, st));
         }
+        rc = drain_zc(true);
+        if (rc) return rc;
         ctx->tm.h2d_bytes += zc_bytes;
         PP_CUDA(cudaEventRecord(ev_c1, cs));
         if (trace)

@@ -114,6 +114,7 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
             for (int i = tid; i < BM_WORDS; i += RANK_THREADS) sm.bitmap[i] = 0;
             __syncthreads();
             bool small = true;
+            uint32_t m0 = 0, m1 = 0;  // presence bits of the values 0..63 seen by this thread (see rank_stream_kernel)
             for (int g0 = tid; g0 < n; g0 += RANK_THREADS * 8) {
                 T v[8];
 #pragma unroll
@@ -130,10 +131,19 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                         const uint32_t u = ok ? (uint32_t)v[j] : 0u;
                         vals[g] = (uint16_t)u;
                         const uint32_t bit = 1u << (u & 31);
-                        // most cells hold a handful of distinct counts: test first, the atomic is then rare
-                        if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
+                        // most cells hold a handful of distinct small counts: they are collected in registers; for the
+                        // rest test first, the atomic is then rare
+                        if (u < 32) m0 |= bit;
+                        else if (u < 64) m1 |= bit;
+                        else if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
                     }
                 }
+            }
+            m0 = __reduce_or_sync(0xffffffffu, m0);
+            m1 = __reduce_or_sync(0xffffffffu, m1);
+            if (lane == 0) {
+                if (m0) atomicOr(&sm.bitmap[0], m0);
+                if (m1) atomicOr(&sm.bitmap[1], m1);
             }
             if (__syncthreads_and(small)) {  // CTA-uniform (NaN fails the test and takes the sort path)
                 // exclusive prefix popcount over the 2048 words: 4 words per thread, warp scan, warp totals
@@ -155,9 +165,11 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                 for (int j = 0; j < 4; ++j) { sm.bm_prefix[tid * 4 + j] = run; run += c[j]; }
                 if (tid == RANK_THREADS - 1) atomicMax(&flags[0], (int)run - 1);  // distinct values - 1
                 __syncthreads();
+                const uint32_t b0 = sm.bitmap[0], b1 = sm.bitmap[1], p1 = __popc(b0);
                 for (int g = tid; g < n; g += RANK_THREADS) {
-                    const uint32_t u = vals[g];
-                    out[g] = (uint16_t)(sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & ((1u << (u & 31)) - 1u)));
+                    const uint32_t u = vals[g], below = (1u << (u & 31)) - 1u;
+                    out[g] = (uint16_t)(u < 32 ? __popc(b0 & below) : u < 64 ? p1 + __popc(b1 & below)
+                                                                            : sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & below));
                 }
                 __syncthreads();  // bitmap / prefix / vals reused by the next cell
                 continue;
@@ -400,13 +412,31 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
 constexpr int STREAM_CHUNK = 16384;  // bytes per ring stage
 constexpr int STREAM_MAX_STAGES = 8;
 
+constexpr int LUT_N = 2048;  // counts below this are ranked through a look-up table
 struct alignas(16) StreamSmem {
     uint32_t bitmap[BM_WORDS];
     uint32_t bm_prefix[BM_WORDS];
     uint32_t wtot[32];
     uint64_t full[STREAM_MAX_STAGES], empty[STREAM_MAX_STAGES];
     int bad[2];
+    int dirty;               // a count >= LUT_N was seen: bitmap words >= LUT_N / 32 are in use
+    uint8_t seen[LUT_N];     // presence of the counts < LUT_N: plain byte stores, no atomics (writing 1 is idempotent)
+    uint16_t lut[LUT_N];     // rank of every count < LUT_N of the current cell
 };
+
+// is v an integer in [0, 65536)?  *u = that integer.  float: no conversion instructions (XU pipe) -- adding 2^23 leaves
+// the integer part in the low mantissa bits, and the bit pattern of a non-negative float orders like the float
+// (-0.0 is turned down here and ranked by the general kernel, which ties it with +0.0 all the same).
+__device__ __forceinline__ bool small_count(float v, uint32_t &u) {
+    const float t = v + 8388608.0f;
+    u = __float_as_uint(t) & 0xffffu;
+    return (t - 8388608.0f == v) && (__float_as_uint(v) < 0x47800000u);
+}
+__device__ __forceinline__ bool small_count(double v, uint32_t &u) {
+    const bool ok = is_small_count(v);
+    u = ok ? (uint32_t)v : 0u;
+    return ok;
+}
 
 __device__ __forceinline__ void cons_sync(int n_cons) { asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory"); }
 
@@ -446,9 +476,11 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
             mbar_init(&sm.empty[s], NCONS / 32);
         }
         sm.bad[0] = sm.bad[1] = 0;
+        sm.dirty = 0;
         fence_mbar_init();
     }
     for (int i = tid; i < BM_WORDS; i += NCONS + 32) sm.bitmap[i] = 0;
+    for (int i = tid; i < LUT_N / 4; i += NCONS + 32) reinterpret_cast<uint32_t *>(sm.seen)[i] = 0;
     __syncthreads();
     const uintptr_t xb = reinterpret_cast<uintptr_t>(x);
 
@@ -474,6 +506,7 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
     }
 
     // ---- consumers
+    constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte shared-memory load
     uint32_t q = 0;
     int par = 0;
     for (int64_t slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
@@ -486,25 +519,52 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
         const uintptr_t a = xb + ((uintptr_t)row * (uintptr_t)ld + (uintptr_t)c_min) * sizeof(T);
         const uintptr_t a0 = a & ~(uintptr_t)15, e1 = (a + (uintptr_t)span * sizeof(T) + 15) & ~(uintptr_t)15;
         const int shift = (int)((a - a0) / sizeof(T));  // elements of the first chunk before column c_min
+        // the look-up pass writes eight ranks per 16-byte store from the first 16-byte boundary of the output row on
+        // (`head` scalar ranks before it); the counts are staged at vals[pad + g] so that those groups of eight are
+        // 16-byte aligned in shared memory too (one LDS.128 instead of eight 2-byte loads with bank conflicts)
+        const int head = min(n, (int)(((16 - (reinterpret_cast<uintptr_t>(out) & 15)) & 15) >> 1));
+        const int pad = (8 - head) & 7;
+        // ---- pass 1, chunk by chunk as the bulk copies land: count test, u16 staging, presence
         bool small = true;
         int col0 = -shift;  // column (relative to c_min) of element 0 of the chunk
         for (uintptr_t off = 0; a0 + off < e1; off += STREAM_CHUNK, ++q, col0 += CHE) {
             const int s = (int)(q % (uint32_t)n_stages);
             mbar_wait(&sm.full[s], (q / (uint32_t)n_stages) & 1);
-            const T *src = reinterpret_cast<const T *>(ring + (size_t)s * STREAM_CHUNK);
-#pragma unroll 4
-            for (int e = tid; e < CHE; e += NCONS) {
-                const int col = col0 + e;
-                if (col >= 0 && col < span) {
-                    const int g = inv ? __ldg(inv + col) : col;
-                    if (g >= 0) {
-                        const T v = src[e];
-                        const bool ok = is_small_count(v);
-                        small = small && ok;
-                        const uint32_t u = ok ? (uint32_t)v : 0u;
-                        vals[g] = (uint16_t)u;
-                        const uint32_t bit = 1u << (u & 31);
-                        if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
+            const uint4 *src = reinterpret_cast<const uint4 *>(ring + (size_t)s * STREAM_CHUNK);
+#pragma unroll 2
+            for (int e4 = tid; e4 < CHE / EPV; e4 += NCONS) {
+                const uint4 raw = src[e4];
+                T v[EPV];
+                if (sizeof(T) == 4) {
+                    v[0] = (T)__uint_as_float(raw.x);
+                    v[1] = (T)__uint_as_float(raw.y);
+                    v[EPV - 2] = (T)__uint_as_float(raw.z);
+                    v[EPV - 1] = (T)__uint_as_float(raw.w);
+                } else {
+                    v[0] = (T)__hiloint2double((int)raw.y, (int)raw.x);
+                    v[EPV - 1] = (T)__hiloint2double((int)raw.w, (int)raw.z);
+                }
+#pragma unroll
+                for (int k = 0; k < EPV; ++k) {
+                    const int col = col0 + e4 * EPV + k;
+                    bool valid = (unsigned)col < (unsigned)span;
+                    int g = col;
+                    if (inv) {
+                        g = valid ? __ldg(inv + col) : -1;
+                        valid = g >= 0;
+                    }
+                    uint32_t u;
+                    const bool ok = small_count(v[k], u);
+                    small = small && (ok || !valid);
+                    if (valid && ok) {
+                        vals[pad + g] = (uint16_t)u;
+                        if (u < LUT_N) {
+                            sm.seen[u] = 1;
+                        } else {
+                            sm.dirty = 1;
+                            const uint32_t bit = 1u << (u & 31);
+                            if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
+                        }
                     }
                 }
             }
@@ -512,11 +572,28 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
             if (lane == 0) mbar_arrive(&sm.empty[s]);
         }
         if (!small) sm.bad[par] = 1;
-        cons_sync(NCONS);  // bitmap, vals, bad complete
+        cons_sync(NCONS);  // seen, bitmap, vals, bad complete
         const bool bad = sm.bad[par] != 0;
+        const bool dirty = sm.dirty != 0;
         if (tid == 0) sm.bad[par ^ 1] = 0;  // next cell's flag (nobody reads it before the next cons_sync)
         par ^= 1;
         if (!bad) {
+            // presence bytes -> bitmap words 0 .. LUT_N/32 - 1 (assigned, not OR-ed: no zeroing between cells)
+            if (tid < LUT_N / 32) {
+                const uint4 *sp = reinterpret_cast<const uint4 *>(sm.seen + tid * 32);
+                uint32_t w = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4 b = sp[h];
+                    const uint32_t x4[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)  // four 0/1 bytes -> four bits: byte i lands on bit 24 + i of the product
+                        w |= (((x4[j] & 0x01010101u) * 0x01020408u) >> 24 & 0xfu) << (h * 16 + j * 4);
+                }
+                sm.bitmap[tid] = w;
+            }
+            cons_sync(NCONS);
+            for (int i = tid; i < LUT_N / 4; i += NCONS) reinterpret_cast<uint32_t *>(sm.seen)[i] = 0;  // for the next cell
             // exclusive prefix popcount over the bitmap words: WPT words per thread, warp scan, warp totals
             uint32_t c[WPT], t4 = 0, incl = 0;
             if (tid < PFX) {
@@ -540,30 +617,39 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
                 if (tid == PFX - 1) atomicMax(&flags[0], (int)run - 1);  // distinct values - 1
             }
             cons_sync(NCONS);
-            // look-up: scalar head up to a 16-byte boundary of the output row, then eight ranks per 16-byte store
-            auto rank_of = [&](int g) -> uint32_t {
-                const uint32_t u = vals[g];
+            auto rank_slow = [&](uint32_t u) -> uint32_t {
                 return sm.bm_prefix[u >> 5] + __popc(sm.bitmap[u >> 5] & ((1u << (u & 31)) - 1u));
             };
-            const int head = min(n, (int)(((16 - (reinterpret_cast<uintptr_t>(out) & 15)) & 15) >> 1));
-            if (tid < head) out[tid] = (uint16_t)rank_of(tid);
+            for (int v = tid; v < LUT_N; v += NCONS) sm.lut[v] = (uint16_t)rank_slow((uint32_t)v);
+            cons_sync(NCONS);
+            // ---- look-up: one table read per count; eight ranks per 16-byte store
+            auto rank_of = [&](uint32_t u) -> uint32_t { return u < LUT_N ? (uint32_t)sm.lut[u] : rank_slow(u); };
+            if (tid < head) out[tid] = (uint16_t)rank_of(vals[pad + tid]);
             const int n_vec = (n - head) >> 3;
+            const uint4 *v8p = reinterpret_cast<const uint4 *>(vals + pad + head);  // pad + head is 0 or 8
+#pragma unroll 2
             for (int v8 = tid; v8 < n_vec; v8 += NCONS) {
-                const int g = head + v8 * 8;
+                const uint4 u8 = v8p[v8];
+                const uint32_t in[4] = {u8.x, u8.y, u8.z, u8.w};
                 uint32_t w[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) w[j] = rank_of(g + 2 * j) | (rank_of(g + 2 * j + 1) << 16);
-                *reinterpret_cast<uint4 *>(out + g) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int j = 0; j < 4; ++j) w[j] = rank_of(in[j] & 0xffffu) | (rank_of(in[j] >> 16) << 16);
+                *reinterpret_cast<uint4 *>(out + head + v8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            for (int g = head + n_vec * 8 + tid; g < n; g += NCONS) out[g] = (uint16_t)rank_of(g);
-        } else if (tid == 0) {
-            todo[atomicAdd(&ctl[1], 1)] = (int32_t)slot;
+            for (int g = head + n_vec * 8 + tid; g < n; g += NCONS) out[g] = (uint16_t)rank_of(vals[pad + g]);
+        } else {
+            for (int i = tid; i < LUT_N / 4; i += NCONS) reinterpret_cast<uint32_t *>(sm.seen)[i] = 0;
+            if (tid == 0) todo[atomicAdd(&ctl[1], 1)] = (int32_t)slot;
         }
-        cons_sync(NCONS);  // everybody is done with bitmap / prefix / vals
-        for (int i = tid; i < BM_WORDS; i += NCONS) sm.bitmap[i] = 0;
-        cons_sync(NCONS);
+        cons_sync(NCONS);  // everybody is done with bitmap / prefix / lut / vals
+        if (dirty) {  // rare: counts >= LUT_N used the upper bitmap words
+            for (int i = LUT_N / 32 + tid; i < BM_WORDS; i += NCONS) sm.bitmap[i] = 0;
+            if (tid == 0) sm.dirty = 0;
+            cons_sync(NCONS);
+        }
     }
 }
+
 }  // namespace
 
 // Launch configuration of the streaming kernel for rows of `span` columns holding n kept genes: consumers per CTA
@@ -571,7 +657,7 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
 struct StreamCfg { bool ok; int n_cons, n_stages, grid_per_sm; size_t dyn; };
 static StreamCfg stream_config(pp_ctx *ctx, int64_t n) {
     StreamCfg c = {false, 0, 0, 0, 0};
-    const size_t vals = ((size_t)n * 2 + 127) & ~(size_t)127;
+    const size_t vals = (((size_t)n + 8) * 2 + 127) & ~(size_t)127;  // staged counts (+ up to 7 elements of alignment pad)
     const size_t stat = sizeof(StreamSmem);
     const size_t sm_total = 228 * 1024, reserve = 1024;  // per SM; every resident CTA also reserves 1 KB
     const size_t dyn_max1 = (size_t)ctx->smem_optin - stat, dyn_max2 = sm_total / 2 - reserve - stat;

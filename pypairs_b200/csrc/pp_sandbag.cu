@@ -603,6 +603,17 @@ sort_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long lon
     }
 }
 
+// (key << 16 | class) -> the two arrays the caller receives
+__global__ void split_keys_kernel(const unsigned long long *__restrict__ packed, unsigned long long n,
+                                  uint64_t *__restrict__ keys, int32_t *__restrict__ cls) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long v = packed[i];
+        keys[i] = v >> 16;
+        cls[i] = (int32_t)(v & 0xffffu);
+    }
+}
+
 int radix_sort_u64(pp_ctx *ctx, unsigned long long *d_a, unsigned long long *d_b, int64_t n, int lo_bit,
                    int hi_bit, unsigned long long **sorted) {
     *sorted = d_a;
@@ -1122,44 +1133,34 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         const int hi_bit = 16 + bit_length64((uint64_t)n_genes * (uint64_t)n_genes);
         rc = radix_sort_u64(ctx, d_keys, (unsigned long long *)s_out2, (int64_t)count, 16, hi_bit, &sorted);
         if (rc) return rc;
-        hk = (uint64_t *)malloc(sizeof(uint64_t) * count);
-        hc = (int32_t *)malloc(sizeof(int32_t) * count);
+        // split (key << 16 | class) on the device and copy both arrays straight into the buffers the caller receives
+        bool pin_k = false, pin_c = false;
+        hk = (uint64_t *)pp_result_alloc(sizeof(uint64_t) * count, &pin_k);
+        hc = (int32_t *)pp_result_alloc(sizeof(int32_t) * count, &pin_c);
         if (!hk || !hc) {
-            free(hk);
-            free(hc);
+            pp_free(hk);
+            pp_free(hc);
             return pp_fail(ctx, PP_ENOMEM, "pp_sandbag: host allocation of %llu markers failed", count);
         }
-        // device -> pinned staging (a pageable destination would be staged by the driver at a fraction of the rate)
-        cudaError_t e = cudaSuccess;
-        if (ctx->pin_out_bytes < sizeof(uint64_t) * count) {
-            if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
-            ctx->pin_out = nullptr;
-            ctx->pin_out_bytes = 0;
-            const size_t want = std::max<size_t>(sizeof(uint64_t) * count * 2, (size_t)8 << 20);
-            e = cudaHostAlloc(&ctx->pin_out, want, cudaHostAllocDefault);
-            if (e == cudaSuccess) ctx->pin_out_bytes = want;
+        unsigned long long *other = sorted == d_keys ? (unsigned long long *)s_out2 : d_keys;  // the sort's spare buffer
+        uint64_t *d_k = (uint64_t *)other;
+        void *s_cls = pp_slab(ctx, SLAB_MISC, sizeof(int32_t) * count);
+        cudaError_t e = s_cls ? cudaSuccess : cudaErrorMemoryAllocation;
+        int32_t *d_c = (int32_t *)s_cls;
+        if (e == cudaSuccess) {
+            split_keys_kernel<<<(unsigned)std::min<unsigned long long>((count + 255) / 256, 65535u * 16u), 256, 0, st>>>(sorted, count, d_k, d_c);
+            ctx->launches++;
+            e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->pin_out, sorted, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hk, d_k, sizeof(uint64_t) * count, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hc, d_c, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
-            free(hk);
-            free(hc);
+            pp_free(hk);
+            pp_free(hc);
             return pp_fail(ctx, PP_ECUDA, "pp_sandbag: result copy failed: %s", cudaGetErrorString(e));
         }
         mark("sorted_copied");
-        // unpack into the caller-owned arrays; fresh pages: a few threads take the page faults in parallel
-        const uint64_t *packed = (const uint64_t *)ctx->pin_out;
-        auto unpack = [=](unsigned long long a, unsigned long long b) {
-            for (unsigned long long i = a; i < b; ++i) {
-                hc[i] = (int32_t)(packed[i] & 0xffffu);
-                hk[i] = packed[i] >> 16;
-            }
-        };
-        const int n_thr = count >= (1u << 17) ? 4 : 1;
-        std::vector<std::thread> pool;
-        for (int t = 1; t < n_thr; ++t) pool.emplace_back(unpack, count * t / n_thr, count * (t + 1) / n_thr);
-        unpack(0, count / n_thr);
-        for (auto &th : pool) th.join();
     }
     PP_CUDA(cudaEventRecord(ctx->ev[4], st));
     PP_CUDA(cudaEventSynchronize(ctx->ev[4]));

@@ -67,9 +67,12 @@ def test_streaming_rank_path(dtype, n_cols, n_keep):
     x[6] = 0
     x[7, -1] = 65535.0
     x[8, 0] = -1.0
+    x[9] = (np.arange(n_cols) * 7) % 60000                   # thousands of distinct counts beyond the look-up table
+    x[10] = x[9]                                             # ... twice in a row (upper bitmap words are cleared in between)
+    x[12, ::3] = -0.0                                        # signed zeros tie
     cols = np.sort(rng.choice(n_cols, n_keep, replace=False)).astype(np.int32)
     rows = rng.permutation(n_rows)[:650].astype(np.int32)
-    rows[0] = 11
+    rows[:14] = [11, 3, 4, 5, 6, 7, 8, 9, 10, 9, 12, 13, 10, 2]
     got, mx = _ffi().dense_rank(x, rows, cols)
     sub = x[rows][:, cols]
     exp = np.stack([np.unique(r, return_inverse=True)[1] for r in sub])
