@@ -1043,17 +1043,23 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     const int64_t wave_cells = (int64_t)ctx->n_sm * TILE_CELLS;
     // (measured: with 16 host threads the gather beats full-row copies 161 vs 195 ms on cfg2; with 8 threads per
     // rank, 4 ranks sharing the host, it loses 402 vs 349 ms -- so it needs >= 12 threads for this process)
-    // A second way in for PINNED / registered host matrices: a gather kernel reads the marker columns straight from the
-    // mapped host memory (32-byte sectors over the GPU's own PCIe link: 1 133 sectors = 36 KB instead of 80 KB per cfg2
-    // row, no host core involved).  Alone it moves 0.9 cells/us (profiles/hostbench/zerocopy_probe.cu: 56 ms per 50k
-    // cells against 72 ms for the full rows by DMA); it runs BESIDE the host gather, chunks going to whichever lane has
-    // a free buffer.  With the zero-copy lane present the host gather is worth having from 4 threads on.
-    // PP_FEED = gather | zerocopy | copy forces one way (tests, experiments).
+    // Three ways for a chunk of cells of a HOST matrix to reach the device (profiles/feed_probe.py, cfg2 = 100k x 20k
+    // f32, 1 479 marker genes, library time of the call):
+    //   gather    host threads copy the marker columns into pinned staging, DMA of [cells, U]
+    //             16 threads: 82 ms (pinned or pageable input); 4 threads: 113 ms
+    //   zerocopy  PINNED / registered matrices only: a gather kernel reads the marker columns straight from the mapped
+    //             host memory (32-byte sectors over the GPU's own PCIe link: 1 133 sectors = 36 KB instead of 80 KB per
+    //             row, no host core involved): 128 ms, whatever the host is doing
+    //   copy      DMA of the full rows, columns picked by the rank kernel: 151 ms pinned, 710 ms pageable
+    // So: wide matrices go through the gather, except that a pinned matrix is read in place when this process has
+    // fewer than 4 host threads (many ranks on a small host).  Running both lanes side by side (PP_FEED=both, chunks
+    // to whichever lane is free) loses on this box -- 114 ms with 16 threads --: the two contend for host memory.
+    // PP_FEED = gather | zerocopy | both | copy forces a way (tests, experiments).
     const bool narrow = !csr && !x_is_device && (int64_t)U * 4 <= n_cols;
     const char *feed_env = getenv("PP_FEED");
-    const std::string feed = feed_env ? feed_env : "auto";
+    std::string feed = feed_env ? feed_env : "auto";
     const uint8_t *xz = nullptr;  // device-side address of x0 when the matrix is mapped host memory
-    if (narrow && (feed == "auto" || feed == "zerocopy") && n_cells > 0) {
+    if (narrow && (feed == "auto" || feed == "zerocopy" || feed == "both") && n_cells > 0) {
         cudaPointerAttributes a0, a1;
         const uint8_t *last = x0 + ((size_t)(n_cells - 1) * ld + (size_t)n_cols) * esz - 1;
         if (cudaPointerGetAttributes(&a0, x0) == cudaSuccess && cudaPointerGetAttributes(&a1, last) == cudaSuccess &&
@@ -1063,9 +1069,11 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         else
             cudaGetLastError();
     }
-    const bool zc_lane = xz != nullptr;
-    const bool host_gather = narrow && feed != "copy" && feed != "zerocopy" &&
-                             (feed == "gather" || host_threads() >= (zc_lane ? 4 : 12));
+    if (feed == "auto") feed = !narrow ? "copy" : (xz && host_threads() < 4) ? "zerocopy" : "gather";
+    if (!narrow) feed = "copy";
+    if (!xz && (feed == "zerocopy" || feed == "both")) feed = "gather";  // not mapped memory
+    const bool zc_lane = feed == "zerocopy" || feed == "both";
+    const bool host_gather = feed == "gather" || feed == "both";
     const bool compact = host_gather || zc_lane;  // the device chunk buffers hold [cells, U]
     const bool pipelined = !csr && !x_is_device && (n_cells > wave_cells || compact);
     const int64_t chunk_cells = (pipelined || csr) ? std::min(wave_cells, n_cells) : n_cells;

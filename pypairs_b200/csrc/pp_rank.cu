@@ -420,8 +420,8 @@ struct alignas(16) StreamSmem {
     uint64_t full[STREAM_MAX_STAGES], empty[STREAM_MAX_STAGES];
     int bad[2];
     int dirty;               // a count >= LUT_N was seen: bitmap words >= LUT_N / 32 are in use
-    uint8_t seen[LUT_N];     // presence of the counts < LUT_N: plain byte stores, no atomics (writing 1 is idempotent)
-    uint16_t lut[LUT_N];     // rank of every count < LUT_N of the current cell
+    alignas(16) uint8_t seen[LUT_N + 16];     // presence of the counts < LUT_N: plain byte stores, no atomics (writing 1 is idempotent)
+    alignas(16) uint16_t lut[LUT_N];     // rank of every count < LUT_N of the current cell
 };
 
 // is v an integer in [0, 65536)?  *u = that integer.  float: no conversion instructions (XU pipe) -- adding 2^23 leaves
@@ -556,15 +556,14 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
                     uint32_t u;
                     const bool ok = small_count(v[k], u);
                     small = small && (ok || !valid);
-                    if (valid && ok) {
-                        vals[pad + g] = (uint16_t)u;
-                        if (u < LUT_N) {
-                            sm.seen[u] = 1;
-                        } else {
-                            sm.dirty = 1;
-                            const uint32_t bit = 1u << (u & 31);
-                            if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
-                        }
+                    // branch-free: elements outside the row (or not counts) store into dummy slots behind the arrays
+                    const bool use = valid && ok;
+                    vals[use ? pad + g : n + 8] = (uint16_t)u;
+                    sm.seen[use && u < LUT_N ? u : LUT_N] = 1;
+                    if (use && u >= LUT_N) {  // rare
+                        sm.dirty = 1;
+                        const uint32_t bit = 1u << (u & 31);
+                        if (!(*(volatile uint32_t *)&sm.bitmap[u >> 5] & bit)) atomicOr(&sm.bitmap[u >> 5], bit);
                     }
                 }
             }
@@ -657,7 +656,7 @@ rank_stream_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restric
 struct StreamCfg { bool ok; int n_cons, n_stages, grid_per_sm; size_t dyn; };
 static StreamCfg stream_config(pp_ctx *ctx, int64_t n) {
     StreamCfg c = {false, 0, 0, 0, 0};
-    const size_t vals = (((size_t)n + 8) * 2 + 127) & ~(size_t)127;  // staged counts (+ up to 7 elements of alignment pad)
+    const size_t vals = (((size_t)n + 16) * 2 + 127) & ~(size_t)127;  // staged counts (+ alignment pad + a dummy slot)
     const size_t stat = sizeof(StreamSmem);
     const size_t sm_total = 228 * 1024, reserve = 1024;  // per SM; every resident CTA also reserves 1 KB
     const size_t dyn_max1 = (size_t)ctx->smem_optin - stat, dyn_max2 = sm_total / 2 - reserve - stat;

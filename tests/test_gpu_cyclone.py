@@ -280,10 +280,11 @@ def test_host_gather_path(dtype):
 
 
 @pytest.mark.parametrize("dtype,feed", [(np.float32, "auto"), (np.float32, "zerocopy"), (np.float64, "zerocopy"),
-                                        (np.float32, "gather"), (np.float32, "copy"), (np.float64, "auto")])
+                                        (np.float32, "gather"), (np.float32, "copy"), (np.float64, "both"),
+                                        (np.float32, "both")])
 def test_pinned_input_zero_copy_lane(monkeypatch, dtype, feed):
-    """A pinned host matrix is also read in place by the zero-copy gather kernel (mapped memory, marker columns
-    only), beside the host gather: every way of feeding the chunks (PP_FEED) gives the scores of the device path."""
+    """A pinned host matrix can be read in place by the zero-copy gather kernel (mapped memory, marker columns only),
+    alone or beside the host gather: every way of feeding the chunks (PP_FEED) gives the scores of the device path."""
     import torch
     from pypairs_b200.cyclone import filter_marker_pairs
     rng = np.random.default_rng(50)
