@@ -73,18 +73,24 @@ def drop_comm(device=None):
         _ffi.comm_destroy(device)
 
 
-def allgather_counts(n):
-    """int from every rank -> int64[world]."""
+def allgather_ints(values):
+    """A few ints from every rank -> int64[world, len(values)]."""
     import torch
     import torch.distributed as dist
     rank, ws = world()
+    vals = np.asarray(values, dtype=np.int64).reshape(-1)
     if ws == 1:
-        return np.array([n], dtype=np.int64)
+        return vals[None, :]
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    t = torch.tensor([int(n)], dtype=torch.int64, device=dev)
+    t = torch.from_numpy(vals).to(dev)
     parts = [torch.zeros_like(t) for _ in range(ws)]
     dist.all_gather(parts, t)
-    return np.array([int(p.item()) for p in parts], dtype=np.int64)
+    return np.stack([p.cpu().numpy() for p in parts])
+
+
+def allgather_counts(n):
+    """int from every rank -> int64[world]."""
+    return allgather_ints([int(n)])[:, 0]
 
 
 def allgather_names(names):

@@ -144,9 +144,10 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
     if marker_pairs is None:
         logg.hint("no marker pairs passed, using default cell cycle prediction marker")
         marker_pairs = datasets.default_cc_marker()
-    all_names = None
-    if local_shard and sample_names is not None and hasattr(data, "shape") and len(sample_names) != data.shape[0]:
-        all_names, sample_names = sample_names, range(data.shape[0])  # names of ALL ranks' cells: checked below
+    given_names = None
+    if local_shard and sample_names is not None and hasattr(data, "shape"):
+        # the names of this rank's cells or of ALL ranks' cells: decided below, by all ranks together
+        given_names, sample_names = sample_names, range(data.shape[0])
     raw, gene_names, sample_names = utils.parse_data(data, gene_names, sample_names)
     pairs, used = filter_marker_pairs(marker_pairs, gene_names)
     total = sum(len(p) for p in pairs.values())
@@ -172,20 +173,24 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
         _dist.ensure_comm()
         if not settings.fix_seed:  # all shards must share one stream
             seed = int(_dist.broadcast_object(seed, 0))
+        names_global = False
         if local_shard:
             begin, end = 0, raw.shape[0]
-            shard_cells = _dist.allgather_counts(raw.shape[0])
+            info = _dist.allgather_ints([raw.shape[0], len(given_names) if given_names is not None else -1])
+            shard_cells = np.ascontiguousarray(info[:, 0])
+            if given_names is not None:  # one decision for all ranks (a rank holding every cell cannot tell on its own)
+                names_global = bool(np.all(info[:, 1] == shard_cells.sum()))
+                if not names_global and not np.all(info[:, 1] == info[:, 0]):
+                    raise ValueError("local_shard: pass the sample names of this rank's cells, or of all cells, on every rank "
+                                     "(cells {}, names {})".format(info[:, 0].tolist(), info[:, 1].tolist()))
         else:
             begin, end = _dist.cell_shard(raw.shape[0], rank, ws)
             shard_cells = _dist.shard_sizes(raw.shape[0], ws)
         scores, tm = _ffi.cyclone(raw, used_idx, pair_idx, iterations, min_iter, min_pairs, rng=rng, seed=seed,
                                   row_begin=begin, n_cells=end - begin, shard_cells=shard_cells,
                                   gather_to=-1 if gather_to is None else int(gather_to))
-        if all_names is not None:
-            if len(all_names) != int(shard_cells.sum()):
-                raise ValueError("{} sample names for {} local / {} total cells".format(
-                    len(all_names), raw.shape[0], int(shard_cells.sum())))
-            sample_names = all_names
+        if given_names is not None:
+            sample_names = given_names if names_global else _dist.allgather_names(given_names)
         elif local_shard:
             sample_names = _dist.allgather_names(sample_names)
         if scores is None:  # not the receiving rank
@@ -193,8 +198,10 @@ def cyclone(data, marker_pairs=None, gene_names=None, sample_names=None, iterati
             cyclone.last_timings = tm
             return None
     else:
-        if all_names is not None:
-            raise ValueError("{} sample names for {} cells".format(len(all_names), raw.shape[0]))
+        if given_names is not None:
+            if len(given_names) != raw.shape[0]:
+                raise ValueError("{} sample names for {} cells".format(len(given_names), raw.shape[0]))
+            sample_names = given_names
         scores, tm = _ffi.cyclone(raw, used_idx, pair_idx, iterations, min_iter, min_pairs, rng=rng, seed=seed)
     df = scores_to_frame(scores, keys, sample_names)
     if utils.is_anndata(data):

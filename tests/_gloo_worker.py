@@ -19,17 +19,20 @@ settings.verbosity = 0
 calls = {"sandbag": [], "cyclone": []}
 
 
-def fake_sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, **kw):
+def fake_sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_shards=1, probe_pairs=None, **kw):
     is_dist, gather_to = bool(kw.get("dist")), kw.get("gather_to", -1)
     if is_dist:
         shard, n_shards = dist.get_rank(), dist.get_world_size()
     calls["sandbag"].append((shard, n_shards, is_dist, gather_to))
-    x = np.asarray(x, dtype=np.float64)
+    x = np.asarray(x.toarray() if hasattr(x, "toarray") else x, dtype=np.float64)
+    if np.isnan(x).any():
+        raise _ffi.PyPairsB200Error(_ffi.PP_ENAN, "NaN in the expression matrix")
     gene_cols = np.asarray(gene_cols)
     if kw.get("drop_unexpressed"):
         gene_cols = gene_cols[(x != 0).any(axis=0)[gene_cols]]
     cats = np.concatenate([np.full(n, k) for k, n in enumerate(class_sizes)])
-    res = orc.check_pairs(x[np.asarray(cell_rows)][:, gene_cols], cats, np.asarray(thresholds))
+    xs = x[np.asarray(cell_rows)][:, gene_cols]
+    res = orc.check_pairs(xs, cats, np.asarray(thresholds))
     r, c = np.where(res != -1)
     keys = (r * len(gene_cols) + c).astype(np.uint64)
     sel = ((r // 7 + c // 5) % n_shards) == shard  # some tile-like split of the pair space
@@ -42,27 +45,44 @@ def fake_sandbag(x, cell_rows, class_sizes, gene_cols, thresholds, shard=0, n_sh
         keys, cls = keys[order], cls[order]
         if gather_to >= 0 and gather_to != shard:
             keys, cls = keys[:0], cls[:0]
-    return keys, cls, {}, gene_cols.astype(np.int32)
+    out = (keys, cls, {})
+    if probe_pairs is not None:
+        pos, neg = orc.pair_counts(xs, cats, len(class_sizes), np.asarray(probe_pairs))
+        out = out + (pos.astype(np.int32), neg.astype(np.int32))
+    if kw.get("drop_unexpressed"):
+        out = out + (gene_cols.astype(np.int32),)
+    return out
 
 
 def fake_cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="mt19937", seed=2803,
-                 perm_tables=None, row_begin=0, n_cells=None, shard_cells=None, gather_to=-1, **kw):
+                 perm_tables=None, row_begin=0, n_cells=None, shard_cells=None, gather_to=-1, want_observed=False, **kw):
     calls["cyclone"].append((row_begin, n_cells, None if shard_cells is None else list(shard_cells), gather_to))
+    x = np.asarray(x.toarray() if hasattr(x, "toarray") else x, dtype=np.float64)
     if n_cells is None:
-        n_cells = np.asarray(x).shape[0] - row_begin
-    x = np.asarray(x, dtype=np.float64)[row_begin:row_begin + n_cells]
-    out = []
+        n_cells = x.shape[0] - row_begin
+    x = x[row_begin:row_begin + n_cells]
+    out, oh, ot = [], [], []
     for u, p in zip(used_idx_list, pairs_list):
         used = np.zeros(x.shape[1], dtype=bool)
         used[u] = True
-        out.append(orc.phase_scores(x, iterations, min_iter, min_pairs, p, used, seed=seed))
-    out = np.stack(out)
+        if rng == "philox":  # the emulation has no Philox stream: any deterministic per-cell function will do
+            sc, h, t = orc.phase_scores(x, iterations, min_iter, min_pairs, p, used, seed=int(seed) % 1000 + 1, return_observed=True)
+        else:
+            sc, h, t = orc.phase_scores(x, iterations, min_iter, min_pairs, p, used, seed=seed, return_observed=True)
+        out.append(sc)
+        oh.append(h)
+        ot.append(t)
+    res = [np.stack(out).reshape(len(out), n_cells), np.stack(oh).reshape(len(out), n_cells).astype(np.int32),
+           np.stack(ot).reshape(len(out), n_cells).astype(np.int32)]
     if shard_cells is not None:  # what pp_cyclone_dist does on the device: all-gather of the score columns
         assert shard_cells[dist.get_rank()] == n_cells
-        parts = [None] * dist.get_world_size()
-        dist.all_gather_object(parts, out)
-        out = np.concatenate(parts, axis=1) if gather_to < 0 or gather_to == dist.get_rank() else None
-    return out, {}
+        for i in range(3):
+            parts = [None] * dist.get_world_size()
+            dist.all_gather_object(parts, res[i])
+            res[i] = np.concatenate(parts, axis=1) if gather_to < 0 or gather_to == dist.get_rank() else None
+    if want_observed:
+        return res[0], {}, res[1], res[2]
+    return res[0], {}
 
 
 def main():
@@ -110,6 +130,18 @@ def main():
     assert loc.equals(single_s) and list(loc.index) == sn
     loc2 = pairs.cyclone(x[lo:hi], mk, gn, sn, iterations=60, min_iter=10, min_pairs=2, local_shard=True)
     assert loc2.equals(single_s)
+    # one rank holds every cell, the other none: "names of my cells" and "names of all cells" look the same to rank 0,
+    # the ranks agree on the meaning through the exchanged counts (no rank-dependent collective)
+    lo, hi = (0, n) if rank == 0 else (n, n)
+    for names_arg in (sn, sn[lo:hi]):
+        one = pairs.cyclone(x[lo:hi], mk, gn, names_arg, iterations=60, min_iter=10, min_pairs=2, local_shard=True)
+        assert one.equals(single_s)
+    try:
+        pairs.cyclone(x[lo:hi], mk, gn, sn[:5], iterations=60, min_iter=10, min_pairs=2, local_shard=True)
+        raise AssertionError("inconsistent sample names accepted")
+    except ValueError:
+        pass
+    lo, hi = (0, 40) if rank == 0 else (40, n)
     uni = ["z\u00e4{}".format(i) * (1 + i % 3) for i in range(n)]     # non-ASCII, ragged widths
     got = _dist.allgather_names(uni[lo:hi])
     assert list(got) == uni

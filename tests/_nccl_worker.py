@@ -1,11 +1,20 @@
 """Worker of tests/test_gpu_dist.py: one of WORLD_SIZE NCCL ranks, one GPU each, real kernels and real collectives.
 
 Every rank checks pairs.sandbag / pairs.cyclone under torch.distributed (pp_sandbag_dist / pp_cyclone_dist: the
-library's own NCCL collectives) against the single-GPU entry points on the same device and against the CPU oracle."""
+library's own NCCL collectives) against the single-GPU entry points on the same device and against the CPU oracle.
+
+PP_WORKER_EMULATE=1 (tests/test_host.py, no GPU): the same script over gloo with the CUDA entry points replaced by the
+oracle-backed stand-ins of tests/_gloo_worker.py -- it proves that every rank issues the same sequence of collectives
+for every scenario below (a mismatch is a deadlock on the GPU box).  A watchdog dumps the stacks and exits after
+PP_WORKER_WATCHDOG seconds."""
+import faulthandler
 import os
 import sys
 
 import numpy as np
+
+EMULATE = os.environ.get("PP_WORKER_EMULATE") == "1"
+faulthandler.dump_traceback_later(int(os.environ.get("PP_WORKER_WATCHDOG", "200")), exit=True)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,6 +27,12 @@ from pypairs_b200 import _dist, _ffi, pairs, settings  # noqa: E402
 from test_gpu_sandbag import synth  # noqa: E402
 
 settings.verbosity = 0
+FORMS = ("host", "csr") if EMULATE else ("host", "device", "csr")
+
+
+def to_form(x, form):
+    import scipy.sparse as sp
+    return x if form == "host" else torch.from_numpy(x).cuda() if form == "device" else sp.csr_matrix(x)
 
 
 def sandbag_checks(rank, ws):
@@ -41,8 +56,8 @@ def sandbag_checks(rank, ws):
         p = __import__("pypairs_b200.sandbag", fromlist=["prepare"]).prepare(x, ann, gn, sn, frac)
         k1, c1, _, kept1 = _ffi.sandbag(p["raw"], p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
                                         drop_unexpressed=True)
-        for form in ("host", "device", "csr"):
-            xin = x if form == "host" else torch.from_numpy(x).cuda() if form == "device" else sp.csr_matrix(x)
+        for form in FORMS:
+            xin = to_form(x, form)
             kd, cd, _, keptd = _ffi.sandbag(xin, p["cell_rows"], p["class_sizes"], p["gene_cols"], p["thresholds"],
                                             drop_unexpressed=True, dist=True, gather_to=-1)
             assert np.array_equal(kd, k1) and np.array_equal(cd, c1) and np.array_equal(keptd, kept1), (n, g, c, form)
@@ -105,8 +120,8 @@ def cyclone_checks(rank, ws):
                 assert np.array_equal(orc.phase_scores(x[:16], 200, 20, 5, pr[k], used[k]), s1[i][:16], equal_nan=True)
         sizes = _dist.shard_sizes(n, ws)
         b, e = _dist.cell_shard(n, rank, ws)
-        for form in ("host", "device", "csr"):
-            xin = x if form == "host" else torch.from_numpy(x).cuda() if form == "device" else sp.csr_matrix(x)
+        for form in FORMS:
+            xin = to_form(x, form)
             sd, _, ohd, otd = _ffi.cyclone(xin, ui, pi, 200, 20, 5, row_begin=b, n_cells=e - b, shard_cells=sizes,
                                            want_observed=True)
             assert np.array_equal(sd, s1, equal_nan=True) and np.array_equal(ohd, oh1) and np.array_equal(otd, ot1), form
@@ -115,7 +130,7 @@ def cyclone_checks(rank, ws):
         full = pairs.cyclone(x, markers, names, sn, iterations=200, min_iter=20, min_pairs=5)
         assert all(np.array_equal(full[k].values, s1[i], equal_nan=True) for i, k in enumerate(keys)) and list(full.index) == sn
         # local shards of unequal size (an empty one when there are fewer cells than ranks)
-        cut = [0] + [min(n, (q + 1) * (n // ws) + (5 if q == 0 else 0)) for q in range(ws - 1)] + [n]
+        cut = [0] + [min(n, (q + 1) * (n // ws) + 5) for q in range(ws - 1)] + [n]
         lo, hi = cut[rank], cut[rank + 1]
         loc = pairs.cyclone(x[lo:hi], markers, names, sn[lo:hi], iterations=200, min_iter=20, min_pairs=5, local_shard=True)
         assert loc.equals(full)
@@ -131,13 +146,21 @@ def cyclone_checks(rank, ws):
 
 def main():
     rank, ws = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", torch.cuda.current_device()))
-    assert _dist.ensure_comm() == (rank, ws) and _ffi.comm_info() == (rank, ws)
+    if EMULATE:
+        import _gloo_worker as emu
+        _ffi.sandbag, _ffi.cyclone = emu.fake_sandbag, emu.fake_cyclone
+        _dist.ensure_comm = lambda device=None: _dist.world()
+        dist.init_process_group("gloo", rank=rank, world_size=ws)
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", torch.cuda.current_device()))
+        assert _dist.ensure_comm() == (rank, ws) and _ffi.comm_info() == (rank, ws)
     sandbag_checks(rank, ws)
+    print("sandbag checks done, rank", rank, flush=True)
     cyclone_checks(rank, ws)
     dist.barrier()
-    _dist.drop_comm()
+    if not EMULATE:
+        _dist.drop_comm()
     dist.destroy_process_group()
     print("NCCL_OK rank", rank)
 

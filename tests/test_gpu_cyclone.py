@@ -253,6 +253,36 @@ def test_sandbag_then_cyclone_flow():
         assert np.array_equal(df[k].values, orc.phase_scores(y, 100, 10, 5, pr[k], us[k]), equal_nan=True)
 
 
+def test_device_resident_flow_with_marker_table():
+    """The same flow with both matrices resident on the device and the markers kept columnar (utils.MarkerTable):
+    nothing is uploaded twice, no tuples, no per-pair name look-ups -- and the frame equals the host / dict flow."""
+    import torch
+    from pypairs_b200 import pairs, utils
+    rng = np.random.default_rng(52)
+    g, sizes = 6000, {"G2M": 50, "S": 61, "G1": 70}
+    lab = np.concatenate([np.full(n, i) for i, n in enumerate(sizes.values())])
+    base = rng.normal(0.0, 1.5, g)
+    de = rng.random(g) < 0.03
+    de_class = rng.integers(0, 3, g)
+    lam = 3.0 * np.exp(base)[None, :] * np.where((lab[:, None] == de_class[None, :]) & de[None, :], 6.0, 1.0)
+    x = rng.poisson(lam).astype(np.float32)
+    y = rng.poisson(3.0 * np.exp(base)[None, :] * np.ones((77, 1))).astype(np.float32)
+    gn = ["gene{}".format(i) for i in range(g)]
+    sn, un = ["cell{}".format(i) for i in range(len(lab))], ["u{}".format(i) for i in range(77)]
+    ann = {k: np.where(lab == i)[0].tolist() for i, k in enumerate(sizes.keys())}
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    table = pairs.sandbag(xd, ann, gn, sn, fraction=0.6, as_table=True)
+    assert isinstance(table, utils.MarkerTable) and len(table) > 1000
+    df_dev = pairs.cyclone(yd, table, gn, un, iterations=200, min_iter=20, min_pairs=5)
+    markers = pairs.sandbag(x, ann, gn, sn, fraction=0.6)
+    assert list(table.to_dict().items()) == list(markers.items())
+    df_host = pairs.cyclone(y, markers, gn, un, iterations=200, min_iter=20, min_pairs=5)
+    assert df_dev.equals(df_host)
+    pr, us = orc.filter_marker_pairs(markers, gn)
+    for k in markers:
+        assert np.array_equal(df_dev[k].values[:12], orc.phase_scores(y[:12], 200, 20, 5, pr[k], us[k]), equal_nan=True)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_host_gather_path(dtype):
     """Wide host matrices (marker genes <= 1/4 of the columns): marker columns are gathered on the host into

@@ -267,6 +267,20 @@ def test_two_rank_gloo_merge():
     assert all("GLOO_OK" in o for o in outs), "\n".join(outs)
 
 
+@pytest.mark.parametrize("ws", [2, 3])
+def test_nccl_worker_scenarios_emulated(ws):
+    """The multi-rank GPU test script (tests/_nccl_worker.py) over gloo with oracle-backed kernels: every rank must
+    issue the same sequence of collectives in every scenario (empty shards, gather_to, local names, NaN, probes)."""
+    port = 31500 + os.getpid() % 2000 + ws
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(ws), PP_WORKER_EMULATE="1",
+               PP_WORKER_WATCHDOG="280")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_nccl_worker.py")], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, cwd=ROOT) for r in range(ws)]
+    outs = [p.communicate(timeout=400)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-3000:] for o in outs)
+    assert all("NCCL_OK" in o for o in outs)
+
+
 def test_evaluate_prediction_vs_reference(golden_dir):
     """pypairs/tests/test_utils.py:7-30 known answers + tables produced by the reference (sklearn)."""
     from pypairs_b200 import utils
