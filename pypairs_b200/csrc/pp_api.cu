@@ -1,7 +1,12 @@
 // pp_api.cu -- context management and the small C-ABI entry points (include/pypairs_b200.h).
+#include <ctype.h>
+#include <sched.h>
 #include <stdarg.h>
 
+#include <string.h>
+#include <stdlib.h>
 #include <algorithm>
+#include <thread>
 #include <mutex>
 
 #include <math.h>
@@ -44,6 +49,58 @@ void *pp_slab(pp_ctx *ctx, int slot, size_t bytes) {
     return ctx->slab[slot];
 }
 
+int pp_host_threads() {
+    if (const char *e = getenv("PP_HOST_THREADS")) return std::max(1, atoi(e));
+    unsigned hc = std::thread::hardware_concurrency();
+    hc = std::min(hc ? hc : 8u, 32u);
+    if (const char *e = getenv("LOCAL_WORLD_SIZE"))  // one process per GPU: share the host cores
+        hc = std::max(1u, hc / (unsigned)std::max(1, atoi(e)));
+    return (int)std::max(1u, hc);
+}
+
+int pp_copy_h2d(pp_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    constexpr size_t CHUNK = (size_t)32 << 20;
+    if (bytes == 0) return PP_OK;
+    bool pageable = false;
+    if (bytes >= 2 * CHUNK) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
+            pageable = at.type == cudaMemoryTypeUnregistered;
+        else
+            cudaGetLastError();
+    }
+    if (!pageable) {
+        PP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return PP_OK;
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (!ctx->pin_h2d[b]) PP_CUDA(cudaHostAlloc(&ctx->pin_h2d[b], CHUNK, cudaHostAllocDefault));
+        if (!ctx->pin_h2d_done[b]) PP_CUDA(cudaEventCreateWithFlags(&ctx->pin_h2d_done[b], cudaEventDisableTiming));
+    }
+    const int n_thr = std::max(1, std::min(pp_host_threads(), 8));
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += CHUNK, ++i) {
+        const int b = i & 1;
+        const size_t n = std::min(CHUNK, bytes - off);
+        if (i >= 2) PP_CUDA(cudaEventSynchronize(ctx->pin_h2d_done[b]));  // the DMA two chunks ago has drained this buffer
+        const uint8_t *s = (const uint8_t *)src + off;
+        uint8_t *d = (uint8_t *)ctx->pin_h2d[b];
+        std::vector<std::thread> pool;
+        try {
+            for (int t = 1; t < n_thr; ++t)
+                pool.emplace_back([=] { memcpy(d + n * t / n_thr, s + n * t / n_thr, n * (t + 1) / n_thr - n * t / n_thr); });
+        } catch (const std::exception &) {  // fewer threads than wished for: the caller's thread copies the rest
+        }
+        const size_t done_by_pool = n * (pool.size() + 1) / n_thr;  // parts 1 .. pool.size()
+        memcpy(d, s, n / n_thr);
+        if (pool.size() + 1 < (size_t)n_thr) memcpy(d + done_by_pool, s + done_by_pool, n - done_by_pool);
+        for (auto &th : pool) th.join();
+        PP_CUDA(cudaMemcpyAsync((uint8_t *)dst + off, d, n, cudaMemcpyHostToDevice, st));
+        PP_CUDA(cudaEventRecord(ctx->pin_h2d_done[b], st));
+    }
+    return PP_OK;
+}
+
 PP_API int pp_version(void) { return PP_ABI_VERSION; }
 
 PP_API int pp_device_count(void) {
@@ -54,6 +111,8 @@ PP_API int pp_device_count(void) {
     }
     return n;
 }
+
+static void bind_to_gpu_numa_node(int device);
 
 PP_API int pp_ctx_create(int device, pp_ctx **out) {
     if (!out) return pp_fail(nullptr, PP_EINVAL, "pp_ctx_create: out is NULL");
@@ -70,6 +129,7 @@ PP_API int pp_ctx_create(int device, pp_ctx **out) {
         return pp_fail(nullptr, PP_ECUDA, "pp_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
                        device, prop.major, prop.minor);
     PP_CUDA(cudaSetDevice(device));
+    bind_to_gpu_numa_node(device);
     pp_ctx *c = new pp_ctx();
     c->device = device;
     c->n_sm = prop.multiProcessorCount;
@@ -93,6 +153,54 @@ PP_API int pp_ctx_create(int device, pp_ctx **out) {
     return PP_OK;
 }
 
+// One process per GPU on a multi-socket host: run this thread (and the threads it starts: the gather crew, the staging
+// copies) on the cores of the GPU's own NUMA node, so that host buffers allocated from now on are local to the GPU's
+// PCIe root.  Only under a multi-rank launcher (LOCAL_WORLD_SIZE > 1) or with PP_NUMA_BIND=1; PP_NUMA_BIND=0 switches it
+// off.  Best effort: any failure leaves the affinity as it was.
+static void bind_to_gpu_numa_node(int device) {
+    const char *env = getenv("PP_NUMA_BIND");
+    const char *lws = getenv("LOCAL_WORLD_SIZE");
+    const bool want = env ? atoi(env) != 0 : (lws && atoi(lws) > 1);
+    if (!want) return;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (char *c = bus; *c; ++c) *c = (char)tolower(*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return;
+    cpu_set_t now, set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(now), &now) != 0) return;
+    int n_set = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-15,32-47"
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (CPU_ISSET(c, &now)) {  // never widen what the launcher allowed
+                CPU_SET(c, &set);
+                ++n_set;
+            }
+    }
+    if (n_set > 0) sched_setaffinity(0, sizeof(set), &set);
+}
+
 PP_API void pp_ctx_destroy(pp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -103,6 +211,10 @@ PP_API void pp_ctx_destroy(pp_ctx *ctx) {
     for (int b = 0; b < 2; ++b)
         if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->pin_h2d[b]) cudaFreeHost(ctx->pin_h2d[b]);
+        if (ctx->pin_h2d_done[b]) cudaEventDestroy(ctx->pin_h2d_done[b]);
+    }
     for (int i = 0; i < pp_ctx::N_SLABS; ++i)
         if (ctx->slab[i]) cudaFree(ctx->slab[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

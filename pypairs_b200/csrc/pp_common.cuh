@@ -36,6 +36,8 @@ struct pp_ctx {
     cudaEvent_t ev[8] = {};
     void *pin[2] = {nullptr, nullptr};  // pinned staging buffers of the host-gather path (grown on demand)
     size_t pin_bytes = 0;
+    void *pin_h2d[2] = {nullptr, nullptr};  // pinned staging ring of pp_copy_h2d (pageable sources)
+    cudaEvent_t pin_h2d_done[2] = {nullptr, nullptr};
     void *pin_out = nullptr;  // pinned staging buffer for results copied device -> host (grown on demand)
     size_t pin_out_bytes = 0;
     // grow-only device slabs for the few large buffers of a call (matrix copy, rank matrix, bit planes, ...): calls
@@ -55,6 +57,12 @@ extern thread_local std::string g_pp_err;  // errors raised without a ctx
 int pp_fail(pp_ctx *ctx, int code, const char *fmt, ...);
 // pointer to at least `bytes` of device memory in slab `slot` (contents undefined); nullptr + error on failure
 void *pp_slab(pp_ctx *ctx, int slot, size_t bytes);
+// host threads this process may use for staging work (PP_HOST_THREADS, else hardware threads / ranks on the host)
+int pp_host_threads();
+// host -> device copy on `st`.  Pinned / registered sources go straight to the DMA engine; a large PAGEABLE source is
+// copied by a few threads into a ring of pinned staging buffers, chunk by chunk, each chunk's DMA overlapping the
+// next chunk's memcpy (a plain cudaMemcpyAsync from pageable memory is staged by the driver at ~11 GB/s).
+int pp_copy_h2d(pp_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
 // host buffer for a variable-size result the caller releases with pp_free(): pinned (pool) when large, else malloc
 void *pp_result_alloc(size_t bytes, bool *pinned);
 enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, SLAB_CHUNK0 = 5, SLAB_CHUNK1 = 6, SLAB_MISC = 7, SLAB_SORT = 8, SLAB_ZC0 = 9, SLAB_ZC1 = 10 };

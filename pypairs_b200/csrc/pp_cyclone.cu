@@ -821,14 +821,7 @@ zc_gather_kernel(const T *__restrict__ x, int64_t ld, int64_t r0, int64_t nr, co
     }
 }
 
-int host_threads() {
-    if (const char *e = getenv("PP_HOST_THREADS")) return std::max(1, atoi(e));
-    unsigned hc = std::thread::hardware_concurrency();
-    hc = std::min(hc ? hc : 8u, 32u);
-    if (const char *e = getenv("LOCAL_WORLD_SIZE"))  // one process per GPU: share the host cores
-        hc = std::max(1u, hc / (unsigned)std::max(1, atoi(e)));
-    return (int)std::max(1u, hc);
-}
+int host_threads() { return pp_host_threads(); }
 
 }  // namespace
 
@@ -1051,9 +1044,12 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     //             host memory (32-byte sectors over the GPU's own PCIe link: 1 133 sectors = 36 KB instead of 80 KB per
     //             row, no host core involved): 128 ms, whatever the host is doing
     //   copy      DMA of the full rows, columns picked by the rank kernel: 151 ms pinned, 710 ms pageable
+    // With 8 ranks on one host (4 threads each, all at once; profiles/r02/feed_probe_n8_4threads.txt): gather 305-330 ms,
+    // zerocopy 176-249 ms (the ranks whose GPU sits on the other socket of the matrix are the slow ones), copy 233-352 ms.
     // So: wide matrices go through the gather, except that a pinned matrix is read in place when this process has
-    // fewer than 4 host threads (many ranks on a small host).  Running both lanes side by side (PP_FEED=both, chunks
-    // to whichever lane is free) loses on this box -- 114 ms with 16 threads --: the two contend for host memory.
+    // fewer than 4 host threads or shares the host with three or more other ranks.  Running both lanes side by side
+    // (PP_FEED=both, chunks to whichever lane is free) loses on one GPU -- 114 ms with 16 threads --: the two contend
+    // for host memory.
     // PP_FEED = gather | zerocopy | both | copy forces a way (tests, experiments).
     const bool narrow = !csr && !x_is_device && (int64_t)U * 4 <= n_cols;
     const char *feed_env = getenv("PP_FEED");
@@ -1069,7 +1065,13 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         else
             cudaGetLastError();
     }
-    if (feed == "auto") feed = !narrow ? "copy" : (xz && host_threads() < 4) ? "zerocopy" : "gather";
+    if (feed == "auto") {
+        // ranks of this job on this host (torchrun's LOCAL_WORLD_SIZE): from four on they saturate the host's memory with
+        // their gathers (8 ranks x 4 threads, 100k cells each: 305-330 ms per call against 176-249 ms for the zero-copy reads)
+        const char *lws = getenv("LOCAL_WORLD_SIZE");
+        const int local_ranks = lws ? std::max(1, atoi(lws)) : 1;
+        feed = !narrow ? "copy" : (xz && (host_threads() < 4 || local_ranks >= 4)) ? "zerocopy" : "gather";
+    }
     if (!narrow) feed = "copy";
     if (!xz && (feed == "zerocopy" || feed == "both")) feed = "gather";  // not mapped memory
     const bool zc_lane = feed == "zerocopy" || feed == "both";

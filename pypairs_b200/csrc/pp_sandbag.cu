@@ -772,7 +772,8 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         if (!(s_x = pp_slab(ctx, SLAB_X, (size_t)std::max<int64_t>(nr_local, 1) * ld * esz))) return PP_ENOMEM;
         if (nr_local > 0) {
             const size_t bytes = ((size_t)(nr_local - 1) * ld + (size_t)n_cols) * esz;  // the last row may end at n_cols
-            PP_CUDA(cudaMemcpyAsync(s_x, (const uint8_t *)x + (size_t)r0 * ld * esz, bytes, cudaMemcpyHostToDevice, st));
+            rc = pp_copy_h2d(ctx, s_x, (const uint8_t *)x + (size_t)r0 * ld * esz, bytes, st);
+            if (rc) return rc;
             ctx->tm.h2d_bytes = (int64_t)bytes;
         }
         dx_local = (const uint8_t *)s_x;
@@ -887,6 +888,64 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     std::vector<uint32_t> red(4 + (size_t)n_genes);
     PP_CUDA(cudaMemcpyAsync(red.data(), d_red.p, sizeof(uint32_t) * red.size(), cudaMemcpyDeviceToHost, st));
+
+    // ---- while the device ranks: everything about tiles and chunks that does not depend on the rank widths.
+    //      Tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain position pairs a < b).
+    const int NB_t = (int)((n_genes + 63) / 64);
+    const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB_t;
+    std::vector<TileDesc> tiles;
+    std::vector<int64_t> tile_pairs;
+    {
+        int64_t t_index = 0;
+        // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
+        // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
+        // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
+        constexpr int SUP_A = 8, SUP_B = 18;
+        for (int sa = 0; sa < TA; sa += SUP_A)
+            for (int sb = A_BLOCKS * sa; sb < TB; sb += SUP_B)
+                for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
+                    for (int tb = std::max(sb, A_BLOCKS * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
+                        if (t_index % n_shards != shard) continue;
+                        TileDesc td;
+                        td.ta = ta;
+                        td.tb = tb;
+                        td.m = td.bp = 0;  // filled in once the rank widths are known
+                        tiles.push_back(td);
+                        const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
+                        const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
+                        int64_t np_tile = std::max<int64_t>(0, a1 - a0) * std::max<int64_t>(0, b1 - b0);  // all a < all b
+                        if (b0 < a1) {  // the tile touches the diagonal
+                            np_tile = 0;
+                            for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                        }
+                        tile_pairs.push_back(np_tile);
+                    }
+    }
+    // Chunks: for every class, region after region, runs of <= words_per_chunk(bp) words of that class; one table per
+    // plane count (all of them: which ones are in use is only known later, and they are small); table 0 (one chunk
+    // per piece) serves the probe kernel.
+    std::vector<Chunk> chunks;
+    PairParams P;
+    for (int bp = 0; bp <= MAX_PLANES; ++bp) {
+        P.chunk_off[bp] = (int32_t)chunks.size();
+        const int wc = bp == 0 ? Wl : words_per_chunk(bp);
+        for (int k = 0; k < n_classes; ++k) {
+            for (int q = 0; q < wd; ++q) {
+                const int w0 = piece_w0[(size_t)q * n_classes + k], w1 = w0 + piece_w[(size_t)q * n_classes + k];
+                for (int w = w0; w < w1; w += wc) {
+                    Chunk c;
+                    c.w_begin = w;
+                    c.n_words = std::min(wc, w1 - w);
+                    c.class_end = -1;
+                    c.owner = q;
+                    chunks.push_back(c);
+                }
+            }
+            chunks.back().class_end = k;  // classes are non-empty: the last chunk pushed belongs to class k
+        }
+        P.chunk_cnt[bp] = (int32_t)chunks.size() - P.chunk_off[bp];
+    }
+    mark("tables_built");
     PP_CUDA(cudaStreamSynchronize(st));
     mark("ranked");
     if (red[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
@@ -945,67 +1004,20 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
     mark("bitslice_enqueued");
 
-    // ---- tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain position pairs a < b)
-    const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB;
-    std::vector<TileDesc> tiles;
-    int64_t t_index = 0, n_pairs_shard = 0;
+    // ---- plane counts of this shard's tiles (the tile list itself was made while the rank kernel ran)
+    int64_t n_pairs_shard = 0;
     double plane_pairs = 0.0;  // sum over the shard's gene pairs of the planes compared
-    bool bp_used[MAX_PLANES + 1] = {false};
-    // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
-    // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
-    // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
-    constexpr int SUP_A = 8, SUP_B = 18;
-    for (int sa = 0; sa < TA; sa += SUP_A)
-        for (int sb = A_BLOCKS * sa; sb < TB; sb += SUP_B)
-            for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
-                for (int tb = std::max(sb, A_BLOCKS * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
-                    if (t_index % n_shards != shard) continue;
-                    TileDesc td;
-                    td.ta = ta;
-                    td.tb = tb;
-                    const int ba = std::max(blk_bits[A_BLOCKS * ta], blk_bits[A_BLOCKS * ta + 1]), bb = blk_bits[tb];
-                    td.m = std::min(ba, bb);
-                    td.bp = td.m + (ba != bb ? 1 : 0);
-                    bp_used[td.bp] = true;
-                    tiles.push_back(td);
-                    const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
-                    const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
-                    int64_t np_tile = std::max<int64_t>(0, a1 - a0) * std::max<int64_t>(0, b1 - b0);  // all a < all b
-                    if (b0 < a1) {  // the tile touches the diagonal
-                        np_tile = 0;
-                        for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
-                    }
-                    n_pairs_shard += np_tile;
-                    plane_pairs += (double)np_tile * td.bp;
-                }
+    for (size_t t = 0; t < tiles.size(); ++t) {
+        TileDesc &td = tiles[t];
+        const int ba = std::max(blk_bits[A_BLOCKS * td.ta], blk_bits[A_BLOCKS * td.ta + 1]), bb = blk_bits[td.tb];
+        td.m = std::min(ba, bb);
+        td.bp = td.m + (ba != bb ? 1 : 0);
+        n_pairs_shard += tile_pairs[t];
+        plane_pairs += (double)tile_pairs[t] * td.bp;
+    }
     ctx->tm.n_units = n_pairs_shard;
     ctx->tm.avg_planes = n_pairs_shard > 0 ? (float)(plane_pairs / (double)n_pairs_shard) : 0.f;
 
-    // ---- chunks: for every class, region after region, runs of <= words_per_chunk(bp) words of that class; one
-    //      table per plane count in use; table 0 (one chunk per piece) serves the probe kernel
-    std::vector<Chunk> chunks;
-    PairParams P;
-    for (int bp = 0; bp <= MAX_PLANES; ++bp) {
-        P.chunk_off[bp] = (int32_t)chunks.size();
-        P.chunk_cnt[bp] = 0;
-        if (bp > 0 && !bp_used[bp]) continue;
-        const int wc = bp == 0 ? Wl : words_per_chunk(bp);
-        for (int k = 0; k < n_classes; ++k) {
-            for (int q = 0; q < wd; ++q) {
-                const int w0 = piece_w0[(size_t)q * n_classes + k], w1 = w0 + piece_w[(size_t)q * n_classes + k];
-                for (int w = w0; w < w1; w += wc) {
-                    Chunk c;
-                    c.w_begin = w;
-                    c.n_words = std::min(wc, w1 - w);
-                    c.class_end = -1;
-                    c.owner = q;
-                    chunks.push_back(c);
-                }
-            }
-            chunks.back().class_end = k;  // classes are non-empty: the last chunk pushed belongs to class k
-        }
-        P.chunk_cnt[bp] = (int32_t)chunks.size() - P.chunk_off[bp];
-    }
     const size_t dyn_smem = (size_t)STAGES * (A_BLOCKS + 1) * STAGE_PLANE_WORDS * 64 * 4;
     std::vector<int32_t> thr32(n_classes), mpd32(n_classes);
     for (int k = 0; k < n_classes; ++k) {

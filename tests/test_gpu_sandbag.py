@@ -85,6 +85,29 @@ def test_streaming_rank_path(dtype, n_cols, n_keep):
     assert e.value.code == _ffi().PP_ENAN
 
 
+def test_large_pageable_input_is_staged():
+    """A pageable host matrix of more than 64 MB goes through the threaded staging copy (pp_copy_h2d: chunks of 32 MB
+    through two pinned buffers); a pinned one and a device tensor do not -- same markers from all three."""
+    import torch
+    rng = np.random.default_rng(8)
+    x, lab = synth(rng, 1301, 13001, 3, frac_de=0.02, dtype=np.float32)  # 67.7 MB, odd sizes: a partial last chunk
+    thr = np.ceil(np.bincount(lab, minlength=3) * 0.65).astype(np.int64)
+    k_page, c_page, _ = run_kernel(x, lab, 3, thr)
+    xt = torch.from_numpy(x)
+    k_dev, c_dev, _ = run_kernel(xt.cuda(), lab, 3, thr)
+    k_pin, c_pin, _ = run_kernel(xt.pin_memory().numpy(), lab, 3, thr)
+    assert len(k_dev) > 100
+    assert np.array_equal(k_page, k_dev) and np.array_equal(c_page, c_dev)
+    assert np.array_equal(k_pin, k_dev) and np.array_equal(c_pin, c_dev)
+    sub = np.sort(rng.choice(13001, 300, replace=False))
+    rr, cc, kk = orc.sandbag_arrays(x[:, sub].astype(np.float64), lab, 3, 0.65)
+    pos = np.full(13001, -1)
+    pos[sub] = np.arange(300)
+    rows, cols = (k_page // np.uint64(13001)).astype(np.int64), (k_page % np.uint64(13001)).astype(np.int64)
+    m = (pos[rows] >= 0) & (pos[cols] >= 0)
+    assert np.array_equal(pos[rows[m]], rr) and np.array_equal(pos[cols[m]], cc) and np.array_equal(c_page[m], kk)
+
+
 @pytest.mark.parametrize("name", SANDBAG_CASE_NAMES)
 def test_golden_cases(sandbag_cases, name):
     c = sandbag_cases
