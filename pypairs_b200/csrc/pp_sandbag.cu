@@ -820,6 +820,83 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     if (n_genes < 2 || n_cells == 0) return PP_OK;  // no pairs (the same decision on every rank)
     if (n_genes > 65535) return pp_fail(ctx, PP_ELIMIT, "pp_sandbag: more than 65535 kept genes");
 
+    // ---- on a helper thread, while this one feeds the device: everything about tiles and chunks that does not depend on
+    //      the rank widths (0.4 ms of host work for cfg3, 2 ms for cfg4 -- on the critical path otherwise, at 8 GPUs the
+    //      device work before the pair kernel is shorter than that).
+    //      Tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain position pairs a < b).
+    const int NB_t = (int)((n_genes + 63) / 64);
+    const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB_t;
+    std::vector<TileDesc> tiles;
+    std::vector<int64_t> tile_pairs;
+    std::vector<Chunk> chunks;
+    PairParams P;
+    bool tables_failed = false;
+    auto build_tables = [&]() {
+        try {
+            {
+                int64_t t_index = 0;
+                // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
+                // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
+                // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
+                constexpr int SUP_A = 8, SUP_B = 18;
+                for (int sa = 0; sa < TA; sa += SUP_A)
+                    for (int sb = A_BLOCKS * sa; sb < TB; sb += SUP_B)
+                        for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
+                            for (int tb = std::max(sb, A_BLOCKS * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
+                                if (t_index % n_shards != shard) continue;
+                                TileDesc td;
+                                td.ta = ta;
+                                td.tb = tb;
+                                td.m = td.bp = 0;  // filled in once the rank widths are known
+                                tiles.push_back(td);
+                                const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
+                                const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
+                                int64_t np_tile = std::max<int64_t>(0, a1 - a0) * std::max<int64_t>(0, b1 - b0);  // all a < all b
+                                if (b0 < a1) {  // the tile touches the diagonal
+                                    np_tile = 0;
+                                    for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
+                                }
+                                tile_pairs.push_back(np_tile);
+                            }
+            }
+            // Chunks: for every class, region after region, runs of <= words_per_chunk(bp) words of that class; one table per
+            // plane count (all of them: which ones are in use is only known later, and they are small); table 0 (one chunk
+            // per piece) serves the probe kernel.
+            for (int bp = 0; bp <= MAX_PLANES; ++bp) {
+                P.chunk_off[bp] = (int32_t)chunks.size();
+                const int wc = bp == 0 ? Wl : words_per_chunk(bp);
+                for (int k = 0; k < n_classes; ++k) {
+                    for (int q = 0; q < wd; ++q) {
+                        const int w0 = piece_w0[(size_t)q * n_classes + k], w1 = w0 + piece_w[(size_t)q * n_classes + k];
+                        for (int w = w0; w < w1; w += wc) {
+                            Chunk c;
+                            c.w_begin = w;
+                            c.n_words = std::min(wc, w1 - w);
+                            c.class_end = -1;
+                            c.owner = q;
+                            chunks.push_back(c);
+                        }
+                    }
+                    chunks.back().class_end = k;  // classes are non-empty: the last chunk pushed belongs to class k
+                }
+                P.chunk_cnt[bp] = (int32_t)chunks.size() - P.chunk_off[bp];
+            }
+        } catch (const std::exception &) {
+            tables_failed = true;
+        }
+    };
+    struct Joiner {  // joined on every exit path
+        std::thread t;
+        ~Joiner() {
+            if (t.joinable()) t.join();
+        }
+    } table_thread;
+    try {
+        table_thread.t = std::thread(build_tables);
+    } catch (const std::exception &) {
+        build_tables();  // no thread to be had: build them here
+    }
+
     // ---- my slots: row (relative to my block) of every cell of my pieces, -1 = padding cell
     const int64_t n_slots = (int64_t)W_me * 32;
     std::vector<int32_t> slots((size_t)std::max<int64_t>(n_slots, 1), -1);
@@ -889,63 +966,6 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     std::vector<uint32_t> red(4 + (size_t)n_genes);
     PP_CUDA(cudaMemcpyAsync(red.data(), d_red.p, sizeof(uint32_t) * red.size(), cudaMemcpyDeviceToHost, st));
 
-    // ---- while the device ranks: everything about tiles and chunks that does not depend on the rank widths.
-    //      Tiles of this shard: (ta, tb) with tb >= A_BLOCKS * ta (only those contain position pairs a < b).
-    const int NB_t = (int)((n_genes + 63) / 64);
-    const int TA = (int)((n_genes + TILE_A - 1) / TILE_A), TB = NB_t;
-    std::vector<TileDesc> tiles;
-    std::vector<int64_t> tile_pairs;
-    {
-        int64_t t_index = 0;
-        // Super-tile order: the ~n_sm tiles that run at the same time come from one SUP_A x SUP_B patch of the tile
-        // grid, so they share their 2*SUP_A + SUP_B operand blocks through L2 instead of streaming each operand
-        // from HBM once per tile (ncu: 11.7 GB of DRAM reads per cfg3 launch in row-major tile order).
-        constexpr int SUP_A = 8, SUP_B = 18;
-        for (int sa = 0; sa < TA; sa += SUP_A)
-            for (int sb = A_BLOCKS * sa; sb < TB; sb += SUP_B)
-                for (int ta = sa; ta < std::min(sa + SUP_A, TA); ++ta)
-                    for (int tb = std::max(sb, A_BLOCKS * ta); tb < std::min(sb + SUP_B, TB); ++tb, ++t_index) {
-                        if (t_index % n_shards != shard) continue;
-                        TileDesc td;
-                        td.ta = ta;
-                        td.tb = tb;
-                        td.m = td.bp = 0;  // filled in once the rank widths are known
-                        tiles.push_back(td);
-                        const int64_t a0 = (int64_t)ta * TILE_A, a1 = std::min<int64_t>(a0 + TILE_A, n_genes);
-                        const int64_t b0 = (int64_t)tb * TILE_B, b1 = std::min<int64_t>(b0 + TILE_B, n_genes);
-                        int64_t np_tile = std::max<int64_t>(0, a1 - a0) * std::max<int64_t>(0, b1 - b0);  // all a < all b
-                        if (b0 < a1) {  // the tile touches the diagonal
-                            np_tile = 0;
-                            for (int64_t a = a0; a < a1; ++a) np_tile += std::max<int64_t>(0, b1 - std::max(b0, a + 1));
-                        }
-                        tile_pairs.push_back(np_tile);
-                    }
-    }
-    // Chunks: for every class, region after region, runs of <= words_per_chunk(bp) words of that class; one table per
-    // plane count (all of them: which ones are in use is only known later, and they are small); table 0 (one chunk
-    // per piece) serves the probe kernel.
-    std::vector<Chunk> chunks;
-    PairParams P;
-    for (int bp = 0; bp <= MAX_PLANES; ++bp) {
-        P.chunk_off[bp] = (int32_t)chunks.size();
-        const int wc = bp == 0 ? Wl : words_per_chunk(bp);
-        for (int k = 0; k < n_classes; ++k) {
-            for (int q = 0; q < wd; ++q) {
-                const int w0 = piece_w0[(size_t)q * n_classes + k], w1 = w0 + piece_w[(size_t)q * n_classes + k];
-                for (int w = w0; w < w1; w += wc) {
-                    Chunk c;
-                    c.w_begin = w;
-                    c.n_words = std::min(wc, w1 - w);
-                    c.class_end = -1;
-                    c.owner = q;
-                    chunks.push_back(c);
-                }
-            }
-            chunks.back().class_end = k;  // classes are non-empty: the last chunk pushed belongs to class k
-        }
-        P.chunk_cnt[bp] = (int32_t)chunks.size() - P.chunk_off[bp];
-    }
-    mark("tables_built");
     PP_CUDA(cudaStreamSynchronize(st));
     mark("ranked");
     if (red[1]) return pp_fail(ctx, PP_ENAN, "pp_sandbag: NaN in the expression matrix");
@@ -1004,7 +1024,10 @@ static int sandbag_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaEventRecord(ctx->ev[2], st));
     mark("bitslice_enqueued");
 
-    // ---- plane counts of this shard's tiles (the tile list itself was made while the rank kernel ran)
+    // ---- plane counts of this shard's tiles (the tile list itself was made on the helper thread meanwhile)
+    if (table_thread.t.joinable()) table_thread.t.join();
+    if (tables_failed) return pp_fail(ctx, PP_ENOMEM, "pp_sandbag: host allocation of the tile tables failed");
+    mark("tables_joined");
     int64_t n_pairs_shard = 0;
     double plane_pairs = 0.0;  // sum over the shard's gene pairs of the planes compared
     for (size_t t = 0; t < tiles.size(); ++t) {
