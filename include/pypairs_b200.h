@@ -102,6 +102,13 @@ int pp_ctx_create(int device, pp_ctx **out);
 void pp_ctx_destroy(pp_ctx *ctx);
 const char *pp_last_error(pp_ctx *ctx);
 void pp_free(void *p);
+/*
+ * pp_alloc_result -- host memory for an output array the caller passes to pp_cyclone* (out_scores, out_obs_*): blocks
+ * of 64 KB and more come pinned from the library's pool, so the device -> host copy of the result lands in them
+ * directly (no staging copy, no page faults of a fresh allocation); any other host pointer works too, through a
+ * staging buffer.  Released with pp_free().  NULL if the allocation fails.
+ */
+void *pp_alloc_result(size_t bytes);
 int pp_get_timings(pp_ctx *ctx, pp_timings *out);
 
 /*

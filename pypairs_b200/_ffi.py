@@ -21,7 +21,7 @@ SYMBOLS = ["pp_version", "pp_device_count", "pp_ctx_create", "pp_ctx_destroy", "
            "pp_get_timings", "pp_sandbag", "pp_sandbag_csr", "pp_cyclone", "pp_cyclone_csr", "pp_phase_scores",
            "pp_perm_table", "pp_dense_rank", "pp_alu_peak", "pp_nccl_load", "pp_nccl_version", "pp_comm_unique_id",
            "pp_comm_init", "pp_comm_destroy", "pp_comm_info", "pp_sandbag_dist", "pp_sandbag_csr_dist",
-           "pp_cyclone_dist", "pp_cyclone_csr_dist", "pp_score_labels"]
+           "pp_cyclone_dist", "pp_cyclone_csr_dist", "pp_score_labels", "pp_alloc_result"]
 
 
 class Csr(ctypes.Structure):
@@ -71,6 +71,8 @@ def load():
     lib.pp_last_error.restype = c.c_char_p
     lib.pp_free.argtypes = [vp]
     lib.pp_free.restype = None
+    lib.pp_alloc_result.argtypes = [c.c_size_t]
+    lib.pp_alloc_result.restype = vp
     lib.pp_get_timings.argtypes = [vp, c.POINTER(Timings)]
     lib.pp_sandbag.argtypes = [vp, vp, c.c_int, c.c_int, i64, i64, i64, vp, i64, vp, i32, vp, i64, vp, i32, i32,
                                c.POINTER(vp), c.POINTER(vp), c.POINTER(i64), vp, i64, vp, vp, i32, c.POINTER(vp),
@@ -344,6 +346,18 @@ def _adopt(ptr, dtype, n):
     return np.frombuffer(buf, dtype=dtype, count=n)
 
 
+def _result_array(shape, dtype):
+    """Uninitialised output array for the library to fill: pinned memory from the library's pool when it is large (the
+    result is copied into it by the DMA engine, no staging copy and no page faults of a fresh allocation)."""
+    n = int(np.prod(shape))
+    nbytes = n * np.dtype(dtype).itemsize
+    if nbytes >= (64 << 10):
+        p = load().pp_alloc_result(nbytes)
+        if p:
+            return _adopt(ctypes.c_void_p(p), dtype, n).reshape(shape)
+    return np.empty(shape, dtype=dtype)
+
+
 def score_labels(scores, idx_g1=-1, idx_g2m=-1):
     """(max_class codes, cc codes or None) of pp_score_labels for float64[C, N] scores."""
     lib = load()
@@ -403,9 +417,9 @@ def cyclone(x, used_idx_list, pairs_list, iterations, min_iter, min_pairs, rng="
             raise ValueError("shard_cells has {} entries for {} ranks".format(len(shard_cells), world))
         receive = gather_to < 0 or gather_to == me
         n_out = int(shard_cells.sum())
-    scores = np.empty((nc, n_out), dtype=np.float64) if receive else None
-    oh = np.empty((nc, n_out), dtype=np.int32) if want_observed and receive else None
-    ot = np.empty((nc, n_out), dtype=np.int32) if want_observed and receive else None
+    scores = _result_array((nc, n_out), np.float64) if receive else None
+    oh = _result_array((nc, n_out), np.int32) if want_observed and receive else None
+    ot = _result_array((nc, n_out), np.int32) if want_observed and receive else None
     head = (row_begin, n_cells, nc, _ptr(used), _ptr(used_off), _ptr(pairs), _ptr(pair_off), iterations, min_iter,
             min_pairs, _RNG[rng], seed, _ptr(tabs))
     outs = (_ptr(scores), _ptr(oh), _ptr(ot))

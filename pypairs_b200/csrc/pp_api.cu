@@ -284,6 +284,18 @@ void *pp_result_alloc(size_t bytes, bool *pinned) {
     return malloc(bytes);
 }
 
+PP_API void *pp_alloc_result(size_t bytes) { return pp_result_alloc(bytes, nullptr); }
+
+bool pp_is_pinned_host(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 PP_API void pp_free(void *p) {
     if (!p) return;
     {

@@ -65,6 +65,7 @@ int pp_host_threads();
 int pp_copy_h2d(pp_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStream_t st);
 // host buffer for a variable-size result the caller releases with pp_free(): pinned (pool) when large, else malloc
 void *pp_result_alloc(size_t bytes, bool *pinned);
+bool pp_is_pinned_host(const void *p);  // pinned / registered host memory (a DMA target without staging)
 enum { SLAB_X = 0, SLAB_RANK = 1, SLAB_PLANES = 2, SLAB_OUT = 3, SLAB_OUT2 = 4, SLAB_CHUNK0 = 5, SLAB_CHUNK1 = 6, SLAB_MISC = 7, SLAB_SORT = 8, SLAB_ZC0 = 9, SLAB_ZC1 = 10 };
 
 #define PP_CUDA(call)                                                                              \

@@ -894,6 +894,7 @@ static int cyclone_gather(pp_ctx *ctx, const double *d_scores, const int32_t *d_
     // receiving ranks: shards laid side by side on the device ([n_classes][all cells] per array), one copy to pinned
     // staging, then into the caller's arrays
     uint8_t *stage = nullptr;
+    bool direct = false;
     const size_t sc_all = sizeof(double) * (size_t)n_classes * n_total, ob_all = sizeof(int32_t) * (size_t)n_classes * n_total;
     const size_t all_bytes = sc_all + (want_oh ? ob_all : 0) + (want_ot ? ob_all : 0);
     if (receive && all_bytes) {
@@ -916,16 +917,25 @@ static int cyclone_gather(pp_ctx *ctx, const double *d_scores, const int32_t *d_
             }
             off += nq;
         }
-        if (ctx->pin_out_bytes < all_bytes) {
-            if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
-            ctx->pin_out = nullptr;
-            ctx->pin_out_bytes = 0;
-            const size_t want = std::max<size_t>(all_bytes * 2, (size_t)8 << 20);
-            PP_CUDA(cudaHostAlloc(&ctx->pin_out, want, cudaHostAllocDefault));
-            ctx->pin_out_bytes = want;
+        direct = pp_is_pinned_host(out_scores) && (!want_oh || pp_is_pinned_host(out_obs_hits)) &&
+                 (!want_ot || pp_is_pinned_host(out_obs_total));
+        if (direct) {  // the caller's arrays are pinned (pp_alloc_result): no staging
+            PP_CUDA(cudaMemcpyAsync(out_scores, d_full, sc_all, cudaMemcpyDeviceToHost, st));
+            if (want_oh) PP_CUDA(cudaMemcpyAsync(out_obs_hits, d_full + sc_all, ob_all, cudaMemcpyDeviceToHost, st));
+            if (want_ot)
+                PP_CUDA(cudaMemcpyAsync(out_obs_total, d_full + sc_all + (want_oh ? ob_all : 0), ob_all, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (ctx->pin_out_bytes < all_bytes) {
+                if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
+                ctx->pin_out = nullptr;
+                ctx->pin_out_bytes = 0;
+                const size_t want = std::max<size_t>(all_bytes * 2, (size_t)8 << 20);
+                PP_CUDA(cudaHostAlloc(&ctx->pin_out, want, cudaHostAllocDefault));
+                ctx->pin_out_bytes = want;
+            }
+            stage = (uint8_t *)ctx->pin_out;
+            PP_CUDA(cudaMemcpyAsync(stage, d_full, all_bytes, cudaMemcpyDeviceToHost, st));
         }
-        stage = (uint8_t *)ctx->pin_out;
-        PP_CUDA(cudaMemcpyAsync(stage, d_full, all_bytes, cudaMemcpyDeviceToHost, st));
     }
     PP_CUDA(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
     PP_CUDA(cudaEventRecord(ctx->ev[5], st));
@@ -1573,10 +1583,12 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
                             n_classes, shard_cells, gather_to, out_scores, out_obs_hits, out_obs_total, want_oh, want_ot);
         if (rc) return rc;
     } else {
-    // results: device -> pinned staging -> the caller's (pageable) arrays; a direct copy would be staged by the driver
-    // at a fraction of the rate
+    // results: straight into the caller's arrays when they are pinned (pp_alloc_result), else device -> pinned staging ->
+    // the caller's pageable arrays (a direct copy would be staged by the driver at a fraction of the rate)
     const size_t sc_bytes = sizeof(double) * out_cnt, ob_bytes = sizeof(int32_t) * out_cnt;
-    const size_t stage_bytes = sc_bytes + (want_oh ? ob_bytes : 0) + (want_ot ? ob_bytes : 0) + 16;
+    const bool direct = pp_is_pinned_host(out_scores) && (!want_oh || pp_is_pinned_host(out_obs_hits)) &&
+                        (!want_ot || pp_is_pinned_host(out_obs_total));
+    const size_t stage_bytes = (direct ? 0 : sc_bytes + (want_oh ? ob_bytes : 0) + (want_ot ? ob_bytes : 0)) + 16;
     if (ctx->pin_out_bytes < stage_bytes) {
         if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
         ctx->pin_out = nullptr;
@@ -1587,7 +1599,9 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     }
     uint8_t *stage_p = (uint8_t *)ctx->pin_out;
     int32_t *flags = (int32_t *)stage_p;
-    uint8_t *st_sc = stage_p + 16, *st_oh = st_sc + sc_bytes, *st_ot = st_oh + (want_oh ? ob_bytes : 0);
+    uint8_t *st_sc = direct ? (uint8_t *)out_scores : stage_p + 16;
+    uint8_t *st_oh = direct ? (uint8_t *)out_obs_hits : st_sc + sc_bytes;
+    uint8_t *st_ot = direct ? (uint8_t *)out_obs_total : st_oh + (want_oh ? ob_bytes : 0);
     PP_CUDA(cudaMemcpyAsync(st_sc, d_scores.p, sc_bytes, cudaMemcpyDeviceToHost, st));
     if (want_oh) PP_CUDA(cudaMemcpyAsync(st_oh, d_oh.p, ob_bytes, cudaMemcpyDeviceToHost, st));
     if (want_ot) PP_CUDA(cudaMemcpyAsync(st_ot, d_ot.p, ob_bytes, cudaMemcpyDeviceToHost, st));
@@ -1595,9 +1609,11 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     PP_CUDA(cudaEventRecord(ctx->ev[5], st));
     PP_CUDA(cudaStreamSynchronize(st));
     if (flags[1]) return pp_fail(ctx, PP_ENAN, "pp_cyclone: NaN in the expression matrix");
-    memcpy(out_scores, st_sc, sc_bytes);
-    if (want_oh) memcpy(out_obs_hits, st_oh, ob_bytes);
-    if (want_ot) memcpy(out_obs_total, st_ot, ob_bytes);
+    if (!direct) {
+        memcpy(out_scores, st_sc, sc_bytes);
+        if (want_oh) memcpy(out_obs_hits, st_oh, ob_bytes);
+        if (want_ot) memcpy(out_obs_total, st_ot, ob_bytes);
+    }
     }
     if (pipelined) {  // copies overlap compute: h2d = copy-stream span, main = sum of the score launches
         ctx->tm.h2d_ms = copy_ms;
