@@ -187,7 +187,8 @@ static void bind_to_gpu_numa_node(int device) {
     CPU_ZERO(&set);
     if (sched_getaffinity(0, sizeof(now), &now) != 0) return;
     int n_set = 0;
-    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-15,32-47"
+    char *save = nullptr;
+    for (char *tok = strtok_r(list, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {  // "0-15,32-47"
         int a = 0, b = 0;
         const int k = sscanf(tok, "%d-%d", &a, &b);
         if (k < 1) continue;

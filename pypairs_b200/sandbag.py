@@ -58,10 +58,8 @@ def markers_to_dict(keys, cls, n_genes, gene_names, class_names):
     k64 = np.ascontiguousarray(keys).view(np.int64)  # keys < 2^32: the signed view is exact and divides faster
     rows, cols = k64 // n_genes, k64 % n_genes
     names = list(gene_names)  # the np.str_ scalars `gene_names[g]` yields, made once
-    # classes in order of first appearance in the scan: with repeated indices the last write wins, so writing
-    # the positions in reverse leaves the smallest position of every class
-    first = np.full(len(class_names), len(cls), dtype=np.int64)
-    first[cls[::-1]] = np.arange(len(cls) - 1, -1, -1)
+    # classes in order of first appearance in the scan: smallest position of every class
+    first = utils.first_positions(cls, len(class_names))
     per_class = utils.pair_lists(names, rows, cols, cls, len(class_names))
     out = {}
     for k in np.argsort(first, kind="stable"):

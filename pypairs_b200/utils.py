@@ -22,6 +22,21 @@ except ImportError:  # pragma: no cover
     _c_pair_list = _c_pair_lists = None
 
 
+def first_positions(cls, n_classes):
+    """Position of the first entry of every class in `cls` (len(cls) for a class that does not occur)."""
+    cls = np.asarray(cls)
+    first = np.full(n_classes, len(cls), dtype=np.int64)
+    if n_classes <= 16:  # a handful of vectorised scans
+        for k in range(n_classes):
+            hit = cls == k
+            i = int(hit.argmax()) if len(cls) else 0
+            if len(cls) and hit[i]:
+                first[k] = i
+    else:
+        np.minimum.at(first, cls, np.arange(len(cls), dtype=np.int64))
+    return first
+
+
 def pair_lists(names, rows, cols, cls, n_classes):
     """Per class k the list of (names[rows[i]], names[cols[i]]) over the entries with cls[i] == k, input order kept."""
     names = names if isinstance(names, list) else list(names)
@@ -255,8 +270,7 @@ class MarkerTable(object):
 
     def class_order(self):
         """Class indices in order of first appearance (the reference's dict key order)."""
-        first = np.full(len(self.class_names), len(self.cls), dtype=np.int64)
-        first[self.cls[::-1]] = np.arange(len(self.cls) - 1, -1, -1)
+        first = first_positions(self.cls, len(self.class_names))
         return [int(k) for k in np.argsort(first, kind="stable") if first[k] < len(self.cls)]
 
     def keys(self):
