@@ -163,6 +163,20 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Lanes of the warp that hold the same 8-bit digit as this lane (valid lanes only; an invalid lane gets 0).
+// `match.any` does this in one instruction, but the hardware iterates once per DISTINCT value in the warp: with random
+// digits that is ~30 rounds, ~600 cycles per call (ncu on the radix passes: half of all stall samples sat on its
+// consumer).  Eight ballots, one per digit bit, are independent and pipeline: ~10x faster.
+__device__ __forceinline__ uint32_t warp_digit_peers(uint32_t d, bool valid) {
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return valid ? peers : 0u;
+}
 __device__ __forceinline__ uint32_t lop3_gt(uint32_t a, uint32_t b, uint32_t g) {
     // (a & ~b) | (~(a ^ b) & g) : "a > b" carried from the less significant planes
     uint32_t r;

@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(RANK_THREADS)
 rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cell_rows, int64_t n_slots,
             const int32_t *__restrict__ gene_cols, int n, uint16_t *__restrict__ rank_out, int64_t rank_ld,
             uint8_t *__restrict__ scratch, size_t scratch_per_cta, int32_t *__restrict__ flags,
-            const int32_t *__restrict__ todo, const int32_t *__restrict__ ctl) {
+            const int32_t *__restrict__ todo, const int32_t *__restrict__ ctl, int32_t *__restrict__ todo2,
+            int32_t *__restrict__ ctl2) {
     typedef typename KeyOf<T>::type K;
     __shared__ RankSmem sm;
     extern __shared__ __align__(16) uint16_t vals[];  // [n] staged counts of the fast path
@@ -273,6 +274,11 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                 continue;
             }
         }
+        // ---- cells that need a full sort go to rank_sort_kernel (keys sorted in shared memory) when the caller set it up
+        if (todo2 != nullptr) {
+            if (tid == 0) todo2[atomicAdd(&ctl2[1], 1)] = (int32_t)slot;
+            continue;
+        }
         // ---- 1. gather + key transform, find the key bits that vary
         bool nan = false;
         K first = key_of(xr[gene_cols[0]], nan);
@@ -309,7 +315,7 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                 const int i = ib + lane;
                 const bool valid = i < hi;
                 uint32_t d = valid ? ((uint32_t)(kin[i] >> shift) & 255u) : (256u + lane);
-                uint32_t peers = __match_any_sync(0xffffffffu, d);
+                uint32_t peers = warp_digit_peers(d, valid);
                 if (valid && lane == __ffs(peers) - 1) sm.whist[warp][d] += __popc(peers);
                 __syncwarp();
             }
@@ -352,7 +358,7 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
                 K k = valid ? kin[i] : (K)0;
                 uint16_t ix = valid ? iin[i] : (uint16_t)0;
                 uint32_t d = valid ? ((uint32_t)(k >> shift) & 255u) : (256u + lane);
-                uint32_t peers = __match_any_sync(0xffffffffu, d);
+                uint32_t peers = warp_digit_peers(d, valid);
                 uint32_t base = valid ? sm.whist[warp][d] : 0u;
                 uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
                 if (valid) {
@@ -395,6 +401,198 @@ rank_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cel
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Full sort in SHARED memory (tie-free / real-valued cells; round 2).  rank_kernel's sort path ping-pongs keys + indices
+// through a global scratch in ~40 sequential steps per warp and pass, each waiting for L2 and for a warp-wide digit
+// match: 630 us per cfg3 cell.  Here only the KEYS are sorted -- two shared-memory buffers, stable LSD radix over the
+// varying bytes, warp-contiguous ranges with per-warp digit histograms, digit peers from eight ballots (`match.any`
+// iterates once per distinct digit: half of all stall samples of the first version sat behind it), up to 32 warps so that
+// a warp walks few steps --, then the distinct keys are compacted and every gene's dense rank is a branch-free binary
+// search in that array, eight look-ups interleaved (the row is re-read from L2).
+// (Tried: a bitonic network in place of the radix passes -- no dependent chains, but 120 steps x 32 768 keys are bound by
+// shared-memory bandwidth: 250 us per cfg3 cell against 100.)
+// Used when 2 n keys fit in shared memory (float32: n <= ~24 000; float64: ~12 000); else rank_kernel sorts.
+// ------------------------------------------------------------------------------------------------
+template <int NW> struct alignas(16) SortSmem {
+    uint32_t whist[NW][256];
+    uint32_t dig_total[256];
+    uint32_t wtot[NW];
+    unsigned long long vary[NW];
+    unsigned long long vary_all;
+};
+
+// NW warps per CTA: 32 for long rows (a warp walks its range in steps of 32 keys, one after the other: few steps per
+// warp), 8 for short ones (small CTAs, many cells in flight per SM)
+template <typename T, int NW>
+__global__ void __launch_bounds__(NW * 32)
+rank_sort_kernel(const T *__restrict__ x, int64_t ld, const int32_t *__restrict__ cell_rows,
+                 const int32_t *__restrict__ gene_cols, int n, uint16_t *__restrict__ rank_out, int64_t rank_ld,
+                 int32_t *__restrict__ flags, const int32_t *__restrict__ todo2, const int32_t *__restrict__ ctl2) {
+    typedef typename KeyOf<T>::type K;
+    __shared__ SortSmem<NW> sm;
+    extern __shared__ __align__(16) uint8_t sort_dyn[];
+    const int n_al = (n + 31) & ~31;
+    K *bufA = reinterpret_cast<K *>(sort_dyn), *bufB = bufA + n_al;
+    constexpr int NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_warp = ((n + NW * 32 - 1) / (NW * 32)) * 32;
+    const int lo = min(warp * per_warp, n), hi = min(lo + per_warp, n);
+    const int n_work = ctl2[1];
+    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int64_t slot = todo2[wi];
+        uint16_t *out = rank_out + slot * rank_ld;
+        const T *xr = x + (int64_t)cell_rows[slot] * ld;
+        // ---- 1. keys (eight independent loads in flight per thread: the row comes from DRAM) and the key bits that vary
+        bool nan = false;
+        const K first = key_of(xr[gene_cols[0]], nan);
+        K vary = 0;
+        for (int g0 = tid; g0 < n; g0 += NT * 8) {
+            T v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int g = g0 + j * NT;
+                v[j] = g < n ? xr[gene_cols[g]] : (T)0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int g = g0 + j * NT;
+                if (g < n) {
+                    const K k = key_of(v[j], nan);
+                    bufA[g] = k;
+                    vary |= (k ^ first);
+                }
+            }
+        }
+        if (nan) flags[1] = 1;
+        unsigned long long v64 = (unsigned long long)vary;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v64 |= __shfl_xor_sync(0xffffffffu, v64, o);
+        if (lane == 0) sm.vary[warp] = v64;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long a = 0;
+            for (int w = 0; w < NW; ++w) a |= sm.vary[w];
+            sm.vary_all = a;
+        }
+        __syncthreads();
+        const unsigned long long vary_all = sm.vary_all;
+        K *kin = bufA, *kout = bufB;
+        // ---- 2. stable LSD radix passes over the varying bytes
+        for (int byte = 0; byte < (int)sizeof(K); ++byte) {
+            if (((vary_all >> (8 * byte)) & 0xffull) == 0) continue;
+            const int shift = 8 * byte;
+            for (int i = tid; i < NW * 256; i += NT) (&sm.whist[0][0])[i] = 0;
+            __syncthreads();
+            for (int ib = lo; ib < hi; ib += 32) {
+                const int i = ib + lane;
+                const bool valid = i < hi;
+                const uint32_t d = valid ? ((uint32_t)(kin[i] >> shift) & 255u) : 0u;
+                const uint32_t peers = warp_digit_peers(d, valid);
+                if (valid && lane == __ffs(peers) - 1) sm.whist[warp][d] += __popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t t = 0;
+                for (int w = 0; w < NW; ++w) t += sm.whist[w][tid];
+                sm.dig_total[tid] = t;
+            }
+            __syncthreads();
+            if (warp == 0) {  // exclusive scan of the 256 digit totals, 8 per lane
+                uint32_t v[8], t = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[j] = sm.dig_total[lane * 8 + j]; t += v[j]; }
+                uint32_t incl = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                uint32_t run = incl - t;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { sm.dig_total[lane * 8 + j] = run; run += v[j]; }
+            }
+            __syncthreads();
+            if (tid < 256) {  // digit-major, warp-minor start offsets
+                uint32_t run = sm.dig_total[tid];
+                for (int w = 0; w < NW; ++w) {
+                    const uint32_t c = sm.whist[w][tid];
+                    sm.whist[w][tid] = run;
+                    run += c;
+                }
+            }
+            __syncthreads();
+            for (int ib = lo; ib < hi; ib += 32) {
+                const int i = ib + lane;
+                const bool valid = i < hi;
+                const K k = valid ? kin[i] : (K)0;
+                const uint32_t d = valid ? ((uint32_t)(k >> shift) & 255u) : 0u;
+                const uint32_t peers = warp_digit_peers(d, valid);
+                const uint32_t base = valid ? sm.whist[warp][d] : 0u;
+                if (valid) kout[base + __popc(peers & ((1u << lane) - 1u))] = k;
+                __syncwarp();
+                if (valid && lane == __ffs(peers) - 1) sm.whist[warp][d] = base + __popc(peers);
+                __syncwarp();
+            }
+            __syncthreads();
+            K *t = kin; kin = kout; kout = t;
+        }
+        // ---- 3. the distinct keys, compacted into the other buffer
+        uint32_t cnt = 0;
+        for (int ib = lo; ib < hi; ib += 32) {
+            const int i = ib + lane;
+            const bool head = (i < hi) && (i == 0 || kin[i] != kin[i - 1]);
+            cnt += __popc(__ballot_sync(0xffffffffu, head));
+        }
+        if (lane == 0) sm.wtot[warp] = cnt;
+        __syncthreads();
+        uint32_t base = 0, D = 0;
+        for (int w = 0; w < NW; ++w) {
+            if (w < warp) base += sm.wtot[w];
+            D += sm.wtot[w];
+        }
+        for (int ib = lo; ib < hi; ib += 32) {
+            const int i = ib + lane;
+            const bool head = (i < hi) && (i == 0 || kin[i] != kin[i - 1]);
+            const uint32_t b = __ballot_sync(0xffffffffu, head);
+            if (head) kout[base + __popc(b & ((1u << lane) - 1u))] = kin[i];
+            base += __popc(b);
+        }
+        if (tid == 0) atomicMax(&flags[0], (int)D - 1);
+        __syncthreads();
+        // ---- 4. dense rank = position of the gene's key among the distinct keys
+        int steps = 0;  // ceil(log2(D)) halvings find the lower bound
+        while ((1u << steps) < D) ++steps;
+        for (int g0 = tid; g0 < n; g0 += NT * 8) {  // eight look-ups interleaved: loads (L2) and probes (shared memory) overlap
+            K k[8];
+            int pos[8], len[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int g = g0 + j * NT;
+                bool dummy = false;
+                k[j] = key_of(g < n ? xr[gene_cols[g]] : (T)0, dummy);
+                pos[j] = 0;
+                len[j] = (int)D;
+            }
+            for (int st = 0; st <= steps; ++st) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // branch-free lower bound: [pos, pos + len) always holds the answer
+                    const int half = len[j] >> 1;
+                    const bool right = len[j] > 0 && kout[pos[j] + half] < k[j];
+                    pos[j] = right ? pos[j] + half + 1 : pos[j];
+                    len[j] = right ? len[j] - half - 1 : half;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int g = g0 + j * NT;
+                if (g < n) out[g] = (uint16_t)pos[j];
+            }
+        }
+        __syncthreads();  // buffers reused by the next cell
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Streaming form of the count fast path for DENSE column spans (sandbag: all / almost all genes of a row; the
@@ -726,22 +924,55 @@ static int rank_launch_typed(pp_ctx *ctx, const T *d_x, int64_t ld, const int32_
         todo = d_todo.as<int32_t>();
         ctl = d_ctl.as<int32_t>();
     }
-    // ---- general kernel: everything (no streaming pass), or the cells the streaming pass handed over
+    // ---- general kernel: everything (no streaming pass), or the cells the streaming pass handed over; cells that need
+    //      a full sort are handed on to rank_sort_kernel when 2 n keys fit in shared memory
     const size_t ksz = sizeof(T);
     const size_t n_al = ((size_t)n_genes + 15) & ~(size_t)15;
     const size_t per_cta = 2 * n_al * ksz + 2 * n_al * 2;
     const size_t dyn = ((size_t)n_genes * 2 + 15) & ~(size_t)15;
+    const size_t sort_dyn = 2 * (((size_t)n_genes + 31) & ~(size_t)31) * ksz;
+    const bool sort_small = n_genes <= 4096;  // rank_sort_kernel<T, 8> / <T, 32>
+    const size_t sort_static = sort_small ? sizeof(SortSmem<8>) : sizeof(SortSmem<32>);
+    const bool smem_sort = sort_dyn + sort_static + 1024 <= (size_t)ctx->smem_optin && getenv("PP_NO_SMEM_SORT") == nullptr;
+    DevBuf d_todo2, d_ctl2;
+    if (smem_sort) {
+        PP_CUDA(d_ctl2.alloc(sizeof(int32_t) * 2, st));
+        PP_CUDA(d_todo2.alloc(sizeof(int32_t) * n_slots, st));
+        PP_CUDA(cudaMemsetAsync(d_ctl2.p, 0, sizeof(int32_t) * 2, st));
+    }
     PP_CUDA(cudaFuncSetAttribute(rank_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     // persistent CTAs: exactly as many as are resident at once (a partial second wave would idle half the SMs)
     int per_sm = 1;
     PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_kernel<T>, RANK_THREADS, dyn));
     const int64_t resident = (int64_t)ctx->n_sm * std::max(per_sm, 1);
     const int grid = (int)std::min<int64_t>(n_slots, resident);
-    uint8_t *scratch = (uint8_t *)pp_slab(ctx, SLAB_SORT, per_cta * (size_t)grid);  // sort path only; stream-ordered reuse
-    if (!scratch) return PP_ENOMEM;
+    uint8_t *scratch = nullptr;
+    if (!smem_sort) {  // global ping-pong buffers of rank_kernel's own sort path; stream-ordered reuse
+        scratch = (uint8_t *)pp_slab(ctx, SLAB_SORT, per_cta * (size_t)grid);
+        if (!scratch) return PP_ENOMEM;
+    }
     rank_kernel<T><<<grid, RANK_THREADS, dyn, st>>>(d_x, ld, d_cell_rows, n_slots, d_gene_cols, (int)n_genes, d_rank, rank_ld,
-                                                    scratch, per_cta, d_flags, todo, ctl);
+                                                    scratch, per_cta, d_flags, todo, ctl,
+                                                    smem_sort ? d_todo2.as<int32_t>() : nullptr,
+                                                    smem_sort ? d_ctl2.as<int32_t>() : nullptr);
     PP_CHECK_LAUNCH();
+    if (smem_sort) {
+        int sort_per_sm = 1;
+        if (sort_small) {
+            PP_CUDA(cudaFuncSetAttribute(rank_sort_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_dyn));
+            PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sort_per_sm, rank_sort_kernel<T, 8>, 256, sort_dyn));
+            const int sgrid = (int)std::min<int64_t>(n_slots, (int64_t)ctx->n_sm * std::max(sort_per_sm, 1));
+            rank_sort_kernel<T, 8><<<sgrid, 256, sort_dyn, st>>>(d_x, ld, d_cell_rows, d_gene_cols, (int)n_genes, d_rank, rank_ld, d_flags,
+                                                                 d_todo2.as<int32_t>(), d_ctl2.as<int32_t>());
+        } else {
+            PP_CUDA(cudaFuncSetAttribute(rank_sort_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_dyn));
+            PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sort_per_sm, rank_sort_kernel<T, 32>, 1024, sort_dyn));
+            const int sgrid = (int)std::min<int64_t>(n_slots, (int64_t)ctx->n_sm * std::max(sort_per_sm, 1));
+            rank_sort_kernel<T, 32><<<sgrid, 1024, sort_dyn, st>>>(d_x, ld, d_cell_rows, d_gene_cols, (int)n_genes, d_rank, rank_ld,
+                                                                   d_flags, d_todo2.as<int32_t>(), d_ctl2.as<int32_t>());
+        }
+        PP_CHECK_LAUNCH();
+    }
     return PP_OK;
 }
 

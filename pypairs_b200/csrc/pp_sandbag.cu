@@ -575,7 +575,7 @@ sort_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long lon
         const int64_t i = ib + lane;
         const bool valid = i < hi;
         const uint32_t d = valid ? ((uint32_t)(in[i] >> shift) & 255u) : (256u + lane);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t peers = warp_digit_peers(d, valid);
         if (valid && lane == __ffs(peers) - 1) whist[warp][d] += __popc(peers);
         __syncwarp();
     }
@@ -594,7 +594,7 @@ sort_scatter_kernel(const unsigned long long *__restrict__ in, unsigned long lon
         const bool valid = i < hi;
         const unsigned long long k = valid ? in[i] : 0ull;
         const uint32_t d = valid ? ((uint32_t)(k >> shift) & 255u) : (256u + lane);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t peers = warp_digit_peers(d, valid);
         const uint32_t base = valid ? whist[warp][d] : 0u;
         if (valid) out[base + __popc(peers & ((1u << lane) - 1u))] = k;
         __syncwarp();

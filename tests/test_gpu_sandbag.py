@@ -85,6 +85,31 @@ def test_streaming_rank_path(dtype, n_cols, n_keep):
     assert e.value.code == _ffi().PP_ENAN
 
 
+@pytest.mark.parametrize("dtype,n_genes", [(np.float32, 20000), (np.float32, 1479), (np.float64, 12000), (np.float64, 15000),
+                                             (np.float32, 30000)])
+def test_real_valued_cells_sort_paths(monkeypatch, dtype, n_genes):
+    """Tie-free / real-valued cells: keys sorted in shared memory (rank_sort_kernel) when two key buffers fit, in the
+    global scratch of rank_kernel otherwise (float64 x 15 000, float32 x 30 000) or when PP_NO_SMEM_SORT is set; ties,
+    signed zeros, infinities, a count cell and a few-distinct cell in between."""
+    rng = np.random.default_rng(n_genes)
+    x = rng.lognormal(0.0, 2.0, (70, n_genes)).astype(dtype)
+    x[1] = np.round(x[1], 1)                       # many ties, more than 1024 distinct values
+    x[2, ::2] = -x[2, ::2]
+    x[3, :50] = [0.0, -0.0] * 25
+    x[4, 7], x[4, 8] = np.inf, -np.inf
+    x[5] = rng.poisson(3.0, n_genes)               # count cell (bitmap path)
+    x[6] = rng.integers(0, 300, n_genes) / 7.0     # 300 distinct real values (hash path)
+    x[7] = x[7, 0]                                 # constant
+    rows = np.arange(70, dtype=np.int32)[::-1].copy()
+    cols = np.sort(rng.choice(n_genes, n_genes - n_genes // 10, replace=False)).astype(np.int32)
+    exp = np.stack([np.unique(r, return_inverse=True)[1] for r in x[rows][:, cols]]).astype(np.uint16)
+    got, mx = _ffi().dense_rank(x, rows, cols)
+    assert np.array_equal(got, exp) and mx == exp.max()
+    monkeypatch.setenv("PP_NO_SMEM_SORT", "1")
+    got2, mx2 = _ffi().dense_rank(x, rows, cols)
+    assert np.array_equal(got2, exp) and mx2 == mx
+
+
 def test_large_pageable_input_is_staged():
     """A pageable host matrix of more than 64 MB goes through the threaded staging copy (pp_copy_h2d: chunks of 32 MB
     through two pinned buffers); a pinned one and a device tensor do not -- same markers from all three."""
