@@ -997,6 +997,16 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     ctx->tm = pp_timings();
     ctx->launches = 0;
     ctx->tm.n_units = n_cells;
+    // PP_TRACE=1: host-side time line of the call (ms since entry at every mark), printed at the end
+    const bool tl_on = getenv("PP_TRACE") != nullptr;
+    const auto tl_entry = std::chrono::steady_clock::now();
+    std::string tl_line;
+    auto tl_mark = [&](const char *what) {
+        if (!tl_on) return;
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s=%.3f", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl_entry).count());
+        tl_line += buf;
+    };
     if (n_cells == 0 && !dist) return PP_OK;
     if (n_cells == 0) {  // an empty shard still takes part in the collectives
         PP_CUDA(cudaSetDevice(ctx->device));
@@ -1222,6 +1232,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
     if (want_oh) PP_CUDA(d_oh.alloc(sizeof(int32_t) * out_cnt, st));
     if (want_ot) PP_CUDA(d_ot.alloc(sizeof(int32_t) * out_cnt, st));
     PP_CUDA(cudaEventRecord(ctx->ev[1], ts));  // tables enqueued
+    tl_mark("tables_enqueued");
     bool tables_awaited = false;
 
     ScoreParams P;
@@ -1495,9 +1506,16 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
             }
             return PP_OK;
         };
+        tl_mark("pipeline_start");
         // the first chunks are an eighth, a quarter and a half wave: the device starts after ~1 ms of host work, not ~5
         for (int64_t c0 = 0, nc = 0; c0 < n_cells; c0 += nc, ++i) {
+            if (i == 1) tl_mark("chunk0_enqueued");
             nc = i < 3 ? chunk_cells >> (3 - i) : chunk_cells;
+            // ... and the last ones shrink again (half of what is left, a quarter wave at least): what remains to be done once
+            // the host has gathered its last chunk is that chunk's copy + rank + score -- 12.7 ms after a full wave
+            const int64_t left = n_cells - c0;
+            if (i >= 3 && left <= chunk_cells + chunk_cells / 2)
+                nc = left <= chunk_cells / 4 ? left : std::max(chunk_cells / 4, left / 2);
             nc = std::min({(std::max<int64_t>(nc, 1) + 127) / 128 * 128, chunk_cells, n_cells - c0});
             if (zc_lane && dma_lane) {
                 rc = drain_zc(false);
@@ -1551,6 +1569,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         rc = drain_zc(true);
         if (rc) return rc;
         ctx->tm.h2d_bytes += zc_bytes;
+        tl_mark("chunks_enqueued");
         PP_CUDA(cudaEventRecord(ev_c1, cs));
         if (trace)
             fprintf(stderr, "[pp_cyclone] %d chunks of %lld cells (%d by DMA%s, %d by the zero-copy gather), %d host threads: gather %.1f ms, "
@@ -1571,6 +1590,7 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         PP_CUDA(cudaStreamSynchronize(cs));
         if (zc_lane) PP_CUDA(cudaStreamSynchronize(zs));
         PP_CUDA(cudaStreamSynchronize(st));
+        tl_mark("scored");
         cudaEventElapsedTime(&copy_ms, ev_c0, ev_c1);
         for (size_t j = 0; j + 1 < ev_s.size(); j += 2) {
             float ms = 0.f;
@@ -1615,6 +1635,8 @@ static int cyclone_impl(pp_ctx *ctx, const void *x, int x_dtype, int x_is_device
         if (want_ot) memcpy(out_obs_total, st_ot, ob_bytes);
     }
     }
+    tl_mark("results_on_host");
+    if (tl_on) fprintf(stderr, "pp_cyclone:%s\n", tl_line.c_str());
     if (pipelined) {  // copies overlap compute: h2d = copy-stream span, main = sum of the score launches
         ctx->tm.h2d_ms = copy_ms;
         ctx->tm.main_ms = score_ms;
