@@ -82,7 +82,9 @@ int pp_copy_h2d(pp_ctx *ctx, void *dst, const void *src, size_t bytes, cudaStrea
     for (size_t off = 0; off < bytes; off += CHUNK, ++i) {
         const int b = i & 1;
         const size_t n = std::min(CHUNK, bytes - off);
-        if (i >= 2) PP_CUDA(cudaEventSynchronize(ctx->pin_h2d_done[b]));  // the DMA two chunks ago has drained this buffer
+        // the DMA that last read this buffer (two chunks ago, or in an earlier call) has drained it; an event that was never
+        // recorded is complete
+        PP_CUDA(cudaEventSynchronize(ctx->pin_h2d_done[b]));
         const uint8_t *s = (const uint8_t *)src + off;
         uint8_t *d = (uint8_t *)ctx->pin_h2d[b];
         std::vector<std::thread> pool;
