@@ -195,6 +195,15 @@ def sandbag_matrix_device(g, n, c, kind, seed):
     return x, lab.cpu().numpy().astype(np.int64)
 
 
+def host_memory_allows(extra_bytes):
+    """True if `extra_bytes` more of host memory (summed over the ranks of this host) leave a comfortable margin."""
+    try:
+        import psutil
+        return psutil.virtual_memory().available > 2 * extra_bytes + (16 << 30)
+    except Exception:
+        return True
+
+
 def pinned_copy(x):
     import torch
     t = torch.empty(tuple(x.shape), dtype=x.dtype, pin_memory=True)
@@ -382,7 +391,7 @@ def bench_cyclone(args, ctx, kind="poisson", headline=True):
     assert len(df) == total_cells
     assert np.array_equal(df[keys[0]].values[rank * CYC_CELLS:(rank + 1) * CYC_CELLS], mine[0], equal_nan=True)
     pageable = None
-    if headline and not args.quick:
+    if headline and not args.quick and host_memory_allows(xh.nbytes * world):
         xp = np.array(xh)  # ordinary (pageable) ndarray, what a user holds
         e2e_call(xp)
         pg_ms, _, _ = timed(lambda: e2e_call(xp), min(steps, 3), world)

@@ -242,6 +242,25 @@ def test_default_marker_fixture(golden_dir):
         assert d == json.load(open("/root/reference/pypairs/datasets/leng15_default_markers.json"))
 
 
+def test_first_positions_and_names_index():
+    import pandas as pd
+    from pypairs_b200 import utils
+    from pypairs_b200.cyclone import _names_index
+    rng = np.random.default_rng(3)
+    for n_classes in (1, 3, 16, 17, 300):
+        cls = rng.integers(0, n_classes, 5000)
+        cls = cls[cls != n_classes // 2] if n_classes > 1 else cls      # one class never occurs
+        exp = np.array([np.flatnonzero(cls == k)[0] if (cls == k).any() else len(cls) for k in range(n_classes)])
+        assert np.array_equal(utils.first_positions(cls, n_classes), exp)
+    assert np.array_equal(utils.first_positions(np.empty(0, dtype=np.int64), 3), [0, 0, 0])
+    names = ["cell{}".format(i) for i in range(5000)]
+    a, b = _names_index(names), pd.Index(names)
+    assert a.equals(b) and a.dtype == b.dtype
+    mixed = names[:2500] + [7] + names[2501:]                          # a non-str element: the generic conversion decides
+    assert _names_index(mixed).equals(pd.Index(mixed))
+    assert _names_index(b) is b
+
+
 def test_cell_shard_partition():
     from pypairs_b200._dist import cell_shard
     for n in (0, 1, 7, 64, 1000003):
