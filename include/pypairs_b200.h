@@ -13,7 +13,10 @@
  * Each entry point below names the reference interface it replaces.  Plain C:
  * pointers and sizes only; no torch / C++ types cross the boundary.  One
  * process drives one GPU (one pp_ctx = one device + its streams and scratch);
- * multi-GPU jobs run one process per GPU and pass (shard, n_shards).
+ * multi-GPU jobs run one process per GPU, give every context a communicator
+ * (pp_comm_init) and call the *_dist entry points, which issue the NCCL
+ * collectives themselves; (shard, n_shards) of pp_sandbag remains for callers that
+ * merge the shards' lists on their own.
  *
  * Conventions
  *   - every function returns 0 on success, a PP_E* code otherwise; the message
@@ -21,8 +24,9 @@
  *   - the library never exits or aborts the process;
  *   - `x` may be a host pointer (pageable or pinned) or a device pointer on the
  *     ctx's device (x_is_device != 0); the caller owns every input;
- *   - variable-length outputs are malloc'ed by the library and released with
- *     pp_free(); fixed-size outputs are caller-allocated host buffers;
+ *   - variable-length outputs are allocated by the library (large ones as pinned host
+ *     blocks from an internal pool) and released with pp_free(); fixed-size outputs
+ *     are caller-allocated host buffers (pp_alloc_result gives pinned ones);
  *   - a pp_ctx is not thread-safe; calls block until results are on the host;
  *   - STREAM CONTRACT for device-resident inputs (x_is_device / pp_csr.is_device): the
  *     library reads them on its own non-blocking streams, which do not synchronise with
