@@ -107,8 +107,69 @@ done:
     return out;
 }
 
+/* pair_indices(pairs: sequence of 2-sequences, name_to_idx: dict) -> (bytes of int64[n], bytes of int64[n]):
+ * name_to_idx.get(p[0], -1), name_to_idx.get(p[1], -1) for every pair p, the look-ups of pypairs/tools/cyclone.py:291-300
+ * in one C loop (a marker dict found by sandbag holds millions of pairs). */
+static PyObject *pair_indices(PyObject *self, PyObject *args) {
+    PyObject *pairs, *map, *fast = NULL, *ba = NULL, *bb = NULL, *out = NULL;
+    (void)self;
+    if (!PyArg_ParseTuple(args, "OO!", &pairs, &PyDict_Type, &map)) return NULL;
+    fast = PySequence_Fast(pairs, "pairs must be a sequence");
+    if (!fast) return NULL;
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    ba = PyBytes_FromStringAndSize(NULL, n * (Py_ssize_t)sizeof(int64_t));
+    bb = PyBytes_FromStringAndSize(NULL, n * (Py_ssize_t)sizeof(int64_t));
+    if (!ba || !bb) goto done;
+    {
+        int64_t *a = (int64_t *)PyBytes_AS_STRING(ba), *b = (int64_t *)PyBytes_AS_STRING(bb);
+        for (Py_ssize_t i = 0; i < n; ++i) {
+            PyObject *p = PySequence_Fast_GET_ITEM(fast, i);
+            PyObject *g[2];
+            int own = 0;
+            if (PyTuple_CheckExact(p) && PyTuple_GET_SIZE(p) >= 2) {
+                g[0] = PyTuple_GET_ITEM(p, 0);
+                g[1] = PyTuple_GET_ITEM(p, 1);
+            } else if (PyList_CheckExact(p) && PyList_GET_SIZE(p) >= 2) {
+                g[0] = PyList_GET_ITEM(p, 0);
+                g[1] = PyList_GET_ITEM(p, 1);
+            } else {
+                g[0] = PySequence_GetItem(p, 0);
+                g[1] = g[0] ? PySequence_GetItem(p, 1) : NULL;
+                if (!g[0] || !g[1]) {
+                    Py_XDECREF(g[0]);
+                    goto done;
+                }
+                own = 1;
+            }
+            for (int j = 0; j < 2; ++j) {
+                PyObject *v = PyDict_GetItemWithError(map, g[j]);  /* borrowed */
+                int64_t idx = -1;
+                if (v) {
+                    idx = (int64_t)PyLong_AsLongLong(v);
+                } else if (PyErr_Occurred()) {
+                    if (own) { Py_DECREF(g[0]); Py_DECREF(g[1]); }
+                    goto done;
+                }
+                if (idx == -1 && PyErr_Occurred()) {
+                    if (own) { Py_DECREF(g[0]); Py_DECREF(g[1]); }
+                    goto done;
+                }
+                (j == 0 ? a : b)[i] = idx;
+            }
+            if (own) { Py_DECREF(g[0]); Py_DECREF(g[1]); }
+        }
+    }
+    out = PyTuple_Pack(2, ba, bb);
+done:
+    Py_XDECREF(fast);
+    Py_XDECREF(ba);
+    Py_XDECREF(bb);
+    return out;
+}
+
 static PyMethodDef methods[] = {{"pair_list", pair_list, METH_VARARGS, "list of (names[rows[i]], names[cols[i]]) tuples"},
                                 {"pair_lists", pair_lists, METH_VARARGS, "per-class lists of (names[rows[i]], names[cols[i]])"},
+                                {"pair_indices", pair_indices, METH_VARARGS, "(int64 bytes, int64 bytes) of name_to_idx.get(p[0], -1), .get(p[1], -1)"},
                                 {NULL, NULL, 0, NULL}};
 static struct PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "_pytuples", NULL, -1, methods, NULL, NULL, NULL, NULL};
 PyMODINIT_FUNC PyInit__pytuples(void) { return PyModule_Create(&moduledef); }

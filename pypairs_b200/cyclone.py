@@ -29,9 +29,7 @@ def filter_marker_pairs(marker_pairs, gene_names):
     else:
         per_class = []
         for cat, pairs in marker_pairs.items():
-            per_class.append((cat,
-                              np.fromiter((name_to_idx.get(p[0], -1) for p in pairs), dtype=np.int64, count=len(pairs)),
-                              np.fromiter((name_to_idx.get(p[1], -1) for p in pairs), dtype=np.int64, count=len(pairs))))
+            per_class.append((cat,) + utils.pair_indices(pairs, name_to_idx))
     for cat, ia, ib in per_class:
         ok = (ia >= 0) & (ib >= 0)
         removed += int((~ok).sum())

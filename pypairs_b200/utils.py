@@ -20,6 +20,19 @@ try:  # optional C helper built by __graft_entry__.build(); pure-Python equivale
     from ._pytuples import pair_list as _c_pair_list, pair_lists as _c_pair_lists
 except ImportError:  # pragma: no cover
     _c_pair_list = _c_pair_lists = None
+try:
+    from ._pytuples import pair_indices as _c_pair_indices
+except ImportError:  # pragma: no cover
+    _c_pair_indices = None
+
+
+def pair_indices(pairs, name_to_idx):
+    """(int64[n], int64[n]) = name_to_idx.get(p[0], -1), name_to_idx.get(p[1], -1) for every pair p."""
+    if _c_pair_indices is not None:
+        a, b = _c_pair_indices(pairs, name_to_idx)
+        return np.frombuffer(a, dtype=np.int64), np.frombuffer(b, dtype=np.int64)
+    return (np.fromiter((name_to_idx.get(p[0], -1) for p in pairs), dtype=np.int64, count=len(pairs)),
+            np.fromiter((name_to_idx.get(p[1], -1) for p in pairs), dtype=np.int64, count=len(pairs)))
 
 
 def first_positions(cls, n_classes):
