@@ -41,3 +41,25 @@ pr, used = filter_marker_pairs(mk, big)
 sc, tm = _ffi.cyclone(z, [np.where(used[k])[0] for k in mk], [pr[k] for k in mk], 12, 5, 3)
 print("cyclone general path", float(np.nansum(sc)))
 print(_ffi.perm_table("philox", 5, 1, 100, 30).sum())
+# round 2 kernels: streaming rank (rows >= 8 KB, odd row length, dropped columns), shared-memory sort of real-valued cells,
+# look-up table + upper bitmap words, pinned input read by the zero-copy gather kernel
+import torch  # noqa: E402
+
+n2, g2 = 96, 2601
+lab2 = rng.integers(0, 3, n2)
+w = rng.poisson(rng.gamma(0.5, 6.0, g2)[None, :] + 0.05, (n2, g2)).astype(np.float32)
+w[3] = rng.lognormal(0, 1, g2)
+w[4] = (np.arange(g2) * 7) % 60000
+w[:, 11] = 0
+sizes2 = np.bincount(lab2, minlength=3)
+out = _ffi.sandbag(w, np.argsort(lab2, kind="stable"), sizes2, np.arange(g2), np.ceil(sizes2 * 0.6).astype(np.int64), drop_unexpressed=True)
+print("sandbag streaming rank", len(out[0]), "markers")
+rk, mx = _ffi.dense_rank(w.astype(np.float64), np.arange(n2, dtype=np.int32), np.arange(5, g2 - 3, dtype=np.int32))
+print("dense_rank f64", int(mx))
+yp = torch.from_numpy(rng.poisson(2.0, (700, 6400)).astype(np.float32)).pin_memory()
+names2 = genes + ["X{}".format(i) for i in range(6400 - len(genes))]
+pr2, used2 = filter_marker_pairs(markers, names2)
+for feed in ("zerocopy", "both", "gather"):
+    os.environ["PP_FEED"] = feed
+    sc, tm = _ffi.cyclone(yp.numpy(), [np.where(used2[k])[0] for k in ks], [pr2[k] for k in ks], 10, 5, 5)
+    print("cyclone pinned", feed, float(np.nansum(sc)))
