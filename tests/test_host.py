@@ -33,6 +33,25 @@ def test_library_exports_every_declared_symbol():
             _ffi.sandbag(np.ones((4, 4)), [0, 1], [1, 1], np.arange(4), [1, 1])
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every prototype of include/pypairs_b200.h has as many parameters as the ctypes binding declares."""
+    from pypairs_b200 import _ffi
+    lib = _ffi.load()
+    header = open(os.path.join(ROOT, "include", "pypairs_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(pp_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= len(_ffi.SYMBOLS)
+    checked = 0
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, (name, len(fn.argtypes), n)
+            checked += 1
+    assert checked >= 20
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "pypairs_b200")):
         for f in files:
